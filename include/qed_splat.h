@@ -1,0 +1,205 @@
+/*
+ * qed_splat.h — C-ABI of the B200-native (sm_100a) depth-supervised splat render/train hot path.
+ *
+ * This is the drop-in boundary.  The reference,
+ * leggedrobotics/qed-splatter, reaches this path through ONE Python call,
+ *     gsplat.rendering.rasterization(...)            qed_splatter/model.py:267-288
+ * (import at qed_splatter/model.py:6-9) and through torch autograd for the backward
+ * (loss at qed_splatter/model.py:73-118).  gsplat 1.4.0 implements that call as a chain
+ * of torch custom ops over its CUDA extension `gsplat_cuda`
+ * (gsplat/cuda/_wrapper.py: fully_fused_projection, spherical_harmonics, isect_tiles,
+ * isect_offset_encode, rasterize_to_pixels).  Every entry point below names the gsplat op
+ * (and hence the stage of the model.py:267-288 call) it replaces.
+ *
+ * Conventions
+ *   - plain C: raw device pointers + extents; contiguous row-major tensors; no torch types.
+ *   - every function returns int: 0 = ok, < 0 = QED_ERR_* argument error, > 0 = cudaError_t.
+ *   - never throws, never exits, never synchronises the device, holds no global mutable
+ *     state; all work is enqueued on the `stream` argument (a cudaStream_t).
+ *   - caller owns every buffer.  Outputs are fully overwritten unless stated "accumulates".
+ *   - float = IEEE binary32.  "flat index" = c*N + n into the [C,N,...] arrays.
+ */
+#ifndef QED_SPLAT_H_
+#define QED_SPLAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* qed_stream_t; /* cudaStream_t */
+
+#define QED_OK 0
+#define QED_ERR_BAD_ARG (-1)
+#define QED_ERR_UNSUPPORTED (-2)
+#define QED_ERR_WORKSPACE (-3)
+
+#define QED_ABI_VERSION 1
+
+/* Library / ABI version (QED_ABI_VERSION the .so was built with). */
+int qed_abi_version(void);
+/* Static string for a return code of any function here (cudaGetErrorString for > 0). */
+const char* qed_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a) fused projection + EWA 2-D covariance + SH colour + tile count
+ * replaces: gsplat fully_fused_projection (fwd) + spherical_harmonics (fwd) + the
+ *           `clamp_min(colors + 0.5, 0)`, depth-channel concat and opacity*compensation glue of
+ *           gsplat.rendering.rasterization, + the counting pass of isect_tiles.
+ *           Reached from qed_splatter/model.py:267-288 (args means, quats, scales, opacities,
+ *           colors, viewmats, Ks, width, height, near_plane, far_plane, sh_degree, rasterize_mode).
+ *
+ *  means[N,3] quats[N,4](wxyz) scales[N,3] opacities[N]
+ *  colors_in: sh_degree >= 0 : SH coefficients [N,K,3], uses the first (sh_degree+1)^2 of K
+ *             sh_degree <  0 : colours [N,3] (colors_per_camera=0) or [C,N,3] (=1); ignored when n_color==0
+ *  viewmats[C,4,4] world->camera, Ks[C,3,3]
+ *  n_color in {0,3}: colour channels produced; append_depth in {0,1}: depth appended as last channel.
+ *      D = n_color + append_depth must be 1, 3 or 4   (render_mode D/ED -> 0+1, RGB -> 3+0, RGB+D/ED -> 3+1)
+ *  outputs (all [C,N,...]):
+ *      radii i32, means2d[.,2], depths, conics[.,3], compensations (NULL unless calc_compensations),
+ *      colors_out[.,D], opacities_out (opacity * compensation), tiles_per_gauss i32,
+ *      geom[.,8] packed {mx,my,opacity,depth | conic a,b,c, 0} = the record the compositor gathers.
+ *  Culled entries (radii == 0) get zeros everywhere.
+ */
+int qed_project_fwd(int C, int N, const float* means, const float* quats, const float* scales,
+                    const float* opacities, const float* colors_in, int K, int sh_degree,
+                    int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
+                    float eps2d, float near_plane, float far_plane, float radius_clip,
+                    int calc_compensations, int tile_size, int n_color, int append_depth,
+                    int32_t* radii, float* means2d, float* depths, float* conics, float* compensations,
+                    float* colors_out, float* opacities_out, int32_t* tiles_per_gauss, float* geom,
+                    qed_stream_t stream);
+
+/* Backward of qed_project_fwd.
+ * replaces: gsplat fully_fused_projection (bwd) + spherical_harmonics (bwd) + the glue above.
+ *  v_means2d[C,N,2] v_depths[C,N] v_conics[C,N,3] v_colors[C,N,D] v_opacities_cn[C,N]
+ *      (any may be NULL = zero).  When `packed_grads` != NULL it is the [C*N,12] record written by
+ *      qed_raster_bwd {v_mx,v_my,abs_x,abs_y | v_ca,v_cb,v_cc,v_opacity | v_colour[0..3]} and is
+ *      ADDED to the separate arrays (fused path: pass only packed_grads).
+ *  outputs (overwritten): v_means[N,3] v_quats[N,4] v_scales[N,3] v_opacities[N]
+ *      v_colors_in: same shape as colors_in ([N,K,3], all K rows written, unused ones zero).
+ *  Gradients are summed over the C cameras in a fixed order (deterministic).
+ */
+int qed_project_bwd(int C, int N, const float* means, const float* quats, const float* scales,
+                    const float* opacities, const float* colors_in, int K, int sh_degree,
+                    int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
+                    float eps2d, int calc_compensations, int n_color, int append_depth,
+                    const int32_t* radii, const float* conics, const float* compensations,
+                    const float* v_means2d, const float* v_depths, const float* v_conics,
+                    const float* v_colors, const float* v_opacities_cn, const float* packed_grads,
+                    float* v_means, float* v_quats, float* v_scales, float* v_opacities,
+                    float* v_colors_in, qed_stream_t stream);
+
+/* Pack separate arrays into the compositor's geom record (op-level entry for callers that did not
+ * come through qed_project_fwd, e.g. gsplat-style rasterize_to_pixels(means2d, conics, ..)). */
+int qed_pack_geom(int CN, const float* means2d, const float* conics, const float* opacities,
+                  const float* depths /* may be NULL */, float* geom, qed_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (b) tile intersection: count -> scan -> emit keys -> sort -> per-tile ranges (all integer, bit-exact)
+ * replaces: gsplat isect_tiles (count pass, torch cumsum, fill pass, cub::DeviceRadixSort) and
+ *           isect_offset_encode.  Reached from model.py:267-288 via tile_size=16 (model.py:243,277).
+ */
+
+/* tiles_per_gauss[C*N] from means2d/radii (only needed when projection was not done by qed_project_fwd). */
+int qed_isect_count(int C, int N, const float* means2d, const int32_t* radii, int tile_size, int tile_width,
+                    int tile_height, int32_t* tiles_per_gauss, qed_stream_t stream);
+
+/* Workspace (bytes) for qed_isect_scan over n elements. */
+size_t qed_isect_scan_workspace_bytes(int64_t n);
+/* Inclusive prefix sum cum[i] = sum_{j<=i} tiles_per_gauss[j] (int64); *n_isects_dev = cum[n-1] (int64, device).
+ * Also copies the total to `n_isects_host_pinned` (int64 in pinned host memory) when non-NULL, asynchronously. */
+int qed_isect_scan(int64_t n, const int32_t* tiles_per_gauss, int64_t* cum, int64_t* n_isects_dev,
+                   int64_t* n_isects_host_pinned, void* workspace, size_t workspace_bytes, qed_stream_t stream);
+
+/* Emit unsorted (key,value): key = cam << (32+tile_n_bits) | tile << 32 | bits(depth); value = flat index.
+ * Emission order: ascending flat index, then tile rows, then tile columns (gsplat isect_tiles fill pass). */
+int qed_isect_emit(int C, int N, const float* means2d, const int32_t* radii, const float* depths,
+                   const int64_t* cum, int tile_size, int tile_width, int tile_height, int64_t* isect_ids,
+                   int32_t* flatten_ids, qed_stream_t stream);
+
+/* Stable ascending sort of (int64 key, int32 value) pairs on key bits [0, end_bit).
+ * qed_sort_pairs_cub is the library baseline (what gsplat calls); qed_sort_pairs is this library's own
+ * radix sort.  Both produce identical output.  keys_in/vals_in may be clobbered. */
+size_t qed_sort_pairs_workspace_bytes(int64_t n);
+int qed_sort_pairs(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* keys_out, int32_t* vals_out,
+                   int end_bit, void* workspace, size_t workspace_bytes, qed_stream_t stream);
+size_t qed_sort_pairs_cub_workspace_bytes(int64_t n);
+int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* keys_out, int32_t* vals_out,
+                       int end_bit, void* workspace, size_t workspace_bytes, qed_stream_t stream);
+
+/* isect_offsets[C*tile_height*tile_width] i32: first sorted index of each (camera,tile); empty tiles get
+ * the start of the next non-empty one; tiles after the last entry get n_isects. */
+int qed_tile_ranges(int64_t n_isects, const int64_t* isect_ids_sorted, int C, int tile_width, int tile_height,
+                    int32_t* isect_offsets, qed_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (c) per-tile front-to-back compositing of D channels (RGB + depth)
+ * replaces: gsplat rasterize_to_pixels (fwd) + the ED normalisation tail of rasterization().
+ *  geom[C*N,8], colors[C*N,D] gathered through flatten_ids; backgrounds[C,D] or NULL.
+ *  normalize_last != 0 : last channel /= max(alpha, 1e-10) (render_mode ED / RGB+ED).
+ *  outputs: render[C,H,W,D], alphas[C,H,W], last_ids[C,H,W] i32 (index in sorted list of the last
+ *  composited Gaussian; 0 if none).  For normalize_last the un-normalised last channel is
+ *  recoverable as render*max(alpha,1e-10) (the backward does so).
+ */
+int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
+                   const float* backgrounds, int width, int height, int tile_size, int tile_width,
+                   int tile_height, const int32_t* isect_offsets, const int32_t* flatten_ids,
+                   int normalize_last, float* render, float* alphas, int32_t* last_ids, qed_stream_t stream);
+
+/* (d) compositing backward.
+ * replaces: gsplat rasterize_to_pixels (bwd) incl. absgrad (model.py:284 absgrad=True).
+ *  v_render[C,H,W,D], v_alphas[C,H,W] (NULL = zero): gradients w.r.t. the OUTPUTS of qed_raster_fwd
+ *  (i.e. after ED normalisation when normalize_last).
+ *  packed_grads[C*N,12] ACCUMULATES (caller zero-fills): {v_mx,v_my,|v_mx|,|v_my| | v_conic a,b,c,
+ *  v_opacity | v_colour[0..D-1], 0..}.  Per-Gaussian sums are warp-reduced by shuffles, then one
+ *  atomic add per value per warp.
+ */
+int qed_raster_bwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
+                   const float* backgrounds, int width, int height, int tile_size, int tile_width,
+                   int tile_height, const int32_t* isect_offsets, const int32_t* flatten_ids,
+                   int normalize_last, const float* render, const float* alphas, const int32_t* last_ids,
+                   const float* v_render, const float* v_alphas, float* packed_grads, qed_stream_t stream);
+
+/* Unpack packed_grads into gsplat-shaped gradient tensors (any output may be NULL). */
+int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d, float* v_means2d_abs,
+                     float* v_conics, float* v_colors, float* v_opacities, qed_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (d') qed-splatter loss + its gradient w.r.t. the compositor outputs, fused
+ * replaces: the autograd graph of qed_splatter/model.py:295-306 (background composite, clamp, depth fill)
+ *           and :87-116 (masked depth-L1 * depth_lambda) + the L1 term of splatfacto's RGB loss
+ *           (model.py:83-85), i.e. SURVEY.md §8 rows a11-a13.
+ *  render[C,H,W,4] (RGB + depth; depth normalised iff normalize_last), alphas[C,H,W],
+ *  gt_rgb[C,H,W,3], gt_depth[C,H,W] (<=0 or non-finite = invalid), bg[3].
+ *  loss = rgb_weight * mean|clamp(rgb + (1-a) bg) - gt| + depth_lambda * mean_valid|depth - gt_depth|
+ *  Two launches: a reduction for n_valid / loss sums, then the per-pixel gradient.
+ *  stats_dev[8] (double): {sum|rgb err|, sum|depth err|, n_valid, max depth, 0..}; loss_dev[3] float:
+ *  {total, rgb term, depth term}.  grad_scale multiplies every gradient (1/total views for a sharded batch).
+ */
+int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
+                     const float* gt_rgb, const float* gt_depth, const float* bg, float rgb_weight,
+                     float depth_lambda, float grad_scale, double* stats_dev, float* loss_dev,
+                     float* v_render, float* v_alphas, qed_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * trainer-side kernels
+ */
+/* Fused Adam over a flat arena: param/grad/m/v [n]; per-element lr from lr_by_group[group_of(i)] where the
+ * arena is G contiguous groups with end offsets group_ends[G] (device, int64).  bias corrections from step. */
+int qed_adam_arena(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int G,
+                   const int64_t* group_ends, const float* lr_by_group, float beta1, float beta2, float eps,
+                   int step, qed_stream_t stream);
+
+/* gsplat DefaultStrategy._update_state: for radii>0: grad2d[n] += ||absgrad[c,n] * (W/2*C, H/2*C)||,
+ * count[n] += 1, radii_max[n] = max(radii_max[n], radii[c,n] / max(W,H)).  packed_grads as above. */
+int qed_strategy_update(int C, int N, const float* packed_grads, int use_absgrad, const int32_t* radii,
+                        int width, int height, float* grad2d, float* count, float* radii_max,
+                        qed_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QED_SPLAT_H_ */

@@ -1,0 +1,95 @@
+// Shared helpers for the sm_100a kernels of the splat hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qed_splat.h"
+
+#define QED_CUDA_TRY(expr)                       \
+    do {                                         \
+        cudaError_t _e = (expr);                 \
+        if (_e != cudaSuccess) return (int)_e;   \
+    } while (0)
+
+#define QED_LAUNCH_CHECK()                        \
+    do {                                          \
+        cudaError_t _e = cudaPeekAtLastError();   \
+        if (_e != cudaSuccess) return (int)_e;    \
+    } while (0)
+
+namespace qed {
+
+constexpr float kAlphaThreshold = 1.0f / 255.0f;
+constexpr float kTransmittanceThreshold = 1e-4f;
+constexpr float kMaxAlpha = 0.999f;
+constexpr int kGeomFloats = 8;   // {mx,my,opacity,depth | conic a,b,c,0}
+constexpr int kGradFloats = 12;  // {v_mx,v_my,|v_mx|,|v_my| | v_ca,v_cb,v_cc,v_op | v_colour[4]}
+
+// Individually rounded IEEE ops: the projection mirrors the oracle's pinned op order exactly, so the
+// compiler must never contract a*b+c into an FMA here (these intrinsics are never contracted).
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dvd(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float sqr(float a) { return __fsqrt_rn(a); }
+// a*b + c*d, a*b - c*d with the oracle's rounding (two products, one sum)
+__device__ __forceinline__ float mad2(float a, float b, float c, float d) { return add(mul(a, b), mul(c, d)); }
+__device__ __forceinline__ float msb2(float a, float b, float c, float d) { return sub(mul(a, b), mul(c, d)); }
+// (a*b + c*d) + e*f
+__device__ __forceinline__ float mad3(float a, float b, float c, float d, float e, float f) {
+    return add(add(mul(a, b), mul(c, d)), mul(e, f));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+struct TileBox {
+    int x0, y0, x1, y1;  // [x0,x1) x [y0,y1)
+};
+
+// gsplat isect_tiles: tile_min = floor(mean/ts - r/ts), tile_max = ceil(mean/ts + r/ts), clamped to the grid.
+__device__ __forceinline__ TileBox tile_box(float mx, float my, int radius, float tile_size, int tile_width,
+                                            int tile_height) {
+    float tr = dvd((float)radius, tile_size);
+    float tx = dvd(mx, tile_size);
+    float ty = dvd(my, tile_size);
+    // clamp in float first so the int conversion cannot overflow
+    float fx0 = fminf(fmaxf(floorf(sub(tx, tr)), 0.0f), (float)tile_width);
+    float fy0 = fminf(fmaxf(floorf(sub(ty, tr)), 0.0f), (float)tile_height);
+    float fx1 = fminf(fmaxf(ceilf(add(tx, tr)), 0.0f), (float)tile_width);
+    float fy1 = fminf(fmaxf(ceilf(add(ty, tr)), 0.0f), (float)tile_height);
+    TileBox b;
+    b.x0 = (int)fx0;
+    b.y0 = (int)fy0;
+    b.x1 = (int)fx1;
+    b.y1 = (int)fy1;
+    return b;
+}
+
+}  // namespace qed

@@ -1,0 +1,234 @@
+// Loss + loss-gradient fusion and trainer-side kernels (a14, a16).
+//
+// qed_loss_fwd_bwd replaces the autograd graph the reference builds at qed_splatter/model.py:295-306
+// (background composite, clamp, depth fill with the detached max) and :87-116 (depth-L1 over
+// finite & gt>0 pixels times depth_lambda) plus the L1 term of splatfacto's RGB loss (model.py:83-85).
+// Every camera is one reference step: its depth term is normalised by ITS n_valid, its depth fill uses
+// ITS max; the batch loss is the mean over cameras.
+// qed_adam_arena replaces the 6 torch Adam groups of qed_splatter/config.py:44-68 with one launch over a
+// flat arena; qed_strategy_update is gsplat DefaultStrategy._update_state on the `info` of model.py:267,289-292.
+#include "common.cuh"
+
+namespace qed {
+
+constexpr int kLossThreads = 256;
+
+__device__ __forceinline__ float signf(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
+__device__ __forceinline__ bool finitef(float x) { return fabsf(x) <= 3.402823466e38f; }
+
+// pass 1: per camera n_valid and max depth (depth channel >= 0, so int ordering of the bits works)
+__global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, const float4* __restrict__ render, const float* __restrict__ alphas,
+                                                                 const float* __restrict__ gt_depth, double* __restrict__ stats) {
+    const int cam = blockIdx.y;
+    float maxd = 0.0f;
+    int has_neg = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = render[cam * HW + i].w;
+        if (d > maxd) maxd = d;
+        has_neg |= (d != d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats + cam * 8 + 3), __float_as_int(maxd));
+    (void)has_neg;
+    (void)alphas;
+    (void)gt_depth;
+}
+
+// pass 2: gradients + loss sums
+__global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int C, const float4* __restrict__ render, const float* __restrict__ alphas,
+                                                                const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth,
+                                                                const float* __restrict__ bg, float rgb_weight, float depth_lambda, float grad_scale,
+                                                                double* __restrict__ stats, float4* __restrict__ v_render, float* __restrict__ v_alphas,
+                                                                int phase) {
+    // phase 0: count n_valid + loss sums (needs max depth); phase 1: gradients (needs n_valid)
+    const int cam = blockIdx.y;
+    const float maxd = __int_as_float(*reinterpret_cast<const int*>(stats + cam * 8 + 3));
+    const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+    double s_rgb = 0.0, s_d = 0.0, s_n = 0.0;
+    float inv_nvalid = 0.0f;
+    if (phase == 1) {
+        const double nv = stats[cam * 8 + 2];
+        inv_nvalid = nv > 0.0 ? (float)(1.0 / nv) : 0.0f;
+    }
+    const float g_rgb = rgb_weight * grad_scale / ((float)C * (float)HW * 3.0f);
+    const float g_d = depth_lambda * grad_scale * inv_nvalid / (float)C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = cam * HW + i;
+        const float4 r = render[pix];
+        const float a = alphas[pix];
+        const float om = 1.0f - a;
+        const float pre0 = r.x + om * b0, pre1 = r.y + om * b1, pre2 = r.z + om * b2;
+        const float c0 = fminf(fmaxf(pre0, 0.0f), 1.0f), c1 = fminf(fmaxf(pre1, 0.0f), 1.0f), c2 = fminf(fmaxf(pre2, 0.0f), 1.0f);
+        const float e0 = c0 - gt_rgb[pix * 3 + 0], e1 = c1 - gt_rgb[pix * 3 + 1], e2 = c2 - gt_rgb[pix * 3 + 2];
+        const float gd = gt_depth[pix];
+        const float d = (a > 0.0f) ? r.w : maxd;
+        const bool valid = finitef(d) && finitef(gd) && (gd > 0.0f);
+        if (phase == 0) {
+            s_rgb += (double)(fabsf(e0) + fabsf(e1) + fabsf(e2));
+            if (valid) {
+                s_d += (double)fabsf(d - gd);
+                s_n += 1.0;
+            }
+        } else {
+            float4 v;
+            v.x = (pre0 >= 0.0f && pre0 <= 1.0f) ? g_rgb * signf(e0) : 0.0f;
+            v.y = (pre1 >= 0.0f && pre1 <= 1.0f) ? g_rgb * signf(e1) : 0.0f;
+            v.z = (pre2 >= 0.0f && pre2 <= 1.0f) ? g_rgb * signf(e2) : 0.0f;
+            v.w = (valid && a > 0.0f) ? g_d * signf(d - gd) : 0.0f;
+            v_render[pix] = v;
+            v_alphas[pix] = -(v.x * b0 + v.y * b1 + v.z * b2);
+        }
+    }
+    if (phase == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s_rgb += __shfl_xor_sync(0xffffffffu, s_rgb, o);
+            s_d += __shfl_xor_sync(0xffffffffu, s_d, o);
+            s_n += __shfl_xor_sync(0xffffffffu, s_n, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(stats + cam * 8 + 0, s_rgb);
+            atomicAdd(stats + cam * 8 + 1, s_d);
+            atomicAdd(stats + cam * 8 + 2, s_n);
+        }
+    }
+}
+
+__global__ void loss_finalize_kernel(int C, int64_t HW, float rgb_weight, float depth_lambda, double* __restrict__ stats, float* __restrict__ loss) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double lr = 0.0, ld = 0.0;
+    for (int c = 0; c < C; ++c) {
+        double* s = stats + c * 8;
+        lr += s[0] / ((double)HW * 3.0);
+        ld += s[2] > 0.0 ? s[1] / s[2] : 0.0;
+        float maxd = __int_as_float(*reinterpret_cast<const int*>(s + 3));
+        s[4] = (double)maxd;
+    }
+    lr = rgb_weight * lr / C;
+    ld = depth_lambda * ld / C;
+    loss[0] = (float)(lr + ld);
+    loss[1] = (float)lr;
+    loss[2] = (float)ld;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_arena_kernel(int64_t n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+                                  int G, const int64_t* __restrict__ group_ends, const float* __restrict__ lr_by_group, float beta1, float beta2,
+                                  float eps, float bias1, float bias2_sqrt) {
+    __shared__ int64_t s_ends[16];
+    __shared__ float s_lr[16];
+    if (threadIdx.x < G) {
+        s_ends[threadIdx.x] = group_ends[threadIdx.x];
+        s_lr[threadIdx.x] = lr_by_group[threadIdx.x];
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int g = 0;
+        while (g < G - 1 && i >= s_ends[g]) ++g;
+        const float gr = grad[i];
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bias2_sqrt + eps;
+        param[i] -= (s_lr[g] / bias1) * (mi / denom);
+    }
+}
+
+__global__ void strategy_update_kernel(int C, int N, const float4* __restrict__ packed, int use_absgrad, const int32_t* __restrict__ radii,
+                                       float sx, float sy, float inv_max_wh, float* __restrict__ grad2d, float* __restrict__ count,
+                                       float* __restrict__ radii_max) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float g = 0.0f, cnt = 0.0f, rm = radii_max ? radii_max[n] : 0.0f;
+    for (int c = 0; c < C; ++c) {
+        const int64_t idx = (int64_t)c * N + n;
+        const int r = radii[idx];
+        if (r > 0) {
+            const float4 r0 = packed[idx * 3];
+            const float gx = (use_absgrad ? r0.z : r0.x) * sx, gy = (use_absgrad ? r0.w : r0.y) * sy;
+            g += sqrtf(gx * gx + gy * gy);
+            cnt += 1.0f;
+            rm = fmaxf(rm, (float)r * inv_max_wh);
+        }
+    }
+    if (cnt > 0.0f) {
+        grad2d[n] += g;
+        count[n] += cnt;
+        if (radii_max) radii_max[n] = rm;
+    }
+}
+
+}  // namespace qed
+
+using namespace qed;
+
+extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
+                                const float* gt_rgb, const float* gt_depth, const float* bg, float rgb_weight,
+                                float depth_lambda, float grad_scale, double* stats_dev, float* loss_dev,
+                                float* v_render, float* v_alphas, qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (C <= 0 || width <= 0 || height <= 0) return QED_ERR_BAD_ARG;
+    if (!render || !alphas || !gt_rgb || !gt_depth || !bg || !stats_dev || !loss_dev || !v_render || !v_alphas) return QED_ERR_BAD_ARG;
+    if (C > 65535) return QED_ERR_UNSUPPORTED;
+    const int64_t HW = (int64_t)width * height;
+    QED_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, (size_t)C * 8 * sizeof(double), stream));
+    int bx = (int)((HW + kLossThreads * 4 - 1) / (kLossThreads * 4));
+    if (bx > 148 * 8) bx = 148 * 8;
+    dim3 grid(bx, C);
+    loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, stats_dev);
+    QED_LAUNCH_CHECK();
+    for (int phase = 0; phase < 2; ++phase) {
+        loss_grad_kernel<<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg, rgb_weight,
+                                                            depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render), v_alphas, phase);
+        QED_LAUNCH_CHECK();
+    }
+    loss_finalize_kernel<<<1, 32, 0, stream>>>(C, HW, rgb_weight, depth_lambda, stats_dev, loss_dev);
+    QED_LAUNCH_CHECK();
+    return QED_OK;
+}
+
+extern "C" int qed_adam_arena(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int G,
+                              const int64_t* group_ends, const float* lr_by_group, float beta1, float beta2, float eps,
+                              int step, qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || G <= 0 || G > 16 || step < 1) return QED_ERR_BAD_ARG;
+    if (n == 0) return QED_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !group_ends || !lr_by_group) return QED_ERR_BAD_ARG;
+    const float bias1 = 1.0f - powf(beta1, (float)step);
+    const float bias2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    adam_arena_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group, beta1, beta2, eps, bias1,
+                                                            bias2_sqrt);
+    QED_LAUNCH_CHECK();
+    return QED_OK;
+}
+
+extern "C" int qed_strategy_update(int C, int N, const float* packed_grads, int use_absgrad, const int32_t* radii,
+                                   int width, int height, float* grad2d, float* count, float* radii_max,
+                                   qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (C < 0 || N < 0 || width <= 0 || height <= 0) return QED_ERR_BAD_ARG;
+    if (C == 0 || N == 0) return QED_OK;
+    if (!packed_grads || !radii || !grad2d || !count) return QED_ERR_BAD_ARG;
+    const float sx = (float)width / 2.0f * (float)C, sy = (float)height / 2.0f * (float)C;
+    const float inv = 1.0f / (float)(width > height ? width : height);
+    strategy_update_kernel<<<(N + 255) / 256, 256, 0, stream>>>(C, N, reinterpret_cast<const float4*>(packed_grads), use_absgrad, radii, sx, sy, inv,
+                                                               grad2d, count, radii_max);
+    QED_LAUNCH_CHECK();
+    return QED_OK;
+}
+
+extern "C" int qed_abi_version(void) { return QED_ABI_VERSION; }
+
+extern "C" const char* qed_error_string(int code) {
+    switch (code) {
+        case QED_OK: return "ok";
+        case QED_ERR_BAD_ARG: return "qed: bad argument (null pointer, negative extent or inconsistent shape)";
+        case QED_ERR_UNSUPPORTED: return "qed: unsupported configuration (tile_size != 16, D not in {1,3,4}, sh_degree > 3, or extent too large)";
+        case QED_ERR_WORKSPACE: return "qed: workspace too small";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "qed: unknown error";
+    }
+}

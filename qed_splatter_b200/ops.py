@@ -1,0 +1,314 @@
+"""Op-level host wrappers over the C-ABI (one per stage of the hot path) with torch autograd.
+
+Names and argument meaning follow gsplat 1.4.0's `gsplat/cuda/_wrapper.py`, which is what
+`gsplat.rendering.rasterization` — the call at `/root/reference/qed_splatter/model.py:267-288` — is
+built from: `fully_fused_projection`, `isect_tiles`, `isect_offset_encode`, `rasterize_to_pixels`.
+`project_gaussians` is the fused projection + SH stage this library actually runs.
+
+torch is used for device memory, streams and autograd bookkeeping only; every computation is a kernel
+in `libqedsplat.so`.  CUDA tensors only — CPU tensors raise (no fallback).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, current_stream, ptr
+
+GRAD_FLOATS = 12
+GEOM_FLOATS = 8
+_SORT_IMPL = "own"  # "own" | "cub" (library baseline, same output)
+
+
+def set_sort_impl(name: str) -> str:
+    """Select the radix sort used by isect_tiles: "own" (this library's kernels) or "cub" (baseline)."""
+    global _SORT_IMPL
+    assert name in ("own", "cub")
+    old, _SORT_IMPL = _SORT_IMPL, name
+    return old
+
+
+def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def tile_grid(width: int, height: int, tile_size: int) -> Tuple[int, int]:
+    return math.ceil(width / tile_size), math.ceil(height / tile_size)
+
+
+# --------------------------------------------------------------------------------------------- #
+# (a) fused projection + SH
+# --------------------------------------------------------------------------------------------- #
+class _ProjectGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, opacities, colors, viewmats, Ks, width, height, eps2d, near_plane,
+                far_plane, radius_clip, calc_compensations, sh_degree, n_color, append_depth, tile_size):
+        lib = _lib.load()
+        _lib.require_cuda(means, quats, scales, opacities, colors, viewmats, Ks)
+        means, quats, scales = _f32c(means), _f32c(quats), _f32c(scales)
+        opacities, colors = _f32c(opacities), _f32c(colors)
+        viewmats, Ks = _f32c(viewmats), _f32c(Ks)
+        N, C = means.shape[0], viewmats.shape[0]
+        D = n_color + append_depth
+        dev = means.device
+        K = 0
+        per_cam = 0
+        if n_color:
+            if sh_degree >= 0:
+                assert colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3, "SH coeffs must be [N,K,3]"
+                K = colors.shape[1]
+                assert (sh_degree + 1) ** 2 <= K, "sh_degree too large for the coefficient tensor"
+            else:
+                assert colors.shape[-1] == 3, "only 3 colour channels are supported on this path"
+                per_cam = 1 if colors.dim() == 3 else 0
+                if per_cam:
+                    assert colors.shape[:2] == (C, N)
+        radii = torch.empty(C, N, dtype=torch.int32, device=dev)
+        means2d = torch.empty(C, N, 2, device=dev)
+        depths = torch.empty(C, N, device=dev)
+        conics = torch.empty(C, N, 3, device=dev)
+        comps = torch.empty(C, N, device=dev) if calc_compensations else None
+        colors_out = torch.empty(C, N, D, device=dev)
+        opac_out = torch.empty(C, N, device=dev)
+        tiles = torch.empty(C, N, dtype=torch.int32, device=dev)
+        geom = torch.empty(C, N, GEOM_FLOATS, device=dev)
+        check(lib.qed_project_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors) if n_color else None,
+                                  K, sh_degree, per_cam, ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane,
+                                  far_plane, radius_clip, int(calc_compensations), tile_size, n_color, append_depth,
+                                  ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(colors_out),
+                                  ptr(opac_out), ptr(tiles), ptr(geom), current_stream()), "qed_project_fwd")
+        ctx.save_for_backward(means, quats, scales, opacities, colors, viewmats, Ks, radii, conics, comps)
+        ctx.cfg = (width, height, eps2d, calc_compensations, sh_degree, n_color, append_depth, K, per_cam)
+        ctx.mark_non_differentiable(radii, tiles, geom)
+        if comps is None:
+            comps_out = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(comps_out)
+        else:
+            comps_out = comps
+        return radii, means2d, depths, conics, comps_out, colors_out, opac_out, tiles, geom
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_colors, v_opac, _v_tiles, _v_geom):
+        lib = _lib.load()
+        means, quats, scales, opacities, colors, viewmats, Ks, radii, conics, comps = ctx.saved_tensors
+        width, height, eps2d, calc_comp, sh_degree, n_color, append_depth, K, per_cam = ctx.cfg
+        N, C = means.shape[0], viewmats.shape[0]
+        dev = means.device
+        if calc_comp and v_comps is not None and v_comps.numel() and bool((v_comps != 0).any()):
+            raise NotImplementedError("gradient through `compensations` itself is not on the reference path")
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        v_opacities = torch.empty_like(opacities) if opacities is not None else None
+        v_colors_in = torch.empty_like(colors) if n_color else None
+        check(lib.qed_project_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors) if n_color else None,
+                                  K, sh_degree, per_cam, ptr(viewmats), ptr(Ks), width, height, eps2d, int(calc_comp),
+                                  n_color, append_depth, ptr(radii), ptr(conics), ptr(comps),
+                                  ptr(_f32c(v_means2d)), ptr(_f32c(v_depths)), ptr(_f32c(v_conics)), ptr(_f32c(v_colors)),
+                                  ptr(_f32c(v_opac)), None, ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_opacities),
+                                  ptr(v_colors_in), current_stream()), "qed_project_bwd")
+        return (v_means, v_quats, v_scales, v_opacities, v_colors_in, None, None) + (None,) * 11
+
+
+def project_gaussians(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, colors: Optional[Tensor],
+                      viewmats: Tensor, Ks: Tensor, width: int, height: int, eps2d: float = 0.3,
+                      near_plane: float = 0.01, far_plane: float = 1e10, radius_clip: float = 0.0,
+                      calc_compensations: bool = False, sh_degree: Optional[int] = None, n_color: int = 3,
+                      append_depth: bool = True, tile_size: int = 16):
+    """Fused fully_fused_projection + spherical_harmonics (+ clamp_min(c+0.5), depth concat, opacity*comp).
+
+    -> radii[C,N] i32, means2d[C,N,2], depths[C,N], conics[C,N,3], compensations[C,N]|None,
+       colors[C,N,D], opacities[C,N], tiles_per_gauss[C,N] i32, geom[C,N,8]
+    """
+    if colors is None:
+        colors = torch.empty(0, device=means.device)
+        n_color = 0
+    out = _ProjectGaussians.apply(means, quats, scales, opacities, colors, viewmats, Ks, int(width), int(height),
+                                  float(eps2d), float(near_plane), float(far_plane), float(radius_clip),
+                                  bool(calc_compensations), -1 if sh_degree is None else int(sh_degree), int(n_color),
+                                  int(bool(append_depth)), int(tile_size))
+    radii, means2d, depths, conics, comps, colors_out, opac_out, tiles, geom = out
+    return radii, means2d, depths, conics, (comps if calc_compensations else None), colors_out, opac_out, tiles, geom
+
+
+def fully_fused_projection(means: Tensor, covars, quats: Tensor, scales: Tensor, viewmats: Tensor, Ks: Tensor,
+                           width: int, height: int, eps2d: float = 0.3, near_plane: float = 0.01,
+                           far_plane: float = 1e10, radius_clip: float = 0.0, packed: bool = False,
+                           sparse_grad: bool = False, calc_compensations: bool = False):
+    """gsplat `fully_fused_projection` surface -> (radii, means2d, depths, conics, compensations)."""
+    if covars is not None or packed or sparse_grad:
+        raise NotImplementedError("covars / packed / sparse_grad are not reachable from qed_splatter/model.py:267-288")
+    opac = torch.ones(means.shape[0], device=means.device)
+    radii, means2d, depths, conics, comps, _, _, _, _ = project_gaussians(
+        means, quats, scales, opac, None, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+        calc_compensations, None, 0, True)
+    return radii, means2d, depths, conics, comps
+
+
+# --------------------------------------------------------------------------------------------- #
+# (b) tile intersection
+# --------------------------------------------------------------------------------------------- #
+@torch.no_grad()
+def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+                sort: bool = True, tiles_per_gauss: Optional[Tensor] = None):
+    """gsplat `isect_tiles` -> tiles_per_gauss[C,N] i32, isect_ids[M] i64, flatten_ids[M] i32 (sorted)."""
+    lib = _lib.load()
+    _lib.require_cuda(means2d, radii, depths)
+    means2d, depths = _f32c(means2d.detach()), _f32c(depths.detach())
+    radii = radii.contiguous()
+    assert radii.dtype == torch.int32
+    C, N = radii.shape
+    dev = means2d.device
+    stream = current_stream()
+    if tiles_per_gauss is None:
+        tiles_per_gauss = torch.empty(C, N, dtype=torch.int32, device=dev)
+        check(lib.qed_isect_count(C, N, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height,
+                                  ptr(tiles_per_gauss), stream), "qed_isect_count")
+    CN = C * N
+    cum = torch.empty(CN, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws_bytes = lib.qed_isect_scan_workspace_bytes(CN)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.qed_isect_scan(CN, ptr(tiles_per_gauss), ptr(cum), ptr(total), None, ptr(ws), ws_bytes, stream), "qed_isect_scan")
+    n_isects = int(total.item())  # the one host sync of the forward (gsplat has the same one)
+    isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+    flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    if n_isects:
+        check(lib.qed_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(cum), tile_size, tile_width,
+                                 tile_height, ptr(isect_ids), ptr(flatten_ids), stream), "qed_isect_emit")
+        if sort:
+            tile_n_bits = (tile_width * tile_height).bit_length()
+            cam_n_bits = C.bit_length()
+            isect_ids, flatten_ids = sort_pairs(isect_ids, flatten_ids, 32 + tile_n_bits + cam_n_bits)
+    return tiles_per_gauss, isect_ids, flatten_ids
+
+
+@torch.no_grad()
+def sort_pairs(keys: Tensor, vals: Tensor, end_bit: int = 64, impl: Optional[str] = None):
+    """Stable ascending radix sort of (int64 key, int32 value) pairs on key bits [0, end_bit)."""
+    lib = _lib.load()
+    _lib.require_cuda(keys, vals)
+    impl = impl or _SORT_IMPL
+    n = keys.numel()
+    keys_out = torch.empty_like(keys)
+    vals_out = torch.empty_like(vals)
+    if n == 0:
+        return keys_out, vals_out
+    if impl == "cub":
+        ws_bytes = lib.qed_sort_pairs_cub_workspace_bytes(n)
+        fn, name = lib.qed_sort_pairs_cub, "qed_sort_pairs_cub"
+    else:
+        ws_bytes = lib.qed_sort_pairs_workspace_bytes(n)
+        fn, name = lib.qed_sort_pairs, "qed_sort_pairs"
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    check(fn(n, ptr(keys), ptr(vals), ptr(keys_out), ptr(vals_out), end_bit, ptr(ws), ws_bytes, current_stream()), name)
+    return keys_out, vals_out
+
+
+@torch.no_grad()
+def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height: int) -> Tensor:
+    """gsplat `isect_offset_encode` -> isect_offsets[C,tile_height,tile_width] i32."""
+    lib = _lib.load()
+    _lib.require_cuda(isect_ids)
+    offsets = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=isect_ids.device)
+    check(lib.qed_tile_ranges(isect_ids.numel(), ptr(isect_ids.contiguous()), C, tile_width, tile_height, ptr(offsets),
+                              current_stream()), "qed_tile_ranges")
+    return offsets
+
+
+# --------------------------------------------------------------------------------------------- #
+# (c)/(d) compositing
+# --------------------------------------------------------------------------------------------- #
+class _RasterizeToPixels(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, opacities, backgrounds, geom, width, height, tile_size, isect_offsets,
+                flatten_ids, absgrad, normalize_last):
+        lib = _lib.load()
+        _lib.require_cuda(means2d, conics, colors, opacities, isect_offsets, flatten_ids)
+        C, N = opacities.shape
+        D = colors.shape[-1]
+        dev = means2d.device
+        colors = _f32c(colors)
+        backgrounds = _f32c(backgrounds)
+        if geom is None:
+            geom = torch.empty(C, N, GEOM_FLOATS, device=dev)
+            check(lib.qed_pack_geom(C * N, ptr(_f32c(means2d)), ptr(_f32c(conics)), ptr(_f32c(opacities)), None, ptr(geom),
+                                    current_stream()), "qed_pack_geom")
+        tile_height, tile_width = isect_offsets.shape[1:]
+        n_isects = flatten_ids.numel()
+        render = torch.empty(C, height, width, D, device=dev)
+        alphas = torch.empty(C, height, width, 1, device=dev)
+        last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
+        check(lib.qed_raster_fwd(C, N, n_isects, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile_size,
+                                 tile_width, tile_height, ptr(isect_offsets), ptr(flatten_ids), int(normalize_last),
+                                 ptr(render), ptr(alphas), ptr(last_ids), current_stream()), "qed_raster_fwd")
+        ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, geom, isect_offsets, flatten_ids, render,
+                              alphas, last_ids)
+        ctx.cfg = (width, height, tile_size, absgrad, normalize_last)
+        ctx.mark_non_differentiable(last_ids)
+        return render, alphas, last_ids
+
+    @staticmethod
+    def backward(ctx, v_render, v_alphas, _v_last):
+        lib = _lib.load()
+        means2d, conics, colors, opacities, backgrounds, geom, isect_offsets, flatten_ids, render, alphas, last_ids = ctx.saved_tensors
+        width, height, tile_size, absgrad, normalize_last = ctx.cfg
+        C, N = opacities.shape
+        D = colors.shape[-1]
+        dev = means2d.device
+        tile_height, tile_width = isect_offsets.shape[1:]
+        packed = torch.zeros(C * N, GRAD_FLOATS, device=dev)
+        v_render = _f32c(v_render) if v_render is not None else torch.zeros_like(render)
+        check(lib.qed_raster_bwd(C, N, flatten_ids.numel(), D, ptr(geom), ptr(colors), ptr(backgrounds), width, height,
+                                 tile_size, tile_width, tile_height, ptr(isect_offsets), ptr(flatten_ids),
+                                 int(normalize_last), ptr(render), ptr(alphas), ptr(last_ids), ptr(v_render),
+                                 ptr(_f32c(v_alphas)), ptr(packed), current_stream()), "qed_raster_bwd")
+        v_means2d = torch.empty(C, N, 2, device=dev)
+        v_abs = torch.empty(C, N, 2, device=dev) if absgrad else None
+        v_conics = torch.empty(C, N, 3, device=dev)
+        v_colors = torch.empty(C, N, D, device=dev)
+        v_opac = torch.empty(C, N, device=dev)
+        check(lib.qed_unpack_grads(C * N, D, ptr(packed), ptr(v_means2d), ptr(v_abs), ptr(v_conics), ptr(v_colors),
+                                   ptr(v_opac), current_stream()), "qed_unpack_grads")
+        if absgrad:
+            means2d.absgrad = v_abs  # side channel read by gsplat's DefaultStrategy (model.py:284 absgrad=True)
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[4]:
+            g = v_render
+            if normalize_last:
+                g = g.clone()
+                g[..., -1:] = g[..., -1:] / alphas.clamp(min=1e-10)
+            v_bg = (g * (1.0 - alphas)).sum(dim=(1, 2))
+        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None
+
+
+def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
+                        image_height: int, tile_size: int, isect_offsets: Tensor, flatten_ids: Tensor,
+                        backgrounds: Optional[Tensor] = None, packed: bool = False, absgrad: bool = False,
+                        geom: Optional[Tensor] = None, normalize_last: bool = False, return_last_ids: bool = False):
+    """gsplat `rasterize_to_pixels` -> (render[C,H,W,D], alphas[C,H,W,1]) (+ last_ids when asked)."""
+    if packed:
+        raise NotImplementedError("packed mode is not reachable from qed_splatter/model.py:267-288")
+    if colors.shape[-1] not in (1, 3, 4):
+        raise NotImplementedError("channel count must be 1, 3 or 4 (D, RGB, RGB+D) on this path")
+    if tile_size != 16:
+        raise NotImplementedError("tile_size is 16 on this path (qed_splatter/model.py:243)")
+    render, alphas, last_ids = _RasterizeToPixels.apply(
+        means2d, conics, colors, opacities, backgrounds, geom, int(image_width), int(image_height), int(tile_size),
+        isect_offsets.contiguous(), flatten_ids.contiguous(), bool(absgrad), bool(normalize_last))
+    if return_last_ids:
+        return render, alphas, last_ids
+    return render, alphas
+
+
+def set_raster_cull(enabled: bool) -> bool:
+    """Test hook: disable/enable the exact warp-level culling in the compositor (results are identical)."""
+    return bool(_lib.load().qed_debug_set_raster_cull(int(enabled)))

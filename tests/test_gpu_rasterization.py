@@ -1,0 +1,110 @@
+"""-m gpu: end-to-end parity of `rasterization` (the reference-facing call, model.py:267-288) vs the oracle."""
+import pytest
+import torch
+
+import oracle
+from qed_splatter_b200 import rasterization
+from qed_splatter_b200.scenes import scene_s0
+from helpers import assert_close_frac, scene_args
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(s, cuda, mode, sh_degree=3, rasterize_mode="classic", backgrounds=None, with_grad=True, seed=0):
+    a = scene_args(s)
+    leaves_o = {k: a[k].clone().requires_grad_(with_grad) for k in ("means", "quats", "scales", "opacities", "colors")}
+    ro, ao, io = oracle.rasterization(**leaves_o, viewmats=s.viewmats, Ks=s.Ks, width=s.width, height=s.height,
+                                      render_mode=mode, sh_degree=sh_degree, rasterize_mode=rasterize_mode,
+                                      backgrounds=backgrounds, absgrad=True)
+    leaves_g = {k: a[k].to(cuda).requires_grad_(with_grad) for k in leaves_o}
+    rg, ag, ig = rasterization(**leaves_g, viewmats=s.viewmats.to(cuda), Ks=s.Ks.to(cuda), width=s.width, height=s.height,
+                               tile_size=16, packed=False, near_plane=0.01, far_plane=1e10, render_mode=mode,
+                               sh_degree=sh_degree, sparse_grad=False, absgrad=True, rasterize_mode=rasterize_mode,
+                               backgrounds=None if backgrounds is None else backgrounds.to(cuda))
+    return (ro, ao, io, leaves_o), (rg, ag, ig, leaves_g)
+
+
+@pytest.mark.parametrize("mode", ["RGB", "D", "ED", "RGB+D", "RGB+ED"])
+def test_forward_modes(cuda, mode):
+    s = scene_s0(N=4000, C=2, size=128)
+    (ro, ao, io, _), (rg, ag, ig, _) = _run_both(s, cuda, mode, with_grad=False)
+    assert rg.shape == ro.shape and ag.shape == ao.shape
+    # integer stages bit-exact end to end
+    for k in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"):
+        assert torch.equal(ig[k].cpu(), io[k]), k
+    assert ig["isect_ids"].dtype == torch.int64 and ig["flatten_ids"].dtype == torch.int32 and ig["radii"].dtype == torch.int32
+    assert_close_frac(rg, ro, 1e-4, 1e-4, 2e-3, f"render {mode}")
+    assert_close_frac(ag, ao, 1e-4, 1e-4, 2e-3, f"alpha {mode}")
+
+
+def test_config0_full_parity(cuda):
+    """BASELINE.json configs[0]: 10k Gaussians, 8 cameras 256x256, RGB+ED fwd+bwd with depth-L1 + RGB-L1."""
+    s = scene_s0()
+    (ro, ao, io, lo), (rg, ag, ig, lg) = _run_both(s, cuda, "RGB+ED")
+    for k in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"):
+        assert torch.equal(ig[k].cpu(), io[k]), k
+    assert_close_frac(rg, ro, 1e-4, 1e-4, 1e-3, "render")
+    assert_close_frac(ag, ao, 1e-4, 1e-4, 1e-3, "alpha")
+    bg = torch.tensor([0.2, 0.5, 0.8])
+
+    def loss_fn(render, alpha, gt_rgb, gt_depth, bgc):
+        rgb, depth = oracle.composite_and_fill(render, alpha, bgc)
+        return oracle.rgb_l1_loss(rgb, gt_rgb) + oracle.depth_l1_loss(depth, gt_depth, 0.2)
+
+    io["means2d"].retain_grad()
+    loss_fn(ro, ao, s.gt_rgb, s.gt_depth, bg).backward()
+    ig["means2d"].retain_grad()
+    loss_fn(rg, ag, s.gt_rgb.to(cuda), s.gt_depth.to(cuda), bg.to(cuda)).backward()
+    for k in lo:
+        scale = float(lo[k].grad.abs().mean()) + 1e-12
+        assert_close_frac(lg[k].grad, lo[k].grad, 1e-3, 1e-3 * scale, 5e-3, f"v_{k}")
+    # info contract used by the reference (model.py:289-292) and by gsplat's DefaultStrategy
+    assert ig["means2d"].grad is not None and ig["means2d"].absgrad.shape == (s.C, s.N, 2)
+    scale = float(io["means2d"].grad.abs().mean()) + 1e-12
+    assert_close_frac(ig["means2d"].grad, io["means2d"].grad, 1e-3, 1e-3 * scale, 5e-3, "means2d.grad")
+    assert bool((ig["means2d"].absgrad >= ig["means2d"].grad.abs() - 1e-6).all())
+    assert ig["radii"][0].shape == (s.N,) and ig["n_cameras"] == s.C and ig["width"] == s.width
+
+
+def test_antialiased_and_background_grads(cuda):
+    s = scene_s0(N=3000, C=2, size=96)
+    bgs = torch.rand(s.C, 3, generator=torch.Generator().manual_seed(2))
+    (ro, ao, io, lo), (rg, ag, ig, lg) = _run_both(s, cuda, "RGB+D", sh_degree=2, rasterize_mode="antialiased", backgrounds=bgs)
+    assert_close_frac(rg, ro, 1e-4, 1e-4, 2e-3, "render")
+    gen = torch.Generator().manual_seed(4)
+    vr, va = torch.randn(ro.shape, generator=gen), torch.randn(ao.shape, generator=gen)
+    ((ro * vr).sum() + (ao * va).sum()).backward()
+    ((rg * vr.to(cuda)).sum() + (ag * va.to(cuda)).sum()).backward()
+    for k in lo:
+        scale = float(lo[k].grad.abs().mean()) + 1e-12
+        assert_close_frac(lg[k].grad, lo[k].grad, 1e-3, 1e-3 * scale, 5e-3, f"v_{k}")
+
+
+def test_colors_passthrough_and_edge_cases(cuda):
+    s = scene_s0(N=2000, C=1, size=72)  # 72 = 4.5 tiles
+    rgb = torch.rand(s.N, 3, generator=torch.Generator().manual_seed(9))
+    a = scene_args(s)
+    a["colors"] = rgb
+    ro, ao, io = oracle.rasterization(**a, width=s.width, height=s.height, render_mode="RGB+D", sh_degree=None)
+    rg, ag, ig = rasterization(**{k: v.to(cuda) for k, v in a.items()}, width=s.width, height=s.height, render_mode="RGB+D", sh_degree=None)
+    assert torch.equal(ig["flatten_ids"].cpu(), io["flatten_ids"])
+    assert_close_frac(rg, ro, 1e-4, 1e-4, 2e-3, "render")
+    # everything behind the camera -> empty image, no crash
+    a2 = {k: v.to(cuda) for k, v in a.items()}
+    a2["means"] = a2["means"] + torch.tensor([0.0, 0.0, 0.0], device=cuda)
+    vm = a2["viewmats"].clone()
+    vm[:, 2, 3] = -100.0
+    a2["viewmats"] = vm
+    rg, ag, ig = rasterization(**a2, width=s.width, height=s.height, render_mode="RGB+ED", sh_degree=None)
+    assert float(ag.abs().max()) == 0.0 and float(rg.abs().max()) == 0.0 and ig["isect_ids"].numel() == 0
+
+
+def test_rejects_unsupported(cuda):
+    s = scene_s0(N=100, C=1, size=32).to(cuda)
+    a = scene_args(s)
+    with pytest.raises(NotImplementedError):
+        rasterization(**a, width=32, height=32, packed=True, sh_degree=3)
+    with pytest.raises(ValueError):
+        rasterization(**a, width=32, height=32, render_mode="nope", sh_degree=3)
+    with pytest.raises(RuntimeError):
+        rasterization(**{k: v.cpu() for k, v in a.items()}, width=32, height=32, sh_degree=3)
