@@ -515,8 +515,8 @@ extern "C" int qed_project_bwd(int C, int N, const float* means, const float* qu
         return QED_ERR_BAD_ARG;
     if (calc_compensations && (!compensations || !opacities)) return QED_ERR_BAD_ARG;
     if (n_color > 0 && (!colors_in || !v_colors_in)) return QED_ERR_BAD_ARG;
-    if (sh_degree > 3) return QED_ERR_UNSUPPORTED;
     if (n_color == 0) sh_degree = -1;
+    if (sh_degree > 3) return QED_ERR_UNSUPPORTED;
 
     ProjBwdParams p;
     p.C = C;

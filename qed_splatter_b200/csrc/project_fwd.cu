@@ -392,9 +392,9 @@ extern "C" int qed_project_fwd(int C, int N, const float* means, const float* qu
         return QED_ERR_BAD_ARG;
     if (calc_compensations && (!compensations || !opacities)) return QED_ERR_BAD_ARG;
     if (n_color > 0 && !colors_in) return QED_ERR_BAD_ARG;
+    if (n_color == 0) sh_degree = -1;
     if (sh_degree > 3) return QED_ERR_UNSUPPORTED;
     if (sh_degree >= 0 && (sh_degree + 1) * (sh_degree + 1) > K) return QED_ERR_BAD_ARG;
-    if (n_color == 0) sh_degree = -1;
 
     ProjFwdParams p;
     p.C = C;

@@ -1,0 +1,175 @@
+"""Fused render + loss + backward pipeline (no autograd graph): the train-step hot path.
+
+This is what the reference does per iteration between `get_outputs` (model.py:199-321), `get_loss_dict`
+(model.py:73-118) and `loss.backward()`, restated as one straight sequence of C-ABI launches:
+
+    project+SH fwd -> tile count scan -> emit keys -> radix sort -> tile ranges -> composite fwd
+      -> loss + loss-gradient (background composite, clamp, depth fill, masked depth-L1, RGB-L1)
+      -> composite bwd (packed per-Gaussian gradient records) -> project+SH bwd
+
+Nothing is unpacked or re-laid-out between the two backward kernels: the compositor's backward writes
+the [C*N,12] packed record that the projection backward reads.  `rasterization()` in rendering.py is
+the autograd drop-in for the unchanged QEDSplatterModel; this class is the same kernels without the
+autograd bookkeeping, used by the trainer and the benchmark.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+from ._lib import check, current_stream, ptr
+
+
+@dataclass
+class StepOutput:
+    loss: Tensor  # [3] float32 device: total, rgb term, depth term
+    grads: Dict[str, Tensor]  # v_means, v_quats, v_scales, v_opacities, v_sh
+    packed_grads: Tensor  # [C*N,12] (absgrad in slots 2,3) for the strategy statistics
+    radii: Tensor  # [C,N] i32
+    render: Tensor  # [C,H,W,4]
+    alphas: Tensor  # [C,H,W,1]
+    n_isects: int
+    n_visible: Optional[int] = None
+
+
+class FusedSplatStep:
+    """Holds reusable device buffers; `forward()` renders, `step()` renders + loss + full backward."""
+
+    def __init__(self, device, sort_impl: str = "own"):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.sort_impl = sort_impl
+        self._total = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._stats = None
+        self._loss = torch.zeros(3, device=self.device)
+        self._cap_isects = 0
+        self._buf: Dict[str, Tensor] = {}
+
+    # -- buffers ------------------------------------------------------------------------------
+    def _get(self, name: str, shape, dtype=torch.float32) -> Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        t = self._buf.get(name)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t[:n].view(*shape)
+
+    # -- forward ------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, means, quats, scales, opacities, sh, viewmats, Ks, width: int, height: int, sh_degree: int,
+                render_mode: str = "RGB+ED", rasterize_mode: str = "classic", near_plane: float = 0.01,
+                far_plane: float = 1e10, eps2d: float = 0.3, backgrounds: Optional[Tensor] = None):
+        lib, stream = self.lib, current_stream()
+        _lib.require_cuda(means, quats, scales, opacities, sh, viewmats, Ks)
+        C, N = viewmats.shape[0], means.shape[0]
+        want_rgb = render_mode in ("RGB", "RGB+D", "RGB+ED")
+        want_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
+        n_color, append = (3 if want_rgb else 0), int(want_depth)
+        D = n_color + append
+        normalize = int(render_mode in ("ED", "RGB+ED"))
+        comp = rasterize_mode == "antialiased"
+        K = sh.shape[1] if (want_rgb and sh_degree is not None) else 0
+        deg = -1 if (sh_degree is None or not want_rgb) else int(sh_degree)
+        tile = 16
+        tw, th = ops.tile_grid(width, height, tile)
+
+        radii = self._get("radii", (C, N), torch.int32)
+        means2d = self._get("means2d", (C, N, 2))
+        depths = self._get("depths", (C, N))
+        conics = self._get("conics", (C, N, 3))
+        comps = self._get("comps", (C, N)) if comp else None
+        colors = self._get("colors", (C, N, D))
+        opac = self._get("opac", (C, N))
+        tiles = self._get("tiles", (C, N), torch.int32)
+        geom = self._get("geom", (C, N, 8))
+        check(lib.qed_project_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh) if want_rgb else None, K, deg,
+                                  int(want_rgb and sh_degree is None and sh.dim() == 3), ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane,
+                                  far_plane, 0.0, int(comp), tile, n_color, append, ptr(radii), ptr(means2d), ptr(depths),
+                                  ptr(conics), ptr(comps), ptr(colors), ptr(opac), ptr(tiles), ptr(geom), stream), "qed_project_fwd")
+        CN = C * N
+        cum = self._get("cum", (CN,), torch.int64)
+        ws_bytes = lib.qed_isect_scan_workspace_bytes(CN)
+        ws = self._get("scan_ws", (ws_bytes,), torch.uint8)
+        check(lib.qed_isect_scan(CN, ptr(tiles), ptr(cum), ptr(self._total), None, ptr(ws), ws_bytes, stream), "qed_isect_scan")
+        M = int(self._total.item())  # the single host sync of the step
+        cap = max(M, 1)
+        ids_u = self._get("ids_u", (cap,), torch.int64)[:M]
+        flat_u = self._get("flat_u", (cap,), torch.int32)[:M]
+        ids = self._get("ids", (cap,), torch.int64)[:M]
+        flat = self._get("flat", (cap,), torch.int32)[:M]
+        offsets = self._get("offsets", (C, th, tw), torch.int32)
+        if M:
+            check(lib.qed_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(cum), tile, tw, th, ptr(ids_u), ptr(flat_u),
+                                     stream), "qed_isect_emit")
+            end_bit = 32 + (tw * th).bit_length() + C.bit_length()
+            if self.sort_impl == "cub":
+                sb = lib.qed_sort_pairs_cub_workspace_bytes(M)
+                sws = self._get("sort_ws", (sb,), torch.uint8)
+                check(lib.qed_sort_pairs_cub(M, ptr(ids_u), ptr(flat_u), ptr(ids), ptr(flat), end_bit, ptr(sws), sb, stream), "qed_sort_pairs_cub")
+            else:
+                sb = lib.qed_sort_pairs_workspace_bytes(M)
+                sws = self._get("sort_ws", (sb,), torch.uint8)
+                check(lib.qed_sort_pairs(M, ptr(ids_u), ptr(flat_u), ptr(ids), ptr(flat), end_bit, ptr(sws), sb, stream), "qed_sort_pairs")
+        check(lib.qed_tile_ranges(M, ptr(ids) if M else None, C, tw, th, ptr(offsets), stream), "qed_tile_ranges")
+        render = self._get("render", (C, height, width, D))
+        alphas = self._get("alphas", (C, height, width, 1))
+        last_ids = self._get("last_ids", (C, height, width), torch.int32)
+        check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets),
+                                 ptr(flat) if M else None, normalize, ptr(render), ptr(alphas), ptr(last_ids), stream), "qed_raster_fwd")
+        self._fwd = dict(C=C, N=N, D=D, M=M, K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
+                         th=th, width=width, height=height, eps2d=eps2d, radii=radii, conics=conics, comps=comps, colors=colors,
+                         geom=geom, offsets=offsets, flat=flat, render=render, alphas=alphas, last_ids=last_ids, backgrounds=backgrounds,
+                         inputs=(means, quats, scales, opacities, sh, viewmats, Ks))
+        return render, alphas
+
+    # -- backward from explicit output gradients ------------------------------------------------
+    @torch.no_grad()
+    def backward(self, v_render: Tensor, v_alphas: Optional[Tensor]):
+        lib, stream, f = self.lib, current_stream(), self._fwd
+        C, N, D, M = f["C"], f["N"], f["D"], f["M"]
+        means, quats, scales, opacities, sh, viewmats, Ks = f["inputs"]
+        packed = self._get("packed", (C * N, 12))
+        packed.zero_()
+        if M:
+            check(lib.qed_raster_bwd(C, N, M, D, ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]), f["width"], f["height"], 16,
+                                     f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"], ptr(f["render"]),
+                                     ptr(f["alphas"]), ptr(f["last_ids"]), ptr(v_render), ptr(v_alphas), ptr(packed), stream), "qed_raster_bwd")
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        v_opac = torch.empty_like(opacities)
+        v_sh = torch.empty_like(sh) if f["n_color"] else None
+        check(lib.qed_project_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh) if f["n_color"] else None, f["K"],
+                                  f["deg"], 0, ptr(viewmats), ptr(Ks), f["width"], f["height"], f["eps2d"], int(f["comp"]), f["n_color"],
+                                  f["append"], ptr(f["radii"]), ptr(f["conics"]), ptr(f["comps"]), None, None, None, None, None,
+                                  ptr(packed), ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_opac), ptr(v_sh), stream), "qed_project_bwd")
+        grads = dict(means=v_means, quats=v_quats, scales=v_scales, opacities=v_opac, sh=v_sh)
+        return grads, packed
+
+    # -- full step: render + qed-splatter loss + backward -----------------------------------------
+    @torch.no_grad()
+    def step(self, means, quats, scales, opacities, sh, viewmats, Ks, width: int, height: int, sh_degree: int,
+             gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, render_mode: str = "RGB+ED", rgb_weight: float = 0.8,
+             depth_lambda: float = 0.2, grad_scale: float = 1.0, rasterize_mode: str = "classic") -> StepOutput:
+        """`render_mode` RGB+ED (north_star) or RGB+D (what qed_splatter/model.py:257 passes)."""
+        assert render_mode in ("RGB+D", "RGB+ED")
+        lib, stream = self.lib, current_stream()
+        render, alphas = self.forward(means, quats, scales, opacities, sh, viewmats, Ks, width, height, sh_degree, render_mode,
+                                      rasterize_mode)
+        C = viewmats.shape[0]
+        if self._stats is None or self._stats.numel() < C * 8:
+            self._stats = torch.zeros(C * 8, dtype=torch.float64, device=self.device)
+        v_render = self._get("v_render", (C, height, width, 4))
+        v_alphas = self._get("v_alphas", (C, height, width, 1))
+        check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), ptr(gt_depth), ptr(background), rgb_weight,
+                                   depth_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas), stream),
+              "qed_loss_fwd_bwd")
+        grads, packed = self.backward(v_render, v_alphas)
+        return StepOutput(loss=self._loss, grads=grads, packed_grads=packed, radii=self._fwd["radii"], render=render, alphas=alphas,
+                          n_isects=self._fwd["M"])
