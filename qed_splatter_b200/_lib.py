@@ -47,6 +47,7 @@ SIGNATURES = {
 # test hooks, not part of the reference-facing surface
 DEBUG_SIGNATURES = {
     "qed_debug_set_raster_cull": (c_int, [c_int]),
+    "qed_debug_set_raster_counters": (c_int, [P]),
 }
 
 

@@ -43,6 +43,29 @@ struct RasterParams {
     const float* v_render;
     const float* v_alphas;
     float* packed_grads;
+    unsigned long long* counters;  // STATS instantiations only (bench/test instrumentation)
+};
+
+// counters layout: [0] entries loaded, [1] entries staged after the tile-level cull, [2] (warp, Gaussian)
+// candidates after the warp-level cull, [3] lane evaluations by live lanes, [4] pairs that passed the
+// alpha test (composited / differentiated), [5] (warp, Gaussian) groups that ran the gradient reduction
+template <bool STATS>
+struct StatCounters {
+    unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
+    __device__ __forceinline__ void add(int i, unsigned long long v) {
+        if (STATS) c[i] += v;
+    }
+    __device__ __forceinline__ void flush(unsigned long long* out) {
+        if (STATS) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                unsigned long long v = c[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + i, v);
+            }
+        }
+    }
 };
 
 // Conservative test: can a Gaussian reach alpha >= 1/255 at any pixel centre in [x0,x1]x[y0,y1]?
@@ -118,9 +141,9 @@ struct Batch {
 
 // Loads entry `e` (sorted index) for this thread (or nothing if !have), runs the tile-level cull and
 // writes survivors compacted in thread order.  Returns the number of entries staged.  Needs all threads.
-template <int D, bool CULL>
+template <int D, bool CULL, bool STATS>
 __device__ __forceinline__ int stage_batch(const RasterParams& p, Batch<D>& sb, bool have, int64_t e, float tx0, float ty0, float tx1,
-                                           float ty1) {
+                                           float ty1, StatCounters<STATS>& st) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 A = make_float4(0, 0, 0, -1.0f), B = make_float4(0, 0, 0, 0);
     int64_t g = 0;
@@ -133,6 +156,8 @@ __device__ __forceinline__ int stage_batch(const RasterParams& p, Batch<D>& sb, 
         A.w = tau;
         keep = CULL ? ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, tau, tx0, ty0, tx1, ty1) : true;
     }
+    st.add(0, have ? 1 : 0);
+    st.add(1, keep ? 1 : 0);
     const uint32_t m = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) sb.warp_count[warp] = __popc(m);
     __syncthreads();
@@ -158,9 +183,10 @@ __device__ __forceinline__ int stage_batch(const RasterParams& p, Batch<D>& sb, 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int D, bool CULL>
+template <int D, bool CULL, bool STATS>
 __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(const RasterParams p) {
     __shared__ Batch<D> sb;
+    StatCounters<STATS> st;
     const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub_x = (warp & 1) * 8, sub_y = (warp >> 1) * 4;
@@ -190,7 +216,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(const Raster
     for (int64_t b0 = range_start; b0 < range_end; b0 += kBatch) {
         if (__syncthreads_count(done) == kRasterThreads) break;
         const int64_t e = b0 + threadIdx.x;
-        const int count = stage_batch<D, CULL>(p, sb, e < range_end, e, tx0, ty0, tx1, ty1);
+        const int count = stage_batch<D, CULL, STATS>(p, sb, e < range_end, e, tx0, ty0, tx1, ty1, st);
         if (!__all_sync(0xffffffffu, done)) {
             for (int c0 = 0; c0 < count; c0 += 32) {
                 uint32_t cand;
@@ -206,6 +232,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(const Raster
                     const int rem = count - c0;
                     cand = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
                 }
+                if (lane == 0) st.add(2, __popc(cand));
                 while (cand) {
                     const int q = c0 + __ffs(cand) - 1;
                     cand &= cand - 1;
@@ -214,6 +241,8 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(const Raster
                     const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
                     const float vis = __expf(-sigma);
                     const float alpha = fminf(kMaxAlpha, A.z * vis);
+                    st.add(3, done ? 0 : 1);
+                    st.add(4, (!done && sigma >= 0.0f && alpha >= kAlphaThreshold) ? 1 : 0);
                     if (!done && sigma >= 0.0f && alpha >= kAlphaThreshold) {
                         const float next_T = T * (1.0f - alpha);
                         if (next_T <= kTransmittanceThreshold) {
@@ -248,6 +277,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(const Raster
         p.alphas[pix] = alpha_out;
         p.last_ids[pix] = last;
     }
+    st.flush(p.counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -282,9 +312,10 @@ __device__ __forceinline__ float warp_reduce_transpose16(float (&v)[16], int lan
     return r1;
 }
 
-template <int D, bool CULL>
+template <int D, bool CULL, bool STATS>
 __global__ void __launch_bounds__(kRasterThreads) raster_bwd_kernel(const RasterParams p) {
     __shared__ Batch<D> sb;
+    StatCounters<STATS> st;
     __shared__ int s_max_last[kRasterThreads / 32];
     const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -362,7 +393,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_bwd_kernel(const Raster
     // walk the range back to front: batch entries in descending sorted index
     for (int64_t b1 = (int64_t)cta_max + 1; b1 > range_start; b1 -= kBatch) {
         const int64_t e = b1 - 1 - threadIdx.x;
-        const int count = stage_batch<D, CULL>(p, sb, e >= range_start, e, tx0, ty0, tx1, ty1);
+        const int count = stage_batch<D, CULL, STATS>(p, sb, e >= range_start, e, tx0, ty0, tx1, ty1, st);
         for (int c0 = 0; c0 < count; c0 += 32) {
             uint32_t cand;
             {
@@ -378,6 +409,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_bwd_kernel(const Raster
                 }
                 cand = __ballot_sync(0xffffffffu, hit);
             }
+            if (lane == 0) st.add(2, __popc(cand));
             while (cand) {
                 const int q = c0 + __ffs(cand) - 1;
                 cand &= cand - 1;
@@ -388,7 +420,10 @@ __global__ void __launch_bounds__(kRasterThreads) raster_bwd_kernel(const Raster
                 const float opac_vis = A.z * vis;
                 const float alpha = fminf(kMaxAlpha, opac_vis);
                 const bool valid = (sb.sid[q] <= bin_final) && (sigma >= 0.0f) && (alpha >= kAlphaThreshold);
+                st.add(3, (sb.sid[q] <= bin_final) ? 1 : 0);
+                st.add(4, valid ? 1 : 0);
                 if (!__any_sync(0xffffffffu, valid)) continue;
+                if (lane == 0) st.add(5, 1);
                 float v[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[k] = 0.0f;
@@ -430,6 +465,7 @@ __global__ void __launch_bounds__(kRasterThreads) raster_bwd_kernel(const Raster
         // no trailing barrier needed: stage_batch() only overwrites the staging buffers after its first
         // __syncthreads, which every warp reaches only after finishing this batch
     }
+    st.flush(p.counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -465,20 +501,34 @@ __global__ void unpack_grads_kernel(int64_t CN, int D, const float4* __restrict_
 }
 
 static int g_raster_cull = 1;  // test hook: 0 disables the culling (bit-identical results, slower)
+static unsigned long long* g_raster_counters = nullptr;  // instrumentation hook: device uint64[6] or null
 
 template <int D>
-static int launch_raster(const RasterParams& p, bool backward, cudaStream_t stream) {
+static int launch_raster(RasterParams p, bool backward, cudaStream_t stream) {
     dim3 grid(p.tile_w, p.tile_h, p.C);
-    if (!backward) {
+    p.counters = g_raster_counters;
+    if (g_raster_counters) {  // instrumented variant (never used in timed regions)
+        if (!backward) {
+            if (g_raster_cull)
+                raster_fwd_kernel<D, true, true><<<grid, kRasterThreads, 0, stream>>>(p);
+            else
+                raster_fwd_kernel<D, false, true><<<grid, kRasterThreads, 0, stream>>>(p);
+        } else {
+            if (g_raster_cull)
+                raster_bwd_kernel<D, true, true><<<grid, kRasterThreads, 0, stream>>>(p);
+            else
+                raster_bwd_kernel<D, false, true><<<grid, kRasterThreads, 0, stream>>>(p);
+        }
+    } else if (!backward) {
         if (g_raster_cull)
-            raster_fwd_kernel<D, true><<<grid, kRasterThreads, 0, stream>>>(p);
+            raster_fwd_kernel<D, true, false><<<grid, kRasterThreads, 0, stream>>>(p);
         else
-            raster_fwd_kernel<D, false><<<grid, kRasterThreads, 0, stream>>>(p);
+            raster_fwd_kernel<D, false, false><<<grid, kRasterThreads, 0, stream>>>(p);
     } else {
         if (g_raster_cull)
-            raster_bwd_kernel<D, true><<<grid, kRasterThreads, 0, stream>>>(p);
+            raster_bwd_kernel<D, true, false><<<grid, kRasterThreads, 0, stream>>>(p);
         else
-            raster_bwd_kernel<D, false><<<grid, kRasterThreads, 0, stream>>>(p);
+            raster_bwd_kernel<D, false, false><<<grid, kRasterThreads, 0, stream>>>(p);
     }
     QED_LAUNCH_CHECK();
     return QED_OK;
@@ -503,6 +553,12 @@ extern "C" int qed_debug_set_raster_cull(int enabled) {
     int old = g_raster_cull;
     g_raster_cull = enabled ? 1 : 0;
     return old;
+}
+
+// instrumentation hook (not part of the reference surface): counters = device uint64[6] or NULL
+extern "C" int qed_debug_set_raster_counters(void* counters) {
+    g_raster_counters = reinterpret_cast<unsigned long long*>(counters);
+    return QED_OK;
 }
 
 extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,

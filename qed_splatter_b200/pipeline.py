@@ -48,6 +48,13 @@ class FusedSplatStep:
         self._loss = torch.zeros(3, device=self.device)
         self._cap_isects = 0
         self._buf: Dict[str, Tensor] = {}
+        self.marks = None  # set to [] to record (name, cuda event) after every stage (bench.py stage timing)
+
+    def _mark(self, name: str) -> None:
+        if self.marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream())
+            self.marks.append((name, ev))
 
     # -- buffers ------------------------------------------------------------------------------
     def _get(self, name: str, shape, dtype=torch.float32) -> Tensor:
@@ -67,6 +74,7 @@ class FusedSplatStep:
                 far_plane: float = 1e10, eps2d: float = 0.3, backgrounds: Optional[Tensor] = None):
         lib, stream = self.lib, current_stream()
         _lib.require_cuda(means, quats, scales, opacities, sh, viewmats, Ks)
+        self._mark("begin")
         C, N = viewmats.shape[0], means.shape[0]
         want_rgb = render_mode in ("RGB", "RGB+D", "RGB+ED")
         want_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
@@ -92,12 +100,14 @@ class FusedSplatStep:
                                   int(want_rgb and sh_degree is None and sh.dim() == 3), ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane,
                                   far_plane, 0.0, int(comp), tile, n_color, append, ptr(radii), ptr(means2d), ptr(depths),
                                   ptr(conics), ptr(comps), ptr(colors), ptr(opac), ptr(tiles), ptr(geom), stream), "qed_project_fwd")
+        self._mark("project_fwd")
         CN = C * N
         cum = self._get("cum", (CN,), torch.int64)
         ws_bytes = lib.qed_isect_scan_workspace_bytes(CN)
         ws = self._get("scan_ws", (ws_bytes,), torch.uint8)
         check(lib.qed_isect_scan(CN, ptr(tiles), ptr(cum), ptr(self._total), None, ptr(ws), ws_bytes, stream), "qed_isect_scan")
         M = int(self._total.item())  # the single host sync of the step
+        self._mark("scan+sync")
         cap = max(M, 1)
         ids_u = self._get("ids_u", (cap,), torch.int64)[:M]
         flat_u = self._get("flat_u", (cap,), torch.int32)[:M]
@@ -107,6 +117,7 @@ class FusedSplatStep:
         if M:
             check(lib.qed_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(cum), tile, tw, th, ptr(ids_u), ptr(flat_u),
                                      stream), "qed_isect_emit")
+            self._mark("emit")
             end_bit = 32 + (tw * th).bit_length() + C.bit_length()
             if self.sort_impl == "cub":
                 sb = lib.qed_sort_pairs_cub_workspace_bytes(M)
@@ -116,12 +127,15 @@ class FusedSplatStep:
                 sb = lib.qed_sort_pairs_workspace_bytes(M)
                 sws = self._get("sort_ws", (sb,), torch.uint8)
                 check(lib.qed_sort_pairs(M, ptr(ids_u), ptr(flat_u), ptr(ids), ptr(flat), end_bit, ptr(sws), sb, stream), "qed_sort_pairs")
+        self._mark("sort")
         check(lib.qed_tile_ranges(M, ptr(ids) if M else None, C, tw, th, ptr(offsets), stream), "qed_tile_ranges")
+        self._mark("ranges")
         render = self._get("render", (C, height, width, D))
         alphas = self._get("alphas", (C, height, width, 1))
         last_ids = self._get("last_ids", (C, height, width), torch.int32)
         check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets),
                                  ptr(flat) if M else None, normalize, ptr(render), ptr(alphas), ptr(last_ids), stream), "qed_raster_fwd")
+        self._mark("raster_fwd")
         self._fwd = dict(C=C, N=N, D=D, M=M, K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
                          th=th, width=width, height=height, eps2d=eps2d, radii=radii, conics=conics, comps=comps, colors=colors,
                          geom=geom, offsets=offsets, flat=flat, render=render, alphas=alphas, last_ids=last_ids, backgrounds=backgrounds,
@@ -130,25 +144,34 @@ class FusedSplatStep:
 
     # -- backward from explicit output gradients ------------------------------------------------
     @torch.no_grad()
-    def backward(self, v_render: Tensor, v_alphas: Optional[Tensor]):
+    def backward(self, v_render: Tensor, v_alphas: Optional[Tensor], grad_out: Optional[Dict[str, Tensor]] = None):
+        """`grad_out`: optional preallocated {means,quats,scales,opacities,sh} (e.g. views into a flat
+        all-reduce arena) that the projection backward writes straight into."""
         lib, stream, f = self.lib, current_stream(), self._fwd
         C, N, D, M = f["C"], f["N"], f["D"], f["M"]
         means, quats, scales, opacities, sh, viewmats, Ks = f["inputs"]
         packed = self._get("packed", (C * N, 12))
         packed.zero_()
+        self._mark("zero_grads")
         if M:
             check(lib.qed_raster_bwd(C, N, M, D, ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]), f["width"], f["height"], 16,
                                      f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"], ptr(f["render"]),
                                      ptr(f["alphas"]), ptr(f["last_ids"]), ptr(v_render), ptr(v_alphas), ptr(packed), stream), "qed_raster_bwd")
-        v_means = torch.empty_like(means)
-        v_quats = torch.empty_like(quats)
-        v_scales = torch.empty_like(scales)
-        v_opac = torch.empty_like(opacities)
-        v_sh = torch.empty_like(sh) if f["n_color"] else None
+        self._mark("raster_bwd")
+        if grad_out is not None:
+            v_means, v_quats, v_scales, v_opac = grad_out["means"], grad_out["quats"], grad_out["scales"], grad_out["opacities"]
+            v_sh = grad_out["sh"] if f["n_color"] else None
+        else:
+            v_means = torch.empty_like(means)
+            v_quats = torch.empty_like(quats)
+            v_scales = torch.empty_like(scales)
+            v_opac = torch.empty_like(opacities)
+            v_sh = torch.empty_like(sh) if f["n_color"] else None
         check(lib.qed_project_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh) if f["n_color"] else None, f["K"],
                                   f["deg"], 0, ptr(viewmats), ptr(Ks), f["width"], f["height"], f["eps2d"], int(f["comp"]), f["n_color"],
                                   f["append"], ptr(f["radii"]), ptr(f["conics"]), ptr(f["comps"]), None, None, None, None, None,
                                   ptr(packed), ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_opac), ptr(v_sh), stream), "qed_project_bwd")
+        self._mark("project_bwd")
         grads = dict(means=v_means, quats=v_quats, scales=v_scales, opacities=v_opac, sh=v_sh)
         return grads, packed
 
@@ -156,7 +179,8 @@ class FusedSplatStep:
     @torch.no_grad()
     def step(self, means, quats, scales, opacities, sh, viewmats, Ks, width: int, height: int, sh_degree: int,
              gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, render_mode: str = "RGB+ED", rgb_weight: float = 0.8,
-             depth_lambda: float = 0.2, grad_scale: float = 1.0, rasterize_mode: str = "classic") -> StepOutput:
+             depth_lambda: float = 0.2, grad_scale: float = 1.0, rasterize_mode: str = "classic",
+             grad_out: Optional[Dict[str, Tensor]] = None) -> StepOutput:
         """`render_mode` RGB+ED (north_star) or RGB+D (what qed_splatter/model.py:257 passes)."""
         assert render_mode in ("RGB+D", "RGB+ED")
         lib, stream = self.lib, current_stream()
@@ -170,6 +194,49 @@ class FusedSplatStep:
         check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), ptr(gt_depth), ptr(background), rgb_weight,
                                    depth_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas), stream),
               "qed_loss_fwd_bwd")
-        grads, packed = self.backward(v_render, v_alphas)
+        self._mark("loss")
+        grads, packed = self.backward(v_render, v_alphas, grad_out)
+        self._last_v = (v_render, v_alphas)
         return StepOutput(loss=self._loss, grads=grads, packed_grads=packed, radii=self._fwd["radii"], render=render, alphas=alphas,
                           n_isects=self._fwd["M"])
+
+    # -- instrumentation (never inside a timed region) --------------------------------------------
+    @property
+    def launches_per_step(self) -> int:
+        """Kernel launches of one step(): project 1, scan 3, emit 1, sort (own: 3 per 8-bit pass; cub: 8),
+        ranges 1, composite fwd 1, loss 4 (+1 memset), grad clear 1, composite bwd 1, project bwd 1."""
+        f = self._fwd
+        end_bit = 32 + (f["tw"] * f["th"]).bit_length() + f["C"].bit_length()
+        sort = 3 * ((end_bit + 7) // 8) if self.sort_impl == "own" else 8
+        return 1 + 3 + 1 + sort + 1 + 1 + 5 + 1 + 1 + 1
+
+    @torch.no_grad()
+    def count_pairs(self) -> Dict[str, int]:
+        """Re-run the two compositing kernels of the last step() with the instrumented (STATS) variants and
+        return the work counters used for the FP32 roofline."""
+        lib, stream, f = self.lib, current_stream(), self._fwd
+        out = {}
+        if not f["M"]:
+            return out
+        names = ("entries_loaded", "entries_staged", "warp_candidates", "pairs_evaluated", "pairs_contributing", "reduction_groups")
+        for which in ("fwd", "bwd"):
+            cnt = torch.zeros(6, dtype=torch.int64, device=self.device)
+            check(lib.qed_debug_set_raster_counters(ptr(cnt)), "set counters")
+            try:
+                if which == "fwd":
+                    check(lib.qed_raster_fwd(f["C"], f["N"], f["M"], f["D"], ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]),
+                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"],
+                                             ptr(f["render"]), ptr(f["alphas"]), ptr(f["last_ids"]), stream), "qed_raster_fwd(stats)")
+                else:
+                    v_render, v_alphas = self._last_v
+                    scratch = torch.zeros(f["C"] * f["N"], 12, device=self.device)
+                    check(lib.qed_raster_bwd(f["C"], f["N"], f["M"], f["D"], ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]),
+                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"],
+                                             ptr(f["render"]), ptr(f["alphas"]), ptr(f["last_ids"]), ptr(v_render), ptr(v_alphas),
+                                             ptr(scratch), stream), "qed_raster_bwd(stats)")
+                torch.cuda.synchronize()
+            finally:
+                lib.qed_debug_set_raster_counters(None)
+            for n, v in zip(names, cnt.tolist()):
+                out[f"{which}_{n}"] = int(v)
+        return out
