@@ -48,6 +48,7 @@ SIGNATURES = {
 DEBUG_SIGNATURES = {
     "qed_debug_set_raster_cull": (c_int, [c_int]),
     "qed_debug_set_raster_counters": (c_int, [P]),
+    "qed_debug_set_raster_px": (c_int, [c_int, c_int]),
 }
 
 

@@ -4,29 +4,34 @@
 // qed_splatter/model.py:267-288; absgrad (model.py:284) is produced by the backward.
 // Semantics: SURVEY.md Appendix A.5 / A.6 == oracle/torch_impl.py::rasterize_to_pixels(_bwd).
 //
-// Design (B200-first, not gsplat's):
-//   * one CTA per 16x16 tile (the tile size is fixed by the bit-exact intersection contract), 8 warps,
-//     each warp owns an 8x4 pixel sub-rectangle (compact footprint -> warp-level culling pays).
-//   * Gaussians of the tile's sorted range are gathered through flatten_ids in batches of 256 as 32-byte
-//     geometry records + D-float colour records (L2-resident) into shared memory.
-//   * EXACT two-level culling: a Gaussian only changes a pixel if opacity*exp(-sigma) >= 1/255, i.e. the
-//     pixel centre lies inside the ellipse sigma <= ln(255*opacity).  The loader thread tests that ellipse
-//     against the whole tile (survivors are compacted in order with ballots), then every warp tests the
-//     survivors against its own 8x4 rectangle, 32 candidates at a time with one ballot, and only iterates
-//     over the set bits.  The test is conservative (minimum of sigma over the rectangle, plus a margin for
-//     rounding), so results are bit-identical to the un-culled kernel (template CULL=false, kept for tests).
-//   * early termination: per-lane `done`, warp exit on __all_sync(done), CTA exit on __syncthreads_count.
-//   * backward: back-to-front replay from the stored last index; the 12-float per-Gaussian gradient
-//     record is reduced across the warp with a transposed butterfly (16 shuffles instead of 60), then one
-//     red.global.add per value from 12 lanes into the packed [C*N,12] record.
-// Bound: FP32 issue + MUFU (ex2) pipes, not HBM (~30 FLOP + 1 ex2 per evaluated pixel-Gaussian pair).
+// Design (B200-first, not gsplat's).  Both kernels are FP32-issue bound (ncu: ~86 % issue-active), so the
+// design minimises instructions per evaluated (pixel, Gaussian) pair:
+//   * one CTA per 16x16 tile (tile size is fixed by the bit-exact intersection contract); every lane owns
+//     PX pixels (1, 2 or 4), so a warp covers an 8x4, 16x4 or 16x8 pixel footprint.
+//   * Gaussians of the tile's sorted range are gathered through flatten_ids, one per thread per batch, and
+//     re-expressed in the log2 domain:  log2(alpha) = lo + qa dx^2 + qb dx dy + qc dy^2  with
+//     lo = log2(opacity), (qa,qb,qc) = -log2(e) * (a/2, b, c/2).  The exponential is then a bare
+//     ex2.approx (one MUFU) and the quadratic form shares terms between the pixels of a lane.
+//   * EXACT two-level culling: a Gaussian changes a pixel only if alpha >= 1/255, i.e. the pixel centre is
+//     inside the ellipse Q(d) <= lo + log2(255).  The loader thread tests that ellipse against the whole
+//     tile (survivors compacted in order with ballots); every warp then tests 32 survivors at a time
+//     against its own footprint with one ballot and copies the hits, compacted and in order, into a
+//     private shared-memory queue.  The inner loop is a plain counted loop over that queue (3 broadcast
+//     LDS.128 per Gaussian, no index arithmetic).  The test is conservative (minimum of Q over the
+//     rectangle plus a rounding margin), so results are identical to the un-culled kernel (test hook).
+//   * fully predicated inner loops (no divergent branches); early termination per lane, per warp
+//     (__all_sync) and per CTA (__syncthreads_count).
+//   * backward: back-to-front replay from the stored last index with a scalar running
+//     bsum = sum_k buffer[k] v_out[k]; per Gaussian the 12 gradient values of all PX pixels of a lane are
+//     pre-added, then reduced across the warp with a transposed butterfly (16 shuffles instead of 60) and
+//     added with one red.global.add per value from 12 lanes into the packed [C*N,12] record.
 #include "common.cuh"
 
 namespace qed {
 
 constexpr int kTile = 16;
-constexpr int kRasterThreads = kTile * kTile;
-constexpr int kBatch = kRasterThreads;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLog2_255 = 7.99435343685886f;
 
 struct RasterParams {
     int C, N, D, width, height, tile_w, tile_h, normalize_last;
@@ -47,8 +52,8 @@ struct RasterParams {
 };
 
 // counters layout: [0] entries loaded, [1] entries staged after the tile-level cull, [2] (warp, Gaussian)
-// candidates after the warp-level cull, [3] lane evaluations by live lanes, [4] pairs that passed the
-// alpha test (composited / differentiated), [5] (warp, Gaussian) groups that ran the gradient reduction
+// candidates after the warp-level cull, [3] (pixel, Gaussian) evaluations by live pixels, [4] pairs that
+// passed the alpha test (composited / differentiated), [5] (warp, Gaussian) gradient reductions
 template <bool STATS>
 struct StatCounters {
     unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
@@ -68,132 +73,204 @@ struct StatCounters {
     }
 };
 
-// Conservative test: can a Gaussian reach alpha >= 1/255 at any pixel centre in [x0,x1]x[y0,y1]?
-// sigma(d) = 0.5*(a dx^2 + c dy^2) + b dx dy with d = mean - pixel.  Returns false only if the minimum of
-// sigma over the rectangle exceeds tau = ln(255*opacity) by a safety margin.
-__device__ __forceinline__ bool ellipse_hits_rect(float mx, float my, float a, float b, float c, float tau, float x0, float y0,
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Conservative test in the log2 domain: Q(d) = A dx^2 + B dx dy + C dy^2 (positive definite,
+// = log2(e) * sigma), d = mean - pixel centre.  A pixel can only be touched if Q <= tau2 = lo + log2(255).
+// Returns false only if the minimum of Q over the rectangle [x0,x1]x[y0,y1] exceeds tau2 by a margin.
+__device__ __forceinline__ bool ellipse_hits_rect(float mx, float my, float A, float B, float C, float tau2, float x0, float y0,
                                                   float x1, float y1) {
-    if (!(tau >= 0.0f)) return false;  // opacity < 1/255 can never pass the alpha test
-    // d ranges
+    if (!(tau2 >= 0.0f)) return false;  // opacity < 1/255 can never pass the alpha test
     const float dxl = mx - x1, dxh = mx - x0;  // dx in [dxl, dxh]
     const float dyl = my - y1, dyh = my - y0;
     if (dxl <= 0.0f && dxh >= 0.0f && dyl <= 0.0f && dyh >= 0.0f) return true;  // centre inside
-    // the quadratic is convex: its minimum over the rectangle (centre outside) lies on an edge
-    float best = 3.0e38f;
-    float mag = 0.0f;
-    const float inv_c = 1.0f / c, inv_a = 1.0f / a;
-    {  // edges dx = dxl / dxh : minimise over dy
-        float dxs[2] = {dxl, dxh};
+    // convex quadratic, centre outside: the minimum over the rectangle lies on an edge
+    float best = 3.0e38f, mag = 0.0f;
+    const float hC = 0.5f * rcp_approx(C), hA = 0.5f * rcp_approx(A);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            float dx = dxs[e];
-            float dy = fminf(fmaxf(-b * dx * inv_c, dyl), dyh);
-            float t0 = 0.5f * a * dx * dx, t1 = 0.5f * c * dy * dy, t2 = b * dx * dy;
-            float s = t0 + t1 + t2;
-            if (s < best) {
-                best = s;
-                mag = t0 + t1 + fabsf(t2);
-            }
+    for (int e = 0; e < 2; ++e) {  // edges dx = const
+        const float dx = e ? dxh : dxl;
+        const float dy = fminf(fmaxf(-B * dx * hC, dyl), dyh);
+        const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
+        const float s = t0 + t1 + t2;
+        if (s < best) {
+            best = s;
+            mag = t0 + t1 + fabsf(t2);
         }
     }
-    {  // edges dy = dyl / dyh : minimise over dx
-        float dys[2] = {dyl, dyh};
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            float dy = dys[e];
-            float dx = fminf(fmaxf(-b * dy * inv_a, dxl), dxh);
-            float t0 = 0.5f * a * dx * dx, t1 = 0.5f * c * dy * dy, t2 = b * dx * dy;
-            float s = t0 + t1 + t2;
-            if (s < best) {
-                best = s;
-                mag = t0 + t1 + fabsf(t2);
-            }
+    for (int e = 0; e < 2; ++e) {  // edges dy = const
+        const float dy = e ? dyh : dyl;
+        const float dx = fminf(fmaxf(-B * dy * hA, dxl), dxh);
+        const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
+        const float s = t0 + t1 + t2;
+        if (s < best) {
+            best = s;
+            mag = t0 + t1 + fabsf(t2);
         }
     }
-    // margin: 1% + absolute + rounding of the three terms (cancellation for thin, tilted ellipses)
-    return !(best > tau * 1.01f + 0.02f + 1e-5f * mag);
+    // margin: 1 % + absolute + rounding of the three terms (cancellation for thin, tilted ellipses)
+    return !(best > tau2 * 1.01f + 0.03f + 2e-5f * mag);
 }
 
-template <int D>
-__device__ __forceinline__ void load_color(const float* __restrict__ colors, int64_t g, float* out) {
-    if (D == 4) {
-        float4 v = reinterpret_cast<const float4*>(colors)[g];
-        out[0] = v.x;
-        out[1] = v.y;
-        out[2] = v.z;
-        out[3] = v.w;
-    } else {
-#pragma unroll
-        for (int k = 0; k < D; ++k) out[k] = colors[g * D + k];
-    }
-}
-
-// Shared staging of one batch.  Entries are stored in processing order; with CULL only tile-level
-// survivors are kept (order preserved), `sid` is the entry's index in the sorted intersection list.
-template <int D>
-struct Batch {
-    float4 ga[kBatch];  // mx, my, opacity, tau
-    float4 gb[kBatch];  // conic a, b, c, (bits) flat gaussian id
-    float col[kBatch][D];
-    int32_t sid[kBatch];
-    int warp_count[kRasterThreads / 32];
+// Geometry of the thread block: PX pixels per lane -> warps per tile and warp footprint.
+template <int PX>
+struct Shape {
+    static constexpr int kWarps = 8 / PX;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kFootW = PX >= 2 ? 16 : 8;
+    static constexpr int kFootH = PX == 4 ? 8 : 4;
+    static constexpr int kNX = PX >= 2 ? 2 : 1;  // distinct pixel columns per lane (8 apart)
+    static constexpr int kNY = PX == 4 ? 2 : 1;  // distinct pixel rows per lane (4 apart)
+    __device__ static __forceinline__ int origin_x(int warp) { return PX == 1 ? (warp & 1) * 8 : 0; }
+    __device__ static __forceinline__ int origin_y(int warp) { return PX == 1 ? (warp >> 1) * 4 : warp * kFootH; }
 };
 
-// Loads entry `e` (sorted index) for this thread (or nothing if !have), runs the tile-level cull and
-// writes survivors compacted in thread order.  Returns the number of entries staged.  Needs all threads.
-template <int D, bool CULL, bool STATS>
-__device__ __forceinline__ int stage_batch(const RasterParams& p, Batch<D>& sb, bool have, int64_t e, float tx0, float ty0, float tx1,
+// Shared staging: `sa/sb/sc` = one batch (one entry per thread, tile-level survivors compacted in order),
+// `qa/qb/qc` = per-warp queue of the (<= 32) survivors of the warp-level cull for the current chunk.
+//   a = {mx, my, lo, sorted index (bits)}   b = {qa, qb, qc, flat gaussian id (bits)}   c = colour[0..3]
+template <int PX>
+struct Staging {
+    float4 sa[Shape<PX>::kThreads], sb[Shape<PX>::kThreads], sc[Shape<PX>::kThreads];
+    float4 qa[Shape<PX>::kWarps][32], qb[Shape<PX>::kWarps][32], qc[Shape<PX>::kWarps][32];
+    int qm[Shape<PX>::kWarps][32];  // which of the lane's PX 8x4 sub-rectangles the Gaussian can touch
+    int warp_count[Shape<PX>::kWarps];
+    int max_last[Shape<PX>::kWarps];
+};
+
+template <int D>
+__device__ __forceinline__ float4 load_color4(const float* __restrict__ colors, int64_t g) {
+    if (D == 4) return reinterpret_cast<const float4*>(colors)[g];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = colors[g * D];
+    if (D >= 3) {
+        v.y = colors[g * D + 1];
+        v.z = colors[g * D + 2];
+    }
+    return v;
+}
+
+// Loads entry `e` of the sorted list for this thread (or nothing if !have), converts it to the log2 domain,
+// runs the tile-level cull and writes survivors compacted in thread order.  Returns the staged count.
+template <int D, int PX, bool CULL, bool STATS>
+__device__ __forceinline__ int stage_batch(const RasterParams& p, Staging<PX>& sm, bool have, int64_t e, float tx0, float ty0, float tx1,
                                            float ty1, StatCounters<STATS>& st) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 A = make_float4(0, 0, 0, -1.0f), B = make_float4(0, 0, 0, 0);
+    float4 A = make_float4(0, 0, 0, 0), B = make_float4(0, 0, 0, 0);
     int64_t g = 0;
     bool keep = false;
     if (have) {
         g = p.flatten_ids[e];
-        A = p.geom[g * 2];
-        B = p.geom[g * 2 + 1];
-        float tau = __logf(255.0f * A.z);
-        A.w = tau;
-        keep = CULL ? ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, tau, tx0, ty0, tx1, ty1) : true;
+        const float4 ga = p.geom[g * 2];      // mx, my, opacity, depth
+        const float4 gb = p.geom[g * 2 + 1];  // conic a, b, c
+        const float lo = __log2f(ga.z);
+        A = make_float4(ga.x, ga.y, lo, __int_as_float((int)e));
+        B = make_float4(-0.5f * kLog2e * gb.x, -kLog2e * gb.y, -0.5f * kLog2e * gb.z, __int_as_float((int)g));
+        keep = CULL ? ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, lo + kLog2_255, tx0, ty0, tx1, ty1) : true;
     }
     st.add(0, have ? 1 : 0);
     st.add(1, keep ? 1 : 0);
     const uint32_t m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) sb.warp_count[warp] = __popc(m);
+    if (lane == 0) sm.warp_count[warp] = __popc(m);
     __syncthreads();
     int base = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kRasterThreads / 32; ++w) {
-        int cnt = sb.warp_count[w];
+    for (int w = 0; w < Shape<PX>::kWarps; ++w) {
+        const int cnt = sm.warp_count[w];
         if (w < warp) base += cnt;
         total += cnt;
     }
     if (keep) {
         const int pos = base + __popc(m & ((1u << lane) - 1u));
-        B.w = __int_as_float((int)g);
-        sb.ga[pos] = A;
-        sb.gb[pos] = B;
-        load_color<D>(p.colors, g, sb.col[pos]);
-        sb.sid[pos] = (int32_t)e;
+        sm.sa[pos] = A;
+        sm.sb[pos] = B;
+        sm.sc[pos] = load_color4<D>(p.colors, g);
     }
     __syncthreads();
     return total;
 }
 
+// Pixel-centre rectangles of the PX 8x4 sub-rectangles of a warp footprint, clipped to the image.
+template <int PX>
+struct SubRects {
+    float x0[PX], y0[PX], x1[PX], y1[PX];
+    int present;  // bit k set if sub-rectangle k has at least one pixel inside the image
+};
+
+template <int PX>
+__device__ __forceinline__ SubRects<PX> make_subrects(int ox, int oy, int width, int height) {
+    SubRects<PX> r;
+    r.present = 0;
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        const int sx = ox + (k & 1) * 8, sy = oy + (k >> 1) * 4;
+        r.x0[k] = (float)sx + 0.5f;
+        r.y0[k] = (float)sy + 0.5f;
+        r.x1[k] = (float)min(sx + 7, width - 1) + 0.5f;
+        r.y1[k] = (float)min(sy + 3, height - 1) + 0.5f;
+        if (sx < width && sy < height) r.present |= 1 << k;
+    }
+    return r;
+}
+
+// Warp-level cull of staged entries [c0, c0+32): every lane tests one entry against the PX sub-rectangles
+// still of interest (`want` bits; backward: additionally sorted index <= max_sid[k]); entries that can
+// touch at least one are copied, compacted and in order, into the warp's queue together with their
+// sub-rectangle mask.  Returns the number of queued entries (warp-uniform).
+template <int PX, bool CULL, bool BWD>
+__device__ __forceinline__ int fill_queue(Staging<PX>& sm, int c0, int count, const SubRects<PX>& sr, int want, const int* max_sid) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = c0 + lane;
+    int mask = 0;
+    float4 A = make_float4(0, 0, 0, 0), B = make_float4(0, 0, 0, 0);
+    if (q < count && want) {
+        A = sm.sa[q];
+        B = sm.sb[q];
+        const int sid = __float_as_int(A.w);
+        const float tau2 = A.z + kLog2_255;
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            bool hit = (want >> k) & 1;
+            if (BWD) hit = hit && (sid <= max_sid[k]);
+            if (CULL && hit) hit = ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, tau2, sr.x0[k], sr.y0[k], sr.x1[k], sr.y1[k]);
+            if (hit) mask |= 1 << k;
+        }
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, mask != 0);
+    __syncwarp();  // every lane is done reading the previous queue contents
+    if (mask) {
+        const int pos = __popc(m & ((1u << lane) - 1u));
+        sm.qa[warp][pos] = A;
+        sm.qb[warp][pos] = B;
+        sm.qc[warp][pos] = sm.sc[q];
+        sm.qm[warp][pos] = mask;
+    }
+    __syncwarp();
+    return __popc(m);
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int D, bool CULL, bool STATS>
-__global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(const RasterParams p) {
-    __shared__ Batch<D> sb;
+template <int D, int PX, bool CULL, bool STATS>
+__global__ void __launch_bounds__(Shape<PX>::kThreads) raster_fwd_kernel(const RasterParams p) {
+    using S = Shape<PX>;
+    __shared__ Staging<PX> sm;
     StatCounters<STATS> st;
     const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub_x = (warp & 1) * 8, sub_y = (warp >> 1) * 4;
-    const int j = tx * kTile + sub_x + (lane & 7);   // pixel column
-    const int i = ty * kTile + sub_y + (lane >> 3);  // pixel row
-    const bool inside = (i < p.height) && (j < p.width);
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int ox = tx * kTile + S::origin_x(warp), oy = ty * kTile + S::origin_y(warp);
+    const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);  // first pixel of this lane; others at +8 / +4
+    const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
 
     const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
     const int64_t range_start = p.offsets[tile_id];
@@ -202,80 +279,91 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(const Raster
     // pixel-centre rectangles for the culling tests (clipped to the image)
     const float tx0 = (float)(tx * kTile) + 0.5f, ty0 = (float)(ty * kTile) + 0.5f;
     const float tx1 = (float)min(tx * kTile + kTile - 1, p.width - 1) + 0.5f, ty1 = (float)min(ty * kTile + kTile - 1, p.height - 1) + 0.5f;
-    const float wx0 = (float)(tx * kTile + sub_x) + 0.5f, wy0 = (float)(ty * kTile + sub_y) + 0.5f;
-    const float wx1 = fminf((float)(tx * kTile + sub_x + 7) + 0.5f, tx1), wy1 = fminf((float)(ty * kTile + sub_y + 3) + 0.5f, ty1);
-    const bool warp_has_pixels = (wx0 <= tx1) && (wy0 <= ty1);
+    const SubRects<PX> sr = make_subrects<PX>(ox, oy, p.width, p.height);
 
-    float T = 1.0f;
-    float acc[D];
+    float T[PX], acc[PX][D];
+    int32_t last[PX];
+    bool live[PX];
 #pragma unroll
-    for (int k = 0; k < D; ++k) acc[k] = 0.0f;
-    int32_t last = 0;
-    bool done = !inside;
+    for (int k = 0; k < PX; ++k) {
+        T[k] = 1.0f;
+        last[k] = 0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[k][d] = 0.0f;
+        live[k] = (i0 + (k >> 1) * 4 < p.height) && (j0 + (k & 1) * 8 < p.width);
+    }
+    int alive = sr.present;  // warp-uniform: sub-rectangles that still have a live pixel
 
-    for (int64_t b0 = range_start; b0 < range_end; b0 += kBatch) {
-        if (__syncthreads_count(done) == kRasterThreads) break;
+    for (int64_t b0 = range_start; b0 < range_end; b0 += S::kThreads) {
+        if (__syncthreads_count(alive != 0) == 0) break;
         const int64_t e = b0 + threadIdx.x;
-        const int count = stage_batch<D, CULL, STATS>(p, sb, e < range_end, e, tx0, ty0, tx1, ty1, st);
-        if (!__all_sync(0xffffffffu, done)) {
-            for (int c0 = 0; c0 < count; c0 += 32) {
-                uint32_t cand;
-                if (CULL) {
-                    const int q = c0 + lane;
-                    bool hit = false;
-                    if (q < count && warp_has_pixels) {
-                        const float4 A = sb.ga[q], B = sb.gb[q];
-                        hit = ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, A.w, wx0, wy0, wx1, wy1);
-                    }
-                    cand = __ballot_sync(0xffffffffu, hit);
-                } else {
-                    const int rem = count - c0;
-                    cand = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-                }
-                if (lane == 0) st.add(2, __popc(cand));
-                while (cand) {
-                    const int q = c0 + __ffs(cand) - 1;
-                    cand &= cand - 1;
-                    const float4 A = sb.ga[q], B = sb.gb[q];
-                    const float dx = A.x - px, dy = A.y - py;
-                    const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-                    const float vis = __expf(-sigma);
-                    const float alpha = fminf(kMaxAlpha, A.z * vis);
-                    st.add(3, done ? 0 : 1);
-                    st.add(4, (!done && sigma >= 0.0f && alpha >= kAlphaThreshold) ? 1 : 0);
-                    if (!done && sigma >= 0.0f && alpha >= kAlphaThreshold) {
-                        const float next_T = T * (1.0f - alpha);
-                        if (next_T <= kTransmittanceThreshold) {
-                            done = true;
-                        } else {
-                            const float w = alpha * T;
+        const int count = stage_batch<D, PX, CULL, STATS>(p, sm, e < range_end, e, tx0, ty0, tx1, ty1, st);
+        for (int c0 = 0; c0 < count && alive; c0 += 32) {
+            const int nq = fill_queue<PX, CULL, false>(sm, c0, count, sr, alive, nullptr);
+            for (int q = 0; q < nq; ++q) {
+                const float4 A = sm.qa[warp][q], B = sm.qb[warp][q], Cc = sm.qc[warp][q];
+                const int mask = sm.qm[warp][q];
+                if (lane == 0) st.add(2, __popc(mask));
+                float dx[S::kNX], ax[S::kNX], dy[S::kNY], cy[S::kNY];
 #pragma unroll
-                            for (int k = 0; k < D; ++k) acc[k] += sb.col[q][k] * w;
-                            last = sb.sid[q];
-                            T = next_T;
-                        }
-                    }
+                for (int a = 0; a < S::kNX; ++a) {
+                    dx[a] = A.x - (px0 + 8.0f * a);
+                    ax[a] = B.x * dx[a];
                 }
-                if (__all_sync(0xffffffffu, done)) break;
+#pragma unroll
+                for (int b = 0; b < S::kNY; ++b) {
+                    dy[b] = A.y - (py0 + 4.0f * b);
+                    cy[b] = fmaf(B.z * dy[b], dy[b], A.z);
+                }
+#pragma unroll
+                for (int k = 0; k < PX; ++k) {
+                    if (PX > 1 && !((mask >> k) & 1)) continue;  // warp-uniform
+                    const int a = k & 1, b = k >> 1;
+                    const float pw = fmaf(fmaf(B.y, dy[b], ax[a]), dx[a], cy[b]);  // log2(opacity * exp(-sigma))
+                    const float alpha = fminf(kMaxAlpha, ex2_approx(pw));
+                    const bool ok = live[k] && (pw <= A.z) && (alpha >= kAlphaThreshold);  // pw <= lo  <=>  sigma >= 0
+                    const float next_T = T[k] * (1.0f - alpha);
+                    const bool stop = ok && (next_T <= kTransmittanceThreshold);
+                    const bool upd = ok && !stop;
+                    st.add(3, live[k] ? 1 : 0);
+                    st.add(4, upd ? 1 : 0);
+                    const float w = upd ? alpha * T[k] : 0.0f;
+                    acc[k][0] = fmaf(Cc.x, w, acc[k][0]);
+                    if (D >= 3) {
+                        acc[k][1] = fmaf(Cc.y, w, acc[k][1]);
+                        acc[k][2] = fmaf(Cc.z, w, acc[k][2]);
+                    }
+                    if (D == 4) acc[k][3] = fmaf(Cc.w, w, acc[k][3]);
+                    T[k] = upd ? next_T : T[k];
+                    last[k] = upd ? __float_as_int(A.w) : last[k];
+                    live[k] = live[k] && !stop;
+                }
             }
+            alive = 0;
+#pragma unroll
+            for (int k = 0; k < PX; ++k) alive |= __any_sync(0xffffffffu, live[k]) ? (1 << k) : 0;
         }
     }
 
-    if (inside) {
-        const int64_t pix = ((int64_t)cam * p.height + i) * p.width + j;
-        const float alpha_out = 1.0f - T;
-        float out[D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) out[k] = acc[k] + (p.backgrounds ? T * p.backgrounds[cam * D + k] : 0.0f);
-        if (p.normalize_last) out[D - 1] = out[D - 1] / fmaxf(alpha_out, 1e-10f);
-        if (D == 4) {
-            reinterpret_cast<float4*>(p.render)[pix] = make_float4(out[0], out[1], out[2], out[3]);
-        } else {
+    for (int k = 0; k < PX; ++k) {
+        const int i = i0 + (k >> 1) * 4, j = j0 + (k & 1) * 8;
+        if (i < p.height && j < p.width) {
+            const int64_t pix = ((int64_t)cam * p.height + i) * p.width + j;
+            const float alpha_out = 1.0f - T[k];
+            float out[D];
 #pragma unroll
-            for (int k = 0; k < D; ++k) p.render[pix * D + k] = out[k];
+            for (int d = 0; d < D; ++d) out[d] = acc[k][d] + (p.backgrounds ? T[k] * p.backgrounds[cam * D + d] : 0.0f);
+            if (p.normalize_last) out[D - 1] = out[D - 1] / fmaxf(alpha_out, 1e-10f);
+            if (D == 4) {
+                reinterpret_cast<float4*>(p.render)[pix] = make_float4(out[0], out[1], out[2], out[3]);
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) p.render[pix * D + d] = out[d];
+            }
+            p.alphas[pix] = alpha_out;
+            p.last_ids[pix] = last[k];
         }
-        p.alphas[pix] = alpha_out;
-        p.last_ids[pix] = last;
     }
     st.flush(p.counters);
 }
@@ -283,16 +371,26 @@ __global__ void __launch_bounds__(kRasterThreads) raster_fwd_kernel(const Raster
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// Sum 16 per-lane slots over the 32 lanes with 16 shuffles; lane l returns the total of slot l>>1.
-__device__ __forceinline__ float warp_reduce_transpose16(float (&v)[16], int lane) {
+// Sum the 12 per-lane slots v[0..11] over the 32 lanes with 16 shuffles (a transposed butterfly: each
+// stage halves the number of slots a lane still carries).  Slots 4..7 take a plain butterfly in the first
+// stage, so no lane ever carries padding.  Returns the total of slot `reduce_slot(lane)`; lanes for
+// which reduce_lane_active(lane) is false hold a duplicate.
+__device__ __forceinline__ int reduce_slot(int lane) {
+    return ((lane & 8) ? 4 : ((lane & 16) ? 8 : 0)) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+__device__ __forceinline__ bool reduce_lane_active(int lane) { return !(lane & 1) && !((lane & 8) && (lane & 16)); }
+
+__device__ __forceinline__ float warp_reduce_transpose12(const float (&v)[12], int lane) {
     float r8[8], r4[4], r2[2];
     const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 4; ++i) {  // slots i <-> i+8 swap halves
         const float send = h4 ? v[i] : v[i + 8];
         const float keep = h4 ? v[i + 8] : v[i];
         r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
+#pragma unroll
+    for (int i = 4; i < 8; ++i) r8[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 16);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float send = h3 ? r8[i] : r8[i + 4];
@@ -312,153 +410,180 @@ __device__ __forceinline__ float warp_reduce_transpose16(float (&v)[16], int lan
     return r1;
 }
 
-template <int D, bool CULL, bool STATS>
-__global__ void __launch_bounds__(kRasterThreads) raster_bwd_kernel(const RasterParams p) {
-    __shared__ Batch<D> sb;
+template <int D, int PX, bool CULL, bool STATS>
+__global__ void __launch_bounds__(Shape<PX>::kThreads) raster_bwd_kernel(const RasterParams p) {
+    using S = Shape<PX>;
+    __shared__ Staging<PX> sm;
     StatCounters<STATS> st;
-    __shared__ int s_max_last[kRasterThreads / 32];
     const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub_x = (warp & 1) * 8, sub_y = (warp >> 1) * 4;
-    const int j = tx * kTile + sub_x + (lane & 7);
-    const int i = ty * kTile + sub_y + (lane >> 3);
-    const bool inside = (i < p.height) && (j < p.width);
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int ox = tx * kTile + S::origin_x(warp), oy = ty * kTile + S::origin_y(warp);
+    const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);
+    const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
 
     const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
     const int64_t range_start = p.offsets[tile_id];
-    const int64_t range_end = (tile_id == (int64_t)p.C * p.tile_h * p.tile_w - 1) ? p.n_isects : (int64_t)p.offsets[tile_id + 1];
 
     const float tx0 = (float)(tx * kTile) + 0.5f, ty0 = (float)(ty * kTile) + 0.5f;
     const float tx1 = (float)min(tx * kTile + kTile - 1, p.width - 1) + 0.5f, ty1 = (float)min(ty * kTile + kTile - 1, p.height - 1) + 0.5f;
-    const float wx0 = (float)(tx * kTile + sub_x) + 0.5f, wy0 = (float)(ty * kTile + sub_y) + 0.5f;
-    const float wx1 = fminf((float)(tx * kTile + sub_x + 7) + 0.5f, tx1), wy1 = fminf((float)(ty * kTile + sub_y + 3) + 0.5f, ty1);
-    const bool warp_has_pixels = (wx0 <= tx1) && (wy0 <= ty1);
+    const SubRects<PX> sr = make_subrects<PX>(ox, oy, p.width, p.height);
 
-    // per-pixel state
-    float T_final = 1.0f, v_alpha_out = 0.0f;
-    float v_out[D], buffer[D];
-    int32_t bin_final = -1;
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-        v_out[k] = 0.0f;
-        buffer[k] = 0.0f;
-    }
-    if (inside) {
-        const int64_t pix = ((int64_t)cam * p.height + i) * p.width + j;
-        const float alpha_out = p.alphas[pix];
-        T_final = 1.0f - alpha_out;
-        if (T_final < 1.0f) bin_final = p.last_ids[pix];  // pixels nothing was composited into stay at -1
-        if (D == 4) {
-            float4 v = reinterpret_cast<const float4*>(p.v_render)[pix];
-            v_out[0] = v.x;
-            v_out[1] = v.y;
-            v_out[2] = v.z;
-            v_out[3] = v.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < D; ++k) v_out[k] = p.v_render[pix * D + k];
-        }
-        v_alpha_out = p.v_alphas ? p.v_alphas[pix] : 0.0f;
-        if (p.normalize_last) {
-            // out_last = raw_last / max(alpha,1e-10)  (raw includes the background term)
-            const float denom = fmaxf(alpha_out, 1e-10f);
-            const float out_last = p.render[pix * D + D - 1];
-            const float g = v_out[D - 1];
-            v_out[D - 1] = g / denom;
-            if (alpha_out > 1e-10f) v_alpha_out += -g * out_last / denom;
-        }
-        if (p.backgrounds) {
-            // render = acc + T_final * bg  ->  d/dalpha_out of the bg term is -bg
-            float s = 0.0f;
-#pragma unroll
-            for (int k = 0; k < D; ++k) s += p.backgrounds[cam * D + k] * v_out[k];
-            v_alpha_out -= s;
-        }
-    }
-    float T = T_final;
+    // per-lane role in the gradient reduction: which slot this lane ends up holding, and its scale back to
+    // the (mean2d, conic, opacity, colour) parametrisation:
+    //   v_mean = g u / log2e ; v_conic = -(g dx^2 / 2, g dx dy, g dy^2 / 2) ; v_opacity = g / opacity
+    const int slot = reduce_slot(lane);
+    const bool slot_active = reduce_lane_active(lane) && slot < 8 + D;
+    const float slot_scale = slot < 4 ? (1.0f / kLog2e) : ((slot == 4 || slot == 6) ? -0.5f : (slot == 5 ? -1.0f : 1.0f));
 
-    // CTA-wide last contributing index
-    int wmax = bin_final;
+    // per-pixel state: T (transmittance after the current Gaussian), bsum = sum_k buffer[k] v_out[k]
+    // - T_final * v_alpha_out, the output gradients and the last composited index (-1 = nothing composited)
+    float T[PX], bsum[PX], v_out[PX][D];
+    int32_t bin_final[PX];
+    int wmax = -1;
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        const int i = i0 + (k >> 1) * 4, j = j0 + (k & 1) * 8;
+        T[k] = 1.0f;
+        bsum[k] = 0.0f;
+        bin_final[k] = -1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) v_out[k][d] = 0.0f;
+        if (i < p.height && j < p.width) {
+            const int64_t pix = ((int64_t)cam * p.height + i) * p.width + j;
+            const float alpha_out = p.alphas[pix];
+            const float T_final = 1.0f - alpha_out;
+            T[k] = T_final;
+            if (T_final < 1.0f) bin_final[k] = p.last_ids[pix];
+            if (D == 4) {
+                const float4 v = reinterpret_cast<const float4*>(p.v_render)[pix];
+                v_out[k][0] = v.x;
+                v_out[k][1] = v.y;
+                v_out[k][2] = v.z;
+                v_out[k][3] = v.w;
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) v_out[k][d] = p.v_render[pix * D + d];
+            }
+            float v_alpha_out = p.v_alphas ? p.v_alphas[pix] : 0.0f;
+            if (p.normalize_last) {
+                // out_last = raw_last / max(alpha,1e-10)  (raw includes the background term)
+                const float denom = fmaxf(alpha_out, 1e-10f);
+                const float out_last = p.render[pix * D + D - 1];
+                const float g = v_out[k][D - 1];
+                v_out[k][D - 1] = g / denom;
+                if (alpha_out > 1e-10f) v_alpha_out += -g * out_last / denom;
+            }
+            if (p.backgrounds) {
+                // render = acc + T_final * bg  ->  d/dalpha_out of the bg term is -bg
+                float s = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) s += p.backgrounds[cam * D + d] * v_out[k][d];
+                v_alpha_out -= s;
+            }
+            bsum[k] = -T_final * v_alpha_out;
+        }
+        wmax = max(wmax, bin_final[k]);
+    }
+
+    // per-sub-rectangle, warp-wide and CTA-wide last contributing index
+    int sub_max[PX];
+    int want = 0;
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        int m = bin_final[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        sub_max[k] = m;
+        if (m >= 0) want |= 1 << k;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) s_max_last[warp] = wmax;
+    if (lane == 0) sm.max_last[warp] = wmax;
     __syncthreads();
     int cta_max = -1;
 #pragma unroll
-    for (int w = 0; w < kRasterThreads / 32; ++w) cta_max = max(cta_max, s_max_last[w]);
+    for (int w = 0; w < S::kWarps; ++w) cta_max = max(cta_max, sm.max_last[w]);
     if (cta_max < 0) return;
-    const int warp_max = wmax;
 
     // walk the range back to front: batch entries in descending sorted index
-    for (int64_t b1 = (int64_t)cta_max + 1; b1 > range_start; b1 -= kBatch) {
+    for (int64_t b1 = (int64_t)cta_max + 1; b1 > range_start; b1 -= S::kThreads) {
         const int64_t e = b1 - 1 - threadIdx.x;
-        const int count = stage_batch<D, CULL, STATS>(p, sb, e >= range_start, e, tx0, ty0, tx1, ty1, st);
+        const int count = stage_batch<D, PX, CULL, STATS>(p, sm, e >= range_start, e, tx0, ty0, tx1, ty1, st);
         for (int c0 = 0; c0 < count; c0 += 32) {
-            uint32_t cand;
-            {
-                const int q = c0 + lane;
-                bool hit = false;
-                if (q < count && warp_has_pixels && sb.sid[q] <= warp_max) {
-                    if (CULL) {
-                        const float4 A = sb.ga[q], B = sb.gb[q];
-                        hit = ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, A.w, wx0, wy0, wx1, wy1);
-                    } else {
-                        hit = true;
-                    }
+            const int nq = fill_queue<PX, CULL, true>(sm, c0, count, sr, want, sub_max);
+            for (int q = 0; q < nq; ++q) {
+                const float4 A = sm.qa[warp][q], B = sm.qb[warp][q], Cc = sm.qc[warp][q];
+                const int mask = sm.qm[warp][q];
+                if (lane == 0) st.add(2, __popc(mask));
+                const int sid = __float_as_int(A.w);
+                float dx[S::kNX], ax[S::kNX], dy[S::kNY], cy[S::kNY];
+#pragma unroll
+                for (int a = 0; a < S::kNX; ++a) {
+                    dx[a] = A.x - (px0 + 8.0f * a);
+                    ax[a] = B.x * dx[a];
                 }
-                cand = __ballot_sync(0xffffffffu, hit);
-            }
-            if (lane == 0) st.add(2, __popc(cand));
-            while (cand) {
-                const int q = c0 + __ffs(cand) - 1;
-                cand &= cand - 1;
-                const float4 A = sb.ga[q], B = sb.gb[q];
-                const float dx = A.x - px, dy = A.y - py;
-                const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
-                const float vis = __expf(-sigma);
-                const float opac_vis = A.z * vis;
-                const float alpha = fminf(kMaxAlpha, opac_vis);
-                const bool valid = (sb.sid[q] <= bin_final) && (sigma >= 0.0f) && (alpha >= kAlphaThreshold);
-                st.add(3, (sb.sid[q] <= bin_final) ? 1 : 0);
-                st.add(4, valid ? 1 : 0);
-                if (!__any_sync(0xffffffffu, valid)) continue;
+#pragma unroll
+                for (int b = 0; b < S::kNY; ++b) {
+                    dy[b] = A.y - (py0 + 4.0f * b);
+                    cy[b] = fmaf(B.z * dy[b], dy[b], A.z);
+                }
+                // lane-local sums over this lane's PX pixels.  Slots (before the per-slot scale applied
+                // after the reduction): 0,1 g*ux, g*uy | 2,3 |.| | 4,5,6 g dx^2, g dx dy, g dy^2 | 7 g |
+                // 8.. fac * v_out, with g = alpha_raw * v_alpha, ux = 2 qa dx + qb dy, uy = qb dx + 2 qc dy
+                float v[12];
+#pragma unroll
+                for (int s = 0; s < 12; ++s) v[s] = 0.0f;
+                bool any_valid = false;
+#pragma unroll
+                for (int k = 0; k < PX; ++k) {
+                    if (PX > 1 && !((mask >> k) & 1)) continue;  // warp-uniform
+                    const int a = k & 1, b = k >> 1;
+                    const float pw = fmaf(fmaf(B.y, dy[b], ax[a]), dx[a], cy[b]);
+                    const float alpha_raw = ex2_approx(pw);
+                    const float alpha = fminf(kMaxAlpha, alpha_raw);
+                    const bool valid = (sid <= bin_final[k]) && (pw <= A.z) && (alpha >= kAlphaThreshold);
+                    st.add(3, (sid <= bin_final[k]) ? 1 : 0);
+                    st.add(4, valid ? 1 : 0);
+                    any_valid |= valid;
+                    const float ra = rcp_approx(1.0f - alpha);
+                    const float Tn = valid ? T[k] * ra : T[k];  // transmittance in front of this Gaussian
+                    const float fac = valid ? alpha * Tn : 0.0f;
+                    float s1 = Cc.x * v_out[k][0];
+                    v[8] = fmaf(fac, v_out[k][0], v[8]);
+                    if (D >= 3) {
+                        s1 = fmaf(Cc.y, v_out[k][1], s1);
+                        s1 = fmaf(Cc.z, v_out[k][2], s1);
+                        v[9] = fmaf(fac, v_out[k][1], v[9]);
+                        v[10] = fmaf(fac, v_out[k][2], v[10]);
+                    }
+                    if (D == 4) {
+                        s1 = fmaf(Cc.w, v_out[k][3], s1);
+                        v[11] = fmaf(fac, v_out[k][3], v[11]);
+                    }
+                    const float v_alpha = fmaf(Tn, s1, -ra * bsum[k]);
+                    bsum[k] = fmaf(fac, s1, bsum[k]);
+                    T[k] = Tn;
+                    const float g = (valid && alpha_raw <= kMaxAlpha) ? alpha_raw * v_alpha : 0.0f;
+                    const float ux = fmaf(2.0f * B.x, dx[a], B.y * dy[b]);
+                    const float uy = fmaf(2.0f * B.z, dy[b], B.y * dx[a]);
+                    const float gx = g * ux, gy = g * uy;
+                    v[0] += gx;
+                    v[1] += gy;
+                    v[2] += fabsf(gx);
+                    v[3] += fabsf(gy);
+                    const float gdx = g * dx[a], gdy = g * dy[b];
+                    v[4] = fmaf(gdx, dx[a], v[4]);
+                    v[5] = fmaf(gdx, dy[b], v[5]);
+                    v[6] = fmaf(gdy, dy[b], v[6]);
+                    v[7] += g;
+                }
+                if (!__any_sync(0xffffffffu, any_valid)) continue;
                 if (lane == 0) st.add(5, 1);
-                float v[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = 0.0f;
-                if (valid) {
-                    const float ra = 1.0f / (1.0f - alpha);
-                    T *= ra;
-                    const float fac = alpha * T;
-                    float v_alpha = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const float ck = sb.col[q][k];
-                        v[8 + k] = fac * v_out[k];
-                        v_alpha += (ck * T - buffer[k] * ra) * v_out[k];
-                        buffer[k] += ck * fac;
-                    }
-                    v_alpha += T_final * ra * v_alpha_out;
-                    if (opac_vis <= kMaxAlpha) {
-                        const float v_sigma = -opac_vis * v_alpha;
-                        v[4] = 0.5f * v_sigma * dx * dx;
-                        v[5] = v_sigma * dx * dy;
-                        v[6] = 0.5f * v_sigma * dy * dy;
-                        const float gx = v_sigma * (B.x * dx + B.y * dy);
-                        const float gy = v_sigma * (B.y * dx + B.z * dy);
-                        v[0] = gx;
-                        v[1] = gy;
-                        v[2] = fabsf(gx);
-                        v[3] = fabsf(gy);
-                        v[7] = vis * v_alpha;
-                    }
-                }
-                const float r = warp_reduce_transpose16(v, lane);
-                const int slot = lane >> 1;
-                if ((lane & 1) == 0 && slot < 8 + D) {
-                    const int64_t g = __float_as_int(B.w);
-                    atomicAdd(p.packed_grads + g * kGradFloats + slot, r);
+                const float r = warp_reduce_transpose12(v, lane);
+                const float inv_opac = ex2_approx(-A.z);
+                if (slot_active) {
+                    const float scale = (slot == 7) ? inv_opac : slot_scale;
+                    atomicAdd(p.packed_grads + (int64_t)__float_as_int(B.w) * kGradFloats + slot, r * scale);
                 }
             }
         }
@@ -500,35 +625,43 @@ __global__ void unpack_grads_kernel(int64_t CN, int D, const float4* __restrict_
     }
 }
 
-static int g_raster_cull = 1;  // test hook: 0 disables the culling (bit-identical results, slower)
-static unsigned long long* g_raster_counters = nullptr;  // instrumentation hook: device uint64[6] or null
+// test / instrumentation hooks (process-global; not part of the reference surface)
+static int g_raster_cull = 1;                           // 0 disables the culling (identical results, slower)
+static unsigned long long* g_raster_counters = nullptr;  // device uint64[6] -> STATS kernels
+static int g_px_fwd = 1, g_px_bwd = 4;                   // pixels per lane
 
-template <int D>
-static int launch_raster(RasterParams p, bool backward, cudaStream_t stream) {
+template <int D, int PX, bool BWD>
+static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
     dim3 grid(p.tile_w, p.tile_h, p.C);
-    p.counters = g_raster_counters;
-    if (g_raster_counters) {  // instrumented variant (never used in timed regions)
-        if (!backward) {
-            if (g_raster_cull)
-                raster_fwd_kernel<D, true, true><<<grid, kRasterThreads, 0, stream>>>(p);
-            else
-                raster_fwd_kernel<D, false, true><<<grid, kRasterThreads, 0, stream>>>(p);
+    constexpr int T = Shape<PX>::kThreads;
+    const bool cull = g_raster_cull != 0, stats = p.counters != nullptr;
+    if (!BWD) {
+        if (stats) {
+            if (cull) raster_fwd_kernel<D, PX, true, true><<<grid, T, 0, stream>>>(p);
+            else raster_fwd_kernel<D, PX, false, true><<<grid, T, 0, stream>>>(p);
         } else {
-            if (g_raster_cull)
-                raster_bwd_kernel<D, true, true><<<grid, kRasterThreads, 0, stream>>>(p);
-            else
-                raster_bwd_kernel<D, false, true><<<grid, kRasterThreads, 0, stream>>>(p);
+            if (cull) raster_fwd_kernel<D, PX, true, false><<<grid, T, 0, stream>>>(p);
+            else raster_fwd_kernel<D, PX, false, false><<<grid, T, 0, stream>>>(p);
         }
-    } else if (!backward) {
-        if (g_raster_cull)
-            raster_fwd_kernel<D, true, false><<<grid, kRasterThreads, 0, stream>>>(p);
-        else
-            raster_fwd_kernel<D, false, false><<<grid, kRasterThreads, 0, stream>>>(p);
     } else {
-        if (g_raster_cull)
-            raster_bwd_kernel<D, true, false><<<grid, kRasterThreads, 0, stream>>>(p);
-        else
-            raster_bwd_kernel<D, false, false><<<grid, kRasterThreads, 0, stream>>>(p);
+        if (stats) {
+            if (cull) raster_bwd_kernel<D, PX, true, true><<<grid, T, 0, stream>>>(p);
+            else raster_bwd_kernel<D, PX, false, true><<<grid, T, 0, stream>>>(p);
+        } else {
+            if (cull) raster_bwd_kernel<D, PX, true, false><<<grid, T, 0, stream>>>(p);
+            else raster_bwd_kernel<D, PX, false, false><<<grid, T, 0, stream>>>(p);
+        }
+    }
+}
+
+template <int D, bool BWD>
+static int launch_raster(RasterParams p, cudaStream_t stream) {
+    p.counters = g_raster_counters;
+    const int px = BWD ? g_px_bwd : g_px_fwd;
+    switch (px) {
+        case 1: launch_raster_px<D, 1, BWD>(p, stream); break;
+        case 2: launch_raster_px<D, 2, BWD>(p, stream); break;
+        default: launch_raster_px<D, 4, BWD>(p, stream); break;
     }
     QED_LAUNCH_CHECK();
     return QED_OK;
@@ -544,33 +677,9 @@ static int check_raster_args(int C, int N, int64_t n_isects, int D, int width, i
     return QED_OK;
 }
 
-}  // namespace qed
-
-using namespace qed;
-
-// test hook (not part of the reference surface): toggles the exact culling
-extern "C" int qed_debug_set_raster_cull(int enabled) {
-    int old = g_raster_cull;
-    g_raster_cull = enabled ? 1 : 0;
-    return old;
-}
-
-// instrumentation hook (not part of the reference surface): counters = device uint64[6] or NULL
-extern "C" int qed_debug_set_raster_counters(void* counters) {
-    g_raster_counters = reinterpret_cast<unsigned long long*>(counters);
-    return QED_OK;
-}
-
-extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
-                              const float* backgrounds, int width, int height, int tile_size, int tile_width,
-                              int tile_height, const int32_t* isect_offsets, const int32_t* flatten_ids,
-                              int normalize_last, float* render, float* alphas, int32_t* last_ids, qed_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    int rc = check_raster_args(C, N, n_isects, D, width, height, tile_size, tile_width, tile_height);
-    if (rc != QED_OK) return rc;
-    if (C == 0) return QED_OK;
-    if (!isect_offsets || !render || !alphas || !last_ids) return QED_ERR_BAD_ARG;
-    if (n_isects > 0 && (!geom || !colors || !flatten_ids)) return QED_ERR_BAD_ARG;
+static RasterParams make_params(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors, const float* backgrounds,
+                                int width, int height, int tile_width, int tile_height, const int32_t* isect_offsets,
+                                const int32_t* flatten_ids, int normalize_last) {
     RasterParams p{};
     p.C = C;
     p.N = N;
@@ -586,13 +695,50 @@ extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float
     p.backgrounds = backgrounds;
     p.offsets = isect_offsets;
     p.flatten_ids = flatten_ids;
+    return p;
+}
+
+}  // namespace qed
+
+using namespace qed;
+
+extern "C" int qed_debug_set_raster_cull(int enabled) {
+    int old = g_raster_cull;
+    g_raster_cull = enabled ? 1 : 0;
+    return old;
+}
+
+extern "C" int qed_debug_set_raster_counters(void* counters) {
+    g_raster_counters = reinterpret_cast<unsigned long long*>(counters);
+    return QED_OK;
+}
+
+// pixels per lane of the forward / backward compositor (1, 2 or 4; 0 keeps the current value)
+extern "C" int qed_debug_set_raster_px(int px_fwd, int px_bwd) {
+    if (px_fwd == 1 || px_fwd == 2 || px_fwd == 4) g_px_fwd = px_fwd;
+    if (px_bwd == 1 || px_bwd == 2 || px_bwd == 4) g_px_bwd = px_bwd;
+    return g_px_fwd * 10 + g_px_bwd;
+}
+
+extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
+                              const float* backgrounds, int width, int height, int tile_size, int tile_width,
+                              int tile_height, const int32_t* isect_offsets, const int32_t* flatten_ids,
+                              int normalize_last, float* render, float* alphas, int32_t* last_ids, qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_raster_args(C, N, n_isects, D, width, height, tile_size, tile_width, tile_height);
+    if (rc != QED_OK) return rc;
+    if (C == 0) return QED_OK;
+    if (!isect_offsets || !render || !alphas || !last_ids) return QED_ERR_BAD_ARG;
+    if (n_isects > 0 && (!geom || !colors || !flatten_ids)) return QED_ERR_BAD_ARG;
+    RasterParams p = make_params(C, N, n_isects, D, geom, colors, backgrounds, width, height, tile_width, tile_height, isect_offsets,
+                                 flatten_ids, normalize_last);
     p.render = render;
     p.alphas = alphas;
     p.last_ids = last_ids;
     switch (D) {
-        case 1: return launch_raster<1>(p, false, stream);
-        case 3: return launch_raster<3>(p, false, stream);
-        default: return launch_raster<4>(p, false, stream);
+        case 1: return launch_raster<1, false>(p, stream);
+        case 3: return launch_raster<3, false>(p, stream);
+        default: return launch_raster<4, false>(p, stream);
     }
 }
 
@@ -607,21 +753,8 @@ extern "C" int qed_raster_bwd(int C, int N, int64_t n_isects, int D, const float
     if (C == 0 || n_isects == 0) return QED_OK;
     if (!isect_offsets || !render || !alphas || !last_ids || !v_render || !packed_grads || !geom || !colors || !flatten_ids)
         return QED_ERR_BAD_ARG;
-    RasterParams p{};
-    p.C = C;
-    p.N = N;
-    p.D = D;
-    p.width = width;
-    p.height = height;
-    p.tile_w = tile_width;
-    p.tile_h = tile_height;
-    p.normalize_last = normalize_last;
-    p.n_isects = n_isects;
-    p.geom = reinterpret_cast<const float4*>(geom);
-    p.colors = colors;
-    p.backgrounds = backgrounds;
-    p.offsets = isect_offsets;
-    p.flatten_ids = flatten_ids;
+    RasterParams p = make_params(C, N, n_isects, D, geom, colors, backgrounds, width, height, tile_width, tile_height, isect_offsets,
+                                 flatten_ids, normalize_last);
     p.render = const_cast<float*>(render);  // read-only in the backward kernel
     p.alphas = const_cast<float*>(alphas);
     p.last_ids = const_cast<int32_t*>(last_ids);
@@ -629,9 +762,9 @@ extern "C" int qed_raster_bwd(int C, int N, int64_t n_isects, int D, const float
     p.v_alphas = v_alphas;
     p.packed_grads = packed_grads;
     switch (D) {
-        case 1: return launch_raster<1>(p, true, stream);
-        case 3: return launch_raster<3>(p, true, stream);
-        default: return launch_raster<4>(p, true, stream);
+        case 1: return launch_raster<1, true>(p, stream);
+        case 3: return launch_raster<3, true>(p, stream);
+        default: return launch_raster<4, true>(p, stream);
     }
 }
 

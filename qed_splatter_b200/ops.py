@@ -312,3 +312,9 @@ def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opaciti
 def set_raster_cull(enabled: bool) -> bool:
     """Test hook: disable/enable the exact warp-level culling in the compositor (results are identical)."""
     return bool(_lib.load().qed_debug_set_raster_cull(int(enabled)))
+
+
+def set_raster_px(px_fwd: int = 0, px_bwd: int = 0) -> int:
+    """Test/tuning hook: pixels per lane (1, 2 or 4; 0 = keep) of the forward / backward compositor.
+    Returns 10*px_fwd + px_bwd now in effect."""
+    return int(_lib.load().qed_debug_set_raster_px(int(px_fwd), int(px_bwd)))
