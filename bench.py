@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--mode", default="RGB+ED", choices=["RGB+ED", "RGB+D"])
-    ap.add_argument("--sort", default="own", choices=["own", "cub"])
+    ap.add_argument("--sort", default="two_level", choices=["two_level", "own", "cub"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

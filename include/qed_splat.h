@@ -130,6 +130,25 @@ size_t qed_sort_pairs_cub_workspace_bytes(int64_t n);
 int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* keys_out, int32_t* vals_out,
                        int end_bit, void* workspace, size_t workspace_bytes, qed_stream_t stream);
 
+/* Two-level build of the same sorted intersection list (the product path; identical output to
+ * qed_isect_emit + qed_sort_pairs + qed_tile_ranges with ~5x less memory traffic):
+ *   prepare: ordered compaction of the visible (camera, Gaussian) entries, stable radix sort by
+ *            (camera, depth bits), scan of their tile counts in that order.
+ *            counts_dev[2] (int64, device) = {n_visible, n_isects}; also copied asynchronously to
+ *            counts_host_pinned[2] when non-NULL (the caller reads it after a stream sync to size outputs).
+ *   fill:    warp-cooperative coalesced emission of (camera|tile, flat index) in depth order, stable radix
+ *            sort on the camera|tile bits only, then isect_ids = key << 32 | bits(depth) and the per-tile
+ *            ranges (isect_offsets may be NULL to skip them).
+ * `prepare_workspace` must be the buffer qed_isect_prepare filled for the same (C, N). */
+size_t qed_isect_prepare_workspace_bytes(int64_t CN);
+int qed_isect_prepare(int C, int N, const float* depths, const int32_t* tiles_per_gauss, void* workspace,
+                      size_t workspace_bytes, int64_t* counts_dev, int64_t* counts_host_pinned, qed_stream_t stream);
+size_t qed_isect_fill_workspace_bytes(int64_t n_isects);
+int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects, const float* means2d, const int32_t* radii,
+                   const float* depths, int tile_size, int tile_width, int tile_height, const void* prepare_workspace,
+                   void* workspace, size_t workspace_bytes, int64_t* isect_ids, int32_t* flatten_ids,
+                   int32_t* isect_offsets, qed_stream_t stream);
+
 /* isect_offsets[C*tile_height*tile_width] i32: first sorted index of each (camera,tile); empty tiles get
  * the start of the next non-empty one; tiles after the last entry get n_isects. */
 int qed_tile_ranges(int64_t n_isects, const int64_t* isect_ids_sorted, int C, int tile_width, int tile_height,

@@ -8,6 +8,8 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "common.cuh"
+#include "radix.cuh"
+#include "scan.cuh"
 
 namespace qed {
 
@@ -26,95 +28,6 @@ __global__ void isect_count_kernel(int64_t CN, const float2* __restrict__ means2
         cnt = (tb.x1 - tb.x0) * (tb.y1 - tb.y0);
     }
     tiles[i] = cnt;
-}
-
-// ------------------------------------------------------------------------------------------------
-// inclusive scan int32 -> int64, three phases (reduce / scan of block sums / scan + add)
-// ------------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
-__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t* smem_warp, int64_t& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) smem_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        int64_t w = lane < (kScanThreads / 32) ? smem_warp[lane] : 0;
-        int64_t winc = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int64_t t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        if (lane < (kScanThreads / 32)) smem_warp[lane] = winc - w;
-        if (lane == (kScanThreads / 32) - 1) smem_warp[kScanThreads / 32] = winc;
-    }
-    __syncthreads();
-    total = smem_warp[kScanThreads / 32];
-    int64_t res = smem_warp[warp] + inc - v;
-    __syncthreads();
-    return res;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(int64_t n, const int32_t* __restrict__ in, int64_t* __restrict__ block_sums) {
-    __shared__ int64_t sw[kScanThreads / 32 + 1];
-    int64_t base = (int64_t)blockIdx.x * kScanTile;
-    int64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        int64_t i = base + k * kScanThreads + threadIdx.x;
-        if (i < n) s += in[i];
-    }
-    int64_t total;
-    block_exclusive_scan(s, sw, total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-}
-
-// single block: exclusive scan of block sums in place; writes grand total
-__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int64_t nb, int64_t* __restrict__ block_sums, int64_t* __restrict__ total_dev,
-                                                                int64_t* __restrict__ total_host) {
-    __shared__ int64_t sw[kScanThreads / 32 + 1];
-    int64_t carry = 0;
-    for (int64_t base = 0; base < nb; base += kScanThreads) {
-        int64_t i = base + threadIdx.x;
-        int64_t v = i < nb ? block_sums[i] : 0;
-        int64_t total;
-        int64_t ex = block_exclusive_scan(v, sw, total);
-        if (i < nb) block_sums[i] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) {
-        *total_dev = carry;
-        if (total_host) *total_host = carry;
-    }
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_final_kernel(int64_t n, const int32_t* __restrict__ in, const int64_t* __restrict__ block_sums,
-                                                                 int64_t* __restrict__ out) {
-    __shared__ int64_t sw[kScanThreads / 32 + 1];
-    // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems) of the tile
-    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
-    int32_t v[kScanItems];
-    int64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        v[k] = (base + k < n) ? in[base + k] : 0;
-        s += v[k];
-    }
-    int64_t total;
-    int64_t ex = block_exclusive_scan(s, sw, total) + block_sums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        ex += v[k];
-        if (base + k < n) out[base + k] = ex;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -165,152 +78,6 @@ __global__ void tile_ranges_kernel(int64_t n_isects, const int64_t* __restrict__
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// own LSD radix sort (8-bit digits): per pass  upsweep histogram -> digit-major scan -> downsweep
-// (block-local stable rank via __match_any_sync, block-sorted staging in smem, coalesced run writes)
-// ------------------------------------------------------------------------------------------------
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs per block
-constexpr int kRadix = 256;
-
-__global__ void __launch_bounds__(kSortThreads) sort_upsweep_kernel(int64_t n, const uint64_t* __restrict__ keys, int shift, int nblocks,
-                                                                   uint32_t* __restrict__ hist /* [kRadix][nblocks] */) {
-    __shared__ uint32_t sh[kRadix];
-    sh[threadIdx.x] = 0;
-    __syncthreads();
-    int64_t base = (int64_t)blockIdx.x * kSortTile;
-#pragma unroll 4
-    for (int k = 0; k < kSortItems; ++k) {
-        int64_t i = base + k * kSortThreads + threadIdx.x;
-        if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (kRadix - 1)], 1u);
-    }
-    __syncthreads();
-    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
-}
-
-// exclusive scan over the digit-major [kRadix*nblocks] histogram, single block
-__global__ void __launch_bounds__(kScanThreads) sort_scan_kernel(int64_t total, uint32_t* __restrict__ hist) {
-    __shared__ int64_t sw[kScanThreads / 32 + 1];
-    int64_t carry = 0;
-    for (int64_t base = 0; base < total; base += (int64_t)kScanThreads * 4) {
-        int64_t i0 = base + (int64_t)threadIdx.x * 4;
-        uint32_t v[4];
-        int64_t s = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[k] = (i0 + k < total) ? hist[i0 + k] : 0u;
-            s += v[k];
-        }
-        int64_t tot;
-        int64_t ex = block_exclusive_scan(s, sw, tot) + carry;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < total) hist[i0 + k] = (uint32_t)ex;
-            ex += v[k];
-        }
-        carry += tot;
-    }
-}
-
-__global__ void __launch_bounds__(kSortThreads) sort_downsweep_kernel(int64_t n, const uint64_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
-                                                                     uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int shift,
-                                                                     int nblocks, const uint32_t* __restrict__ hist) {
-    constexpr int kWarps = kSortThreads / 32;
-    constexpr int kPerWarp = kSortTile / kWarps;  // 512 consecutive pairs per warp
-    constexpr int kRounds = kPerWarp / 32;        // 16
-    extern __shared__ __align__(16) unsigned char sort_smem[];
-    uint64_t* skeys = reinterpret_cast<uint64_t*>(sort_smem);                      // [kSortTile]
-    int32_t* svals = reinterpret_cast<int32_t*>(skeys + kSortTile);                // [kSortTile]
-    uint32_t(*warp_hist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(svals + kSortTile);  // [kWarps][kRadix]
-    uint32_t* digit_start = &warp_hist[0][0] + kWarps * kRadix;  // start of each digit's run inside the block-sorted tile
-    uint32_t* global_base = digit_start + kRadix;                // global output index of the run's first element
-    uint32_t* sscan = global_base + kRadix;                      // [kWarps + 1]
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * kSortTile;
-    const int tile_n = (n - base) < kSortTile ? (int)(n - base) : kSortTile;
-
-    for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
-    __syncthreads();
-
-    uint64_t key[kRounds];
-    uint16_t rank[kRounds];
-    // phase A: stable rank inside the warp's 512-pair sub-chunk
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        const int local = warp * kPerWarp + r * 32 + lane;
-        const bool valid = local < tile_n;
-        key[r] = valid ? keys_in[base + local] : ~0ull;
-        const uint32_t d = valid ? (uint32_t)((key[r] >> shift) & (kRadix - 1)) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) {
-            old = warp_hist[warp][d];
-            warp_hist[warp][d] = old + __popc(peers);
-        }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[r] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
-        __syncwarp();
-    }
-    __syncthreads();
-    // phase B: thread d: exclusive prefix over warps, block count; then exclusive scan over digits
-    {
-        const int d = threadIdx.x;
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            uint32_t c = warp_hist[w][d];
-            warp_hist[w][d] = run;
-            run += c;
-        }
-        // exclusive scan of `run` over the 256 digits
-        uint32_t inc = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) sscan[warp] = inc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t acc = 0;
-            for (int w = 0; w < kWarps; ++w) {
-                uint32_t t = sscan[w];
-                sscan[w] = acc;
-                acc += t;
-            }
-        }
-        __syncthreads();
-        digit_start[d] = sscan[warp] + inc - run;
-        global_base[d] = hist[(int64_t)d * nblocks + blockIdx.x];
-    }
-    __syncthreads();
-    // phase C: place into block-sorted order in smem
-#pragma unroll
-    for (int r = 0; r < kRounds; ++r) {
-        const int local = warp * kPerWarp + r * 32 + lane;
-        if (local < tile_n) {
-            const uint32_t d = (uint32_t)((key[r] >> shift) & (kRadix - 1));
-            const uint32_t pos = digit_start[d] + warp_hist[warp][d] + rank[r];
-            skeys[pos] = key[r];
-            svals[pos] = vals_in[base + local];
-        }
-    }
-    __syncthreads();
-    // phase D: coalesced run writes
-    for (int i = threadIdx.x; i < tile_n; i += kSortThreads) {
-        const uint64_t k = skeys[i];
-        const uint32_t d = (uint32_t)((k >> shift) & (kRadix - 1));
-        const int64_t dst = (int64_t)global_base[d] + (i - digit_start[d]);
-        keys_out[dst] = k;
-        vals_out[dst] = svals[i];
-    }
-}
-
-constexpr size_t kSortSmemBytes = (size_t)kSortTile * 12 + (size_t)(kSortThreads / 32) * kRadix * 4 + 2 * kRadix * 4 + (kSortThreads / 32 + 1) * 4;
-
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace qed
@@ -330,10 +97,7 @@ extern "C" int qed_isect_count(int C, int N, const float* means2d, const int32_t
     return QED_OK;
 }
 
-extern "C" size_t qed_isect_scan_workspace_bytes(int64_t n) {
-    int64_t nb = (n + kScanTile - 1) / kScanTile;
-    return (size_t)(nb > 0 ? nb : 1) * sizeof(int64_t);
-}
+extern "C" size_t qed_isect_scan_workspace_bytes(int64_t n) { return scan_workspace_bytes(n); }
 
 extern "C" int qed_isect_scan(int64_t n, const int32_t* tiles_per_gauss, int64_t* cum, int64_t* n_isects_dev,
                               int64_t* n_isects_host_pinned, void* workspace, size_t workspace_bytes, qed_stream_t stream_) {
@@ -341,19 +105,12 @@ extern "C" int qed_isect_scan(int64_t n, const int32_t* tiles_per_gauss, int64_t
     if (n < 0 || !n_isects_dev) return QED_ERR_BAD_ARG;
     if (n == 0) {
         QED_CUDA_TRY(cudaMemsetAsync(n_isects_dev, 0, sizeof(int64_t), stream));
-        if (n_isects_host_pinned) QED_CUDA_TRY(cudaMemcpyAsync(n_isects_host_pinned, n_isects_dev, 8, cudaMemcpyDeviceToHost, stream));
-        return QED_OK;
+    } else {
+        if (!tiles_per_gauss || !cum || !workspace) return QED_ERR_BAD_ARG;
+        if (workspace_bytes < scan_workspace_bytes(n)) return QED_ERR_WORKSPACE;
+        int rc = scan_inclusive(n, nullptr, ScanIdentity{tiles_per_gauss}, cum, n_isects_dev, workspace, stream);
+        if (rc != QED_OK) return rc;
     }
-    if (!tiles_per_gauss || !cum || !workspace) return QED_ERR_BAD_ARG;
-    if (workspace_bytes < qed_isect_scan_workspace_bytes(n)) return QED_ERR_WORKSPACE;
-    int64_t nb = (n + kScanTile - 1) / kScanTile;
-    int64_t* sums = reinterpret_cast<int64_t*>(workspace);
-    scan_reduce_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(n, tiles_per_gauss, sums);
-    QED_LAUNCH_CHECK();
-    scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(nb, sums, n_isects_dev, nullptr);
-    QED_LAUNCH_CHECK();
-    scan_final_kernel<<<(unsigned)nb, kScanThreads, 0, stream>>>(n, tiles_per_gauss, sums, cum);
-    QED_LAUNCH_CHECK();
     if (n_isects_host_pinned) QED_CUDA_TRY(cudaMemcpyAsync(n_isects_host_pinned, n_isects_dev, 8, cudaMemcpyDeviceToHost, stream));
     return QED_OK;
 }
@@ -421,8 +178,7 @@ extern "C" int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in,
 // ---- own radix sort ----
 extern "C" size_t qed_sort_pairs_workspace_bytes(int64_t n) {
     if (n <= 0) return 256;
-    int64_t nb = (n + kSortTile - 1) / kSortTile;
-    return align_up((size_t)n * 8, 256) + align_up((size_t)n * 4, 256) + align_up((size_t)kRadix * nb * 4, 256);
+    return align_up((size_t)n * 8, 256) + align_up((size_t)n * 4, 256) + radix_hist_bytes(n);
 }
 
 extern "C" int qed_sort_pairs(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* keys_out, int32_t* vals_out,
@@ -433,34 +189,256 @@ extern "C" int qed_sort_pairs(int64_t n, int64_t* keys_in, int32_t* vals_in, int
     if (n > 0x7fffffffLL) return QED_ERR_UNSUPPORTED;
     if (!keys_in || !vals_in || !keys_out || !vals_out || !workspace) return QED_ERR_BAD_ARG;
     if (workspace_bytes < qed_sort_pairs_workspace_bytes(n)) return QED_ERR_WORKSPACE;
-    const int nb = (int)((n + kSortTile - 1) / kSortTile);
     char* ws = reinterpret_cast<char*>(workspace);
     uint64_t* tmp_keys = reinterpret_cast<uint64_t*>(ws);
     int32_t* tmp_vals = reinterpret_cast<int32_t*>(ws + align_up((size_t)n * 8, 256));
-    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + align_up((size_t)n * 8, 256) + align_up((size_t)n * 4, 256));
-    const int passes = (end_bit + 7) / 8;
-    if (passes == 0) {
-        QED_CUDA_TRY(cudaMemcpyAsync(keys_out, keys_in, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream));
-        QED_CUDA_TRY(cudaMemcpyAsync(vals_out, vals_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+    void* hist = ws + align_up((size_t)n * 8, 256) + align_up((size_t)n * 4, 256);
+    return radix_sort_pairs<uint64_t>(n, nullptr, reinterpret_cast<const uint64_t*>(keys_in), vals_in, reinterpret_cast<uint64_t*>(keys_out),
+                                      vals_out, tmp_keys, tmp_vals, hist, end_bit, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two-level intersection build (the product path).  Same output as emit + 64-bit sort + ranges, with ~5x
+// less memory traffic:
+//   prepare: compact the visible (camera, Gaussian) entries in flat-index order, radix sort them by
+//            (camera, depth bits) (stable, so equal depths keep ascending flat index), scan their tile
+//            counts in that order -> write offsets + n_isects.
+//   fill:    emit (camera|tile, flat index) in depth order, warp-cooperatively and coalesced, then a stable
+//            radix sort on the camera|tile bits only (2 passes for <= 16 bits).  Within a tile the depth
+//            order survives, which is exactly the order of the reference's 64-bit key sort.
+// ------------------------------------------------------------------------------------------------
+namespace qed {
+
+struct PrepareLayout {
+    size_t scan_ws, cumflag, keys[3], vals[3], hist, cum2, total;
+};
+
+static PrepareLayout prepare_layout(int64_t CN) {
+    PrepareLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += align_up(bytes, 256);
+        return r;
+    };
+    L.scan_ws = take(scan_workspace_bytes(CN));
+    L.cumflag = take((size_t)CN * 8);
+    for (int i = 0; i < 3; ++i) L.keys[i] = take((size_t)CN * 8);
+    for (int i = 0; i < 3; ++i) L.vals[i] = take((size_t)CN * 4);
+    L.hist = take(radix_hist_bytes(CN));
+    L.cum2 = take((size_t)CN * 8);
+    L.total = o;
+    return L;
+}
+
+template <typename KeyT>
+__global__ void compact_visible_kernel(int64_t CN, int N, const int32_t* __restrict__ tiles, const int64_t* __restrict__ cumflag,
+                                       const float* __restrict__ depths, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= CN) return;
+    if (tiles[idx] <= 0) return;
+    const int64_t j = cumflag[idx] - 1;
+    const uint32_t db = (uint32_t)__float_as_int(depths[idx]);
+    if (sizeof(KeyT) == 8)
+        keys[j] = (KeyT)(((uint64_t)(idx / N) << 32) | db);
+    else
+        keys[j] = (KeyT)db;
+    vals[j] = (int32_t)idx;
+}
+
+// Entry-parallel emission in depth order.  Every block owns kEmitTile consecutive OUTPUT entries, so the
+// work is balanced no matter how the tile counts are distributed (the nearest Gaussians are adjacent in
+// depth order and can cover thousands of tiles each).  The block finds the Gaussians overlapping its entry
+// range by binary search in cum2, stages their (first tile, box width, flat index, start offset) in shared
+// memory, and every entry then finds its Gaussian by a binary search in that shared slice.
+constexpr int kEmitThreads = 256;
+constexpr int kEmitTile = 2048;
+
+// first_j[b] = index (in depth order) of the Gaussian that owns output entry b * kEmitTile
+__global__ void emit_boundaries_kernel(int64_t n_vis, const int64_t* __restrict__ cum2, int32_t* __restrict__ first_j) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_vis) return;
+    const int64_t start = j > 0 ? cum2[j - 1] : 0, end = cum2[j];
+    for (int64_t b = (start + kEmitTile - 1) / kEmitTile; b * kEmitTile < end; ++b) first_j[b] = (int32_t)j;
+}
+
+__global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis, int64_t n_isects, int N, const int32_t* __restrict__ sorted_vals,
+                                                                  const int64_t* __restrict__ cum2, const int32_t* __restrict__ first_j,
+                                                                  const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
+                                                                  float tile_size, int tile_w, int tile_h, int tile_n_bits,
+                                                                  uint32_t* __restrict__ tkeys, int32_t* __restrict__ tvals) {
+    __shared__ int32_t s_end[kEmitTile + 1];    // cum2[j] - e0 (inclusive end offsets relative to the block)
+    __shared__ int32_t s_first[kEmitTile + 1];  // first tile id (y0 * tile_w + x0) of the Gaussian's box
+    __shared__ int32_t s_bw[kEmitTile + 1];
+    __shared__ int32_t s_idx[kEmitTile + 1];
+    const int64_t e0 = (int64_t)blockIdx.x * kEmitTile;
+    const int64_t e1 = min(e0 + kEmitTile, n_isects);
+    const int64_t j0 = first_j[blockIdx.x];
+    int64_t j1;  // Gaussian that owns entry e1 - 1
+    if (e1 >= n_isects) {
+        j1 = n_vis - 1;
+    } else {
+        const int64_t jn = first_j[blockIdx.x + 1];  // owns entry e1
+        j1 = (cum2[jn - (jn > 0 ? 1 : 0)] == e1 && jn > 0) ? jn - 1 : jn;  // jn starts exactly at e1 -> previous one owns e1-1
+    }
+    const int G = (int)(j1 - j0) + 1;  // every Gaussian has >= 1 entry, so G <= kEmitTile
+    for (int g = threadIdx.x; g < G; g += kEmitThreads) {
+        const int64_t j = j0 + g;
+        const int idx = sorted_vals[j];
+        const float2 m = means2d[idx];
+        const TileBox tb = tile_box(m.x, m.y, radii[idx], tile_size, tile_w, tile_h);
+        s_end[g] = (int32_t)(min(cum2[j], e1) - e0);
+        s_first[g] = tb.y0 * tile_w + tb.x0;
+        s_bw[g] = tb.x1 - tb.x0;
+        s_idx[g] = idx;
+    }
+    __syncthreads();
+    const int64_t start0 = j0 > 0 ? cum2[j0 - 1] : 0;  // global start offset of the first overlapping Gaussian
+    for (int e = threadIdx.x; e < (int)(e1 - e0); e += kEmitThreads) {
+        // first g with s_end[g] > e
+        int lo = 0, hi = G - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_end[mid] > e) hi = mid; else lo = mid + 1;
+        }
+        const int64_t gstart = lo > 0 ? (int64_t)s_end[lo - 1] + e0 : start0;  // earlier ones end inside the block: exact
+        const int k = (int)(e0 + e - gstart);
+        const int bw = s_bw[lo];
+        const int ry = k / bw, rx = k - ry * bw;
+        const int idx = s_idx[lo];
+        tkeys[e0 + e] = ((uint32_t)(idx / N) << tile_n_bits) | (uint32_t)(s_first[lo] + ry * tile_w + rx);
+        tvals[e0 + e] = idx;
+    }
+}
+
+// isect_ids = key << 32 | bits(depth), fused with the per-tile ranges (same rule as tile_ranges_kernel)
+__global__ void compose_ids_ranges_kernel(int64_t n, const uint32_t* __restrict__ tkeys, const int32_t* __restrict__ flat,
+                                          const float* __restrict__ depths, int C, int n_tiles, int tile_n_bits,
+                                          int64_t* __restrict__ isect_ids, int32_t* __restrict__ offsets) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = tkeys[i];
+    const uint32_t db = (uint32_t)__float_as_int(depths[flat[i]]);
+    isect_ids[i] = (int64_t)(((uint64_t)key << 32) | db);
+    if (!offsets) return;
+    const uint32_t mask = (1u << tile_n_bits) - 1u;
+    const int64_t cur = (int64_t)(key >> tile_n_bits) * n_tiles + (key & mask);
+    if (i == 0) {
+        for (int64_t t = 0; t <= cur; ++t) offsets[t] = 0;
+    } else {
+        const uint32_t kp = tkeys[i - 1];
+        const int64_t prev = (int64_t)(kp >> tile_n_bits) * n_tiles + (kp & mask);
+        for (int64_t t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+    }
+    if (i == n - 1) {
+        for (int64_t t = cur + 1; t < (int64_t)C * n_tiles; ++t) offsets[t] = (int32_t)n;
+    }
+}
+
+static int bit_length(int64_t v) {
+    int b = 0;
+    while (((int64_t)1 << b) <= v) ++b;
+    return b;
+}
+
+}  // namespace qed
+
+extern "C" size_t qed_isect_prepare_workspace_bytes(int64_t CN) { return prepare_layout(CN > 0 ? CN : 1).total; }
+
+extern "C" int qed_isect_prepare(int C, int N, const float* depths, const int32_t* tiles_per_gauss, void* workspace,
+                                 size_t workspace_bytes, int64_t* counts_dev, int64_t* counts_host_pinned, qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (C < 0 || N < 0 || !counts_dev) return QED_ERR_BAD_ARG;
+    const int64_t CN = (int64_t)C * N;
+    if (CN == 0) {
+        QED_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, 16, stream));
+    } else {
+        if (CN > 0x7fffffffLL) return QED_ERR_UNSUPPORTED;
+        if (!depths || !tiles_per_gauss || !workspace) return QED_ERR_BAD_ARG;
+        const PrepareLayout L = prepare_layout(CN);
+        if (workspace_bytes < L.total) return QED_ERR_WORKSPACE;
+        char* ws = reinterpret_cast<char*>(workspace);
+        int64_t* cumflag = reinterpret_cast<int64_t*>(ws + L.cumflag);
+        int32_t* vals0 = reinterpret_cast<int32_t*>(ws + L.vals[0]);
+        int32_t* vals1 = reinterpret_cast<int32_t*>(ws + L.vals[1]);
+        int32_t* vals2 = reinterpret_cast<int32_t*>(ws + L.vals[2]);
+        int64_t* cum2 = reinterpret_cast<int64_t*>(ws + L.cum2);
+        // 1. ordered compaction of the visible entries (n_visible -> counts_dev[0])
+        int rc = scan_inclusive(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, cumflag, counts_dev, ws + L.scan_ws, stream);
+        if (rc != QED_OK) return rc;
+        const unsigned blocks = (unsigned)((CN + 255) / 256);
+        // 2. stable sort by (camera, depth bits); sorted flat indices land in vals1
+        if (C == 1) {
+            uint32_t* k0 = reinterpret_cast<uint32_t*>(ws + L.keys[0]);
+            uint32_t* k1 = reinterpret_cast<uint32_t*>(ws + L.keys[1]);
+            uint32_t* k2 = reinterpret_cast<uint32_t*>(ws + L.keys[2]);
+            compact_visible_kernel<uint32_t><<<blocks, 256, 0, stream>>>(CN, N, tiles_per_gauss, cumflag, depths, k0, vals0);
+            QED_LAUNCH_CHECK();
+            rc = radix_sort_pairs<uint32_t>(CN, counts_dev, k0, vals0, k1, vals1, k2, vals2, ws + L.hist, 32, stream);
+        } else {
+            uint64_t* k0 = reinterpret_cast<uint64_t*>(ws + L.keys[0]);
+            uint64_t* k1 = reinterpret_cast<uint64_t*>(ws + L.keys[1]);
+            uint64_t* k2 = reinterpret_cast<uint64_t*>(ws + L.keys[2]);
+            compact_visible_kernel<uint64_t><<<blocks, 256, 0, stream>>>(CN, N, tiles_per_gauss, cumflag, depths, k0, vals0);
+            QED_LAUNCH_CHECK();
+            rc = radix_sort_pairs<uint64_t>(CN, counts_dev, k0, vals0, k1, vals1, k2, vals2, ws + L.hist, 32 + bit_length(C - 1), stream);
+        }
+        if (rc != QED_OK) return rc;
+        // 3. tile counts in depth order -> write offsets, n_isects -> counts_dev[1]
+        rc = scan_inclusive(CN, counts_dev, ScanGather{tiles_per_gauss, vals1}, cum2, counts_dev + 1, ws + L.scan_ws, stream);
+        if (rc != QED_OK) return rc;
+    }
+    if (counts_host_pinned) QED_CUDA_TRY(cudaMemcpyAsync(counts_host_pinned, counts_dev, 16, cudaMemcpyDeviceToHost, stream));
+    return QED_OK;
+}
+
+extern "C" size_t qed_isect_fill_workspace_bytes(int64_t n_isects) {
+    if (n_isects <= 0) return 256;
+    return 5 * align_up((size_t)n_isects * 4, 256) + radix_hist_bytes(n_isects) +
+           align_up((size_t)((n_isects + kEmitTile - 1) / kEmitTile + 1) * 4, 256);
+}
+
+extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects, const float* means2d, const int32_t* radii,
+                              const float* depths, int tile_size, int tile_width, int tile_height, const void* prepare_workspace,
+                              void* workspace, size_t workspace_bytes, int64_t* isect_ids, int32_t* flatten_ids,
+                              int32_t* isect_offsets, qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (C < 0 || N < 0 || n_visible < 0 || n_isects < 0 || tile_size <= 0) return QED_ERR_BAD_ARG;
+    const int64_t CN = (int64_t)C * N;
+    const int n_tiles = tile_width * tile_height;
+    if (n_isects == 0 || CN == 0) {
+        if (isect_offsets && (int64_t)C * n_tiles > 0) QED_CUDA_TRY(cudaMemsetAsync(isect_offsets, 0, (size_t)C * n_tiles * 4, stream));
         return QED_OK;
     }
-    QED_CUDA_TRY(cudaFuncSetAttribute(sort_downsweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes));
-    const uint64_t* src_k = reinterpret_cast<const uint64_t*>(keys_in);
-    const int32_t* src_v = vals_in;
-    for (int pass = 0; pass < passes; ++pass) {
-        // last pass must land in *_out: destinations alternate out/tmp ending on out
-        const bool to_out = ((passes - 1 - pass) % 2) == 0;
-        uint64_t* dst_k = to_out ? reinterpret_cast<uint64_t*>(keys_out) : tmp_keys;
-        int32_t* dst_v = to_out ? vals_out : tmp_vals;
-        const int shift = pass * 8;
-        sort_upsweep_kernel<<<nb, kSortThreads, 0, stream>>>(n, src_k, shift, nb, hist);
-        QED_LAUNCH_CHECK();
-        sort_scan_kernel<<<1, kScanThreads, 0, stream>>>((int64_t)kRadix * nb, hist);
-        QED_LAUNCH_CHECK();
-        sort_downsweep_kernel<<<nb, kSortThreads, kSortSmemBytes, stream>>>(n, src_k, src_v, dst_k, dst_v, shift, nb, hist);
-        QED_LAUNCH_CHECK();
-        src_k = dst_k;
-        src_v = dst_v;
-    }
+    if (n_isects > 0x7fffffffLL) return QED_ERR_UNSUPPORTED;
+    if (!means2d || !radii || !depths || !prepare_workspace || !workspace || !isect_ids || !flatten_ids) return QED_ERR_BAD_ARG;
+    if (workspace_bytes < qed_isect_fill_workspace_bytes(n_isects)) return QED_ERR_WORKSPACE;
+    const int tile_n_bits = bit_length(n_tiles);
+    const int cam_bits = bit_length(C - 1);
+    if (tile_n_bits + cam_bits > 32) return QED_ERR_UNSUPPORTED;
+    const PrepareLayout L = prepare_layout(CN);
+    const char* pws = reinterpret_cast<const char*>(prepare_workspace);
+    const int32_t* sorted_vals = reinterpret_cast<const int32_t*>(pws + L.vals[1]);
+    const int64_t* cum2 = reinterpret_cast<const int64_t*>(pws + L.cum2);
+    char* ws = reinterpret_cast<char*>(workspace);
+    const size_t seg = align_up((size_t)n_isects * 4, 256);
+    uint32_t* k0 = reinterpret_cast<uint32_t*>(ws);
+    uint32_t* k1 = reinterpret_cast<uint32_t*>(ws + seg);
+    uint32_t* k2 = reinterpret_cast<uint32_t*>(ws + 2 * seg);
+    int32_t* v0 = reinterpret_cast<int32_t*>(ws + 3 * seg);
+    int32_t* v2 = reinterpret_cast<int32_t*>(ws + 4 * seg);
+    void* hist = ws + 5 * seg;
+    int32_t* first_j = reinterpret_cast<int32_t*>(ws + 5 * seg + radix_hist_bytes(n_isects));
+    emit_boundaries_kernel<<<(unsigned)((n_visible + 255) / 256), 256, 0, stream>>>(n_visible, cum2, first_j);
+    QED_LAUNCH_CHECK();
+    emit_sorted_kernel<<<(unsigned)((n_isects + kEmitTile - 1) / kEmitTile), kEmitThreads, 0, stream>>>(
+        n_visible, n_isects, N, sorted_vals, cum2, first_j, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width,
+        tile_height, tile_n_bits, k0, v0);
+    QED_LAUNCH_CHECK();
+    int rc = radix_sort_pairs<uint32_t>(n_isects, nullptr, k0, v0, k1, flatten_ids, k2, v2, hist, tile_n_bits + cam_bits, stream);
+    if (rc != QED_OK) return rc;
+    compose_ids_ranges_kernel<<<(unsigned)((n_isects + 255) / 256), 256, 0, stream>>>(n_isects, k1, flatten_ids, depths, C, n_tiles, tile_n_bits,
+                                                                                   isect_ids, isect_offsets);
+    QED_LAUNCH_CHECK();
     return QED_OK;
 }

@@ -1,0 +1,240 @@
+// Own LSD radix sort of (key, int32 value) pairs, 8-bit digits, stable.
+//
+// Per pass: upsweep (per-block digit histogram) -> scan (one block per digit over the per-block counts) ->
+// downsweep (block-local stable rank via __match_any_sync, block-sorted staging in shared memory, then
+// coalesced run writes).  KeyT is uint32_t or uint64_t.  The element count may live in device memory
+// (n_dev), so a sort can follow a device-side compaction without a host sync.
+#pragma once
+#include "common.cuh"
+
+namespace qed {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs per block
+constexpr int kRadix = 256;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(int64_t n_host, const int64_t* n_dev, const KeyT* __restrict__ keys, int shift,
+                                                                    uint32_t mask, int nblocks, uint32_t* __restrict__ hist /* [kRadix][nblocks] */) {
+    __shared__ uint32_t sh[kRadix];
+    const int64_t n = n_dev ? *n_dev : n_host;
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    if (base < n) {
+#pragma unroll 4
+        for (int k = 0; k < kSortItems; ++k) {
+            int64_t i = base + k * kSortThreads + threadIdx.x;
+            if (i < n) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & mask], 1u);
+        }
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// grid = kRadix blocks: block d scans hist[d][0..nblocks) exclusively in place, totals[d] = digit count
+__global__ void __launch_bounds__(256) radix_scan_kernel(int nblocks, uint32_t* __restrict__ hist, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t sw[9];
+    uint32_t* row = hist + (int64_t)blockIdx.x * nblocks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (int base = 0; base < nblocks; base += 256) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? row[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) sw[warp] = inc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int w = 0; w < 8; ++w) {
+                uint32_t t = sw[w];
+                sw[w] = acc;
+                acc += t;
+            }
+            sw[8] = acc;
+        }
+        __syncthreads();
+        if (i < nblocks) row[i] = carry + sw[warp] + inc - v;
+        carry += sw[8];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+template <typename KeyT>
+struct RadixSmem {
+    static constexpr size_t kBytes = (size_t)kSortTile * (sizeof(KeyT) + 4) + (size_t)(kSortThreads / 32) * kRadix * 4 + 2 * kRadix * 4 + 16 * 4;
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads, 3) radix_downsweep_kernel(int64_t n_host, const int64_t* n_dev, const KeyT* __restrict__ keys_in,
+                                                                      const int32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
+                                                                      int32_t* __restrict__ vals_out, int shift, uint32_t mask, int nblocks,
+                                                                      const uint32_t* __restrict__ hist, const uint32_t* __restrict__ totals) {
+    constexpr int kWarps = kSortThreads / 32;
+    constexpr int kPerWarp = kSortTile / kWarps;  // 512 consecutive pairs per warp
+    constexpr int kRounds = kPerWarp / 32;        // 16
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    KeyT* skeys = reinterpret_cast<KeyT*>(sort_smem);                                         // [kSortTile]
+    int32_t* svals = reinterpret_cast<int32_t*>(skeys + kSortTile);                           // [kSortTile]
+    uint32_t(*warp_hist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(svals + kSortTile);  // [kWarps][kRadix]
+    uint32_t* digit_start = &warp_hist[0][0] + kWarps * kRadix;  // start of each digit's run inside the block-sorted tile
+    uint32_t* global_base = digit_start + kRadix;                // global output index of the run's first element
+    uint32_t* sscan = global_base + kRadix;                      // [16]
+
+    const int64_t n = n_dev ? *n_dev : n_host;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+    if (base >= n) return;
+    const int tile_n = (n - base) < kSortTile ? (int)(n - base) : kSortTile;
+
+    for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+
+    // phase 0: all of the tile's loads are issued before anything depends on them (one memory latency)
+    KeyT key[kRounds];
+    int32_t val[kRounds];
+    uint16_t rank[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int local = warp * kPerWarp + r * 32 + lane;
+        key[r] = (local < tile_n) ? keys_in[base + local] : (KeyT)0;
+    }
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int local = warp * kPerWarp + r * 32 + lane;
+        val[r] = (local < tile_n) ? vals_in[base + local] : 0;
+    }
+    // phase A: stable rank inside the warp's 512-pair sub-chunk
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int local = warp * kPerWarp + r * 32 + lane;
+        const bool valid = local < tile_n;
+        const uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & mask) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = warp_hist[warp][d];
+            warp_hist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
+        __syncwarp();
+    }
+    __syncthreads();
+    // phase B: thread d: exclusive prefix over warps + block count; exclusive scans over the digits
+    {
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            uint32_t c = warp_hist[w][d];
+            warp_hist[w][d] = run;
+            run += c;
+        }
+        const uint32_t tot = totals[d];
+        uint32_t inc = run, ginc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            uint32_t g = __shfl_up_sync(0xffffffffu, ginc, o);
+            if (lane >= o) {
+                inc += t;
+                ginc += g;
+            }
+        }
+        if (lane == 31) {
+            sscan[warp] = inc;
+            sscan[8 + warp] = ginc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0, gacc = 0;
+            for (int w = 0; w < kWarps; ++w) {
+                uint32_t t = sscan[w], g = sscan[8 + w];
+                sscan[w] = acc;
+                sscan[8 + w] = gacc;
+                acc += t;
+                gacc += g;
+            }
+        }
+        __syncthreads();
+        digit_start[d] = sscan[warp] + inc - run;
+        global_base[d] = (sscan[8 + warp] + ginc - tot) + hist[(int64_t)d * nblocks + blockIdx.x];
+    }
+    __syncthreads();
+    // phase C: place into block-sorted order in smem
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const int local = warp * kPerWarp + r * 32 + lane;
+        if (local < tile_n) {
+            const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
+            const uint32_t pos = digit_start[d] + warp_hist[warp][d] + rank[r];
+            skeys[pos] = key[r];
+            svals[pos] = val[r];
+        }
+    }
+    __syncthreads();
+    // phase D: coalesced run writes
+    for (int i = threadIdx.x; i < tile_n; i += kSortThreads) {
+        const KeyT k = skeys[i];
+        const uint32_t d = (uint32_t)(k >> shift) & mask;
+        const int64_t dst = (int64_t)global_base[d] + (i - digit_start[d]);
+        keys_out[dst] = k;
+        vals_out[dst] = svals[i];
+    }
+}
+
+inline size_t radix_hist_bytes(int64_t capacity) {
+    int64_t nb = (capacity + kSortTile - 1) / kSortTile;
+    if (nb < 1) nb = 1;
+    return ((size_t)kRadix * nb * 4 + kRadix * 4 + 255) / 256 * 256;
+}
+
+// Sort on key bits [0, end_bit).  Result lands in (keys_out, vals_out); (tmp_keys, tmp_vals) is the
+// ping-pong buffer; `hist` = radix_hist_bytes(capacity) scratch.  keys_in/vals_in are not modified.
+template <typename KeyT>
+inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* keys_in, const int32_t* vals_in, KeyT* keys_out,
+                            int32_t* vals_out, KeyT* tmp_keys, int32_t* tmp_vals, void* hist_ws, int end_bit, cudaStream_t stream) {
+    if (capacity <= 0) return QED_OK;
+    const int nb = (int)((capacity + kSortTile - 1) / kSortTile);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(hist_ws);
+    uint32_t* totals = hist + (size_t)kRadix * nb;
+    const int passes = (end_bit + 7) / 8;
+    if (passes == 0) {
+        if (n_dev) return QED_ERR_UNSUPPORTED;
+        QED_CUDA_TRY(cudaMemcpyAsync(keys_out, keys_in, (size_t)capacity * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream));
+        QED_CUDA_TRY(cudaMemcpyAsync(vals_out, vals_in, (size_t)capacity * 4, cudaMemcpyDeviceToDevice, stream));
+        return QED_OK;
+    }
+    auto down = radix_downsweep_kernel<KeyT>;
+    QED_CUDA_TRY(cudaFuncSetAttribute(down, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RadixSmem<KeyT>::kBytes));
+    const KeyT* src_k = keys_in;
+    const int32_t* src_v = vals_in;
+    for (int pass = 0; pass < passes; ++pass) {
+        const bool to_out = ((passes - 1 - pass) % 2) == 0;  // destinations alternate, ending on *_out
+        KeyT* dst_k = to_out ? keys_out : tmp_keys;
+        int32_t* dst_v = to_out ? vals_out : tmp_vals;
+        const int shift = pass * 8;
+        const int bits = (end_bit - shift) < 8 ? (end_bit - shift) : 8;
+        const uint32_t mask = (1u << bits) - 1u;
+        radix_upsweep_kernel<KeyT><<<nb, kSortThreads, 0, stream>>>(capacity, n_dev, src_k, shift, mask, nb, hist);
+        QED_LAUNCH_CHECK();
+        radix_scan_kernel<<<kRadix, 256, 0, stream>>>(nb, hist, totals);
+        QED_LAUNCH_CHECK();
+        down<<<nb, kSortThreads, RadixSmem<KeyT>::kBytes, stream>>>(capacity, n_dev, src_k, src_v, dst_k, dst_v, shift, mask, nb, hist, totals);
+        QED_LAUNCH_CHECK();
+        src_k = dst_k;
+        src_v = dst_v;
+    }
+    return QED_OK;
+}
+
+}  // namespace qed

@@ -1,0 +1,133 @@
+// Three-phase inclusive scan (reduce / scan of block sums / scan + add) of a transformed int32 input to
+// int64, with the element count optionally read from device memory (so upstream counts need no host sync).
+#pragma once
+#include "common.cuh"
+
+namespace qed {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t v, int64_t* smem_warp, int64_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t w = lane < (kScanThreads / 32) ? smem_warp[lane] : 0;
+        int64_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < (kScanThreads / 32)) smem_warp[lane] = winc - w;
+        if (lane == (kScanThreads / 32) - 1) smem_warp[kScanThreads / 32] = winc;
+    }
+    __syncthreads();
+    total = smem_warp[kScanThreads / 32];
+    int64_t res = smem_warp[warp] + inc - v;
+    __syncthreads();
+    return res;
+}
+
+// input transforms
+struct ScanIdentity {
+    const int32_t* in;
+    __device__ __forceinline__ int32_t operator()(int64_t i) const { return in[i]; }
+};
+struct ScanFlagPositive {  // 1 where in[i] > 0
+    const int32_t* in;
+    __device__ __forceinline__ int32_t operator()(int64_t i) const { return in[i] > 0 ? 1 : 0; }
+};
+struct ScanGather {  // in[index[i]]
+    const int32_t* in;
+    const int32_t* index;
+    __device__ __forceinline__ int32_t operator()(int64_t i) const { return in[index[i]]; }
+};
+
+template <typename F>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(int64_t n_host, const int64_t* n_dev, F f, int64_t* __restrict__ block_sums) {
+    __shared__ int64_t sw[kScanThreads / 32 + 1];
+    const int64_t n = n_dev ? *n_dev : n_host;
+    int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int64_t s = 0;
+    if (base < n) {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            int64_t i = base + k * kScanThreads + threadIdx.x;
+            if (i < n) s += f(i);
+        }
+    }
+    int64_t total;
+    block_exclusive_scan(s, sw, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of block sums in place; writes the grand total
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int64_t nb, int64_t* __restrict__ block_sums, int64_t* __restrict__ total_dev) {
+    __shared__ int64_t sw[kScanThreads / 32 + 1];
+    int64_t carry = 0;
+    for (int64_t base = 0; base < nb; base += kScanThreads) {
+        int64_t i = base + threadIdx.x;
+        int64_t v = i < nb ? block_sums[i] : 0;
+        int64_t total;
+        int64_t ex = block_exclusive_scan(v, sw, total);
+        if (i < nb) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_dev) *total_dev = carry;
+}
+
+template <typename F>
+__global__ void __launch_bounds__(kScanThreads) scan_final_kernel(int64_t n_host, const int64_t* n_dev, F f, const int64_t* __restrict__ block_sums,
+                                                                 int64_t* __restrict__ out) {
+    __shared__ int64_t sw[kScanThreads / 32 + 1];
+    const int64_t n = n_dev ? *n_dev : n_host;
+    // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems) of the tile
+    int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    if ((int64_t)blockIdx.x * kScanTile >= n) return;
+    int32_t v[kScanItems];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? f(base + k) : 0;
+        s += v[k];
+    }
+    int64_t total;
+    int64_t ex = block_exclusive_scan(s, sw, total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        ex += v[k];
+        if (base + k < n) out[base + k] = ex;
+    }
+}
+
+inline size_t scan_workspace_bytes(int64_t capacity) {
+    int64_t nb = (capacity + kScanTile - 1) / kScanTile;
+    return (size_t)(nb > 0 ? nb : 1) * sizeof(int64_t);
+}
+
+// Inclusive scan of f(0..n) into out (int64); total -> *total_dev.  `capacity` >= n sizes the grid when n
+// is only known on the device (n_dev != nullptr).
+template <typename F>
+inline int scan_inclusive(int64_t capacity, const int64_t* n_dev, F f, int64_t* out, int64_t* total_dev, void* workspace, cudaStream_t stream) {
+    int64_t nb = (capacity + kScanTile - 1) / kScanTile;
+    if (nb == 0) nb = 1;
+    int64_t* sums = reinterpret_cast<int64_t*>(workspace);
+    scan_reduce_kernel<F><<<(unsigned)nb, kScanThreads, 0, stream>>>(capacity, n_dev, f, sums);
+    QED_LAUNCH_CHECK();
+    scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(nb, sums, total_dev);
+    QED_LAUNCH_CHECK();
+    scan_final_kernel<F><<<(unsigned)nb, kScanThreads, 0, stream>>>(capacity, n_dev, f, sums, out);
+    QED_LAUNCH_CHECK();
+    return QED_OK;
+}
+
+}  // namespace qed

@@ -21,13 +21,17 @@ from ._lib import check, current_stream, ptr
 
 GRAD_FLOATS = 12
 GEOM_FLOATS = 8
-_SORT_IMPL = "own"  # "own" | "cub" (library baseline, same output)
+_SORT_IMPL = "two_level"  # "two_level" (product path) | "own" | "cub" — identical output
+SORT_IMPLS = ("two_level", "own", "cub")
 
 
 def set_sort_impl(name: str) -> str:
-    """Select the radix sort used by isect_tiles: "own" (this library's kernels) or "cub" (baseline)."""
+    """Select how isect_tiles builds the sorted intersection list:
+    "two_level": depth-sort the visible Gaussians, emit in that order, stable radix on the tile bits (default);
+    "own": gsplat's formulation (emit 64-bit keys, full radix sort) with this library's radix sort;
+    "cub": the same with cub::DeviceRadixSort (the library baseline gsplat uses)."""
     global _SORT_IMPL
-    assert name in ("own", "cub")
+    assert name in SORT_IMPLS
     old, _SORT_IMPL = _SORT_IMPL, name
     return old
 
@@ -158,7 +162,7 @@ def fully_fused_projection(means: Tensor, covars, quats: Tensor, scales: Tensor,
 # --------------------------------------------------------------------------------------------- #
 @torch.no_grad()
 def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
-                sort: bool = True, tiles_per_gauss: Optional[Tensor] = None):
+                sort: bool = True, tiles_per_gauss: Optional[Tensor] = None, impl: Optional[str] = None):
     """gsplat `isect_tiles` -> tiles_per_gauss[C,N] i32, isect_ids[M] i64, flatten_ids[M] i32 (sorted)."""
     lib = _lib.load()
     _lib.require_cuda(means2d, radii, depths)
@@ -168,17 +172,34 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     C, N = radii.shape
     dev = means2d.device
     stream = current_stream()
+    impl = impl or _SORT_IMPL
     if tiles_per_gauss is None:
         tiles_per_gauss = torch.empty(C, N, dtype=torch.int32, device=dev)
         check(lib.qed_isect_count(C, N, ptr(means2d), ptr(radii), tile_size, tile_width, tile_height,
                                   ptr(tiles_per_gauss), stream), "qed_isect_count")
     CN = C * N
+    if impl == "two_level" and sort:
+        pws_bytes = lib.qed_isect_prepare_workspace_bytes(CN)
+        pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
+        counts = torch.zeros(2, dtype=torch.int64, device=dev)
+        check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles_per_gauss), ptr(pws), pws_bytes, ptr(counts), None, stream),
+              "qed_isect_prepare")
+        n_visible, n_isects = (int(v) for v in counts.tolist())  # the one host sync of the forward (gsplat has the same one)
+        isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+        flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+        if n_isects:
+            fws_bytes = lib.qed_isect_fill_workspace_bytes(n_isects)
+            fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
+            check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), tile_size, tile_width,
+                                     tile_height, ptr(pws), ptr(fws), fws_bytes, ptr(isect_ids), ptr(flatten_ids), None, stream),
+                  "qed_isect_fill")
+        return tiles_per_gauss, isect_ids, flatten_ids
     cum = torch.empty(CN, dtype=torch.int64, device=dev)
     total = torch.zeros(1, dtype=torch.int64, device=dev)
     ws_bytes = lib.qed_isect_scan_workspace_bytes(CN)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(lib.qed_isect_scan(CN, ptr(tiles_per_gauss), ptr(cum), ptr(total), None, ptr(ws), ws_bytes, stream), "qed_isect_scan")
-    n_isects = int(total.item())  # the one host sync of the forward (gsplat has the same one)
+    n_isects = int(total.item())
     isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
     flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
     if n_isects:
@@ -187,7 +208,8 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
         if sort:
             tile_n_bits = (tile_width * tile_height).bit_length()
             cam_n_bits = C.bit_length()
-            isect_ids, flatten_ids = sort_pairs(isect_ids, flatten_ids, 32 + tile_n_bits + cam_n_bits)
+            isect_ids, flatten_ids = sort_pairs(isect_ids, flatten_ids, 32 + tile_n_bits + cam_n_bits,
+                                                impl="cub" if impl == "cub" else "own")
     return tiles_per_gauss, isect_ids, flatten_ids
 
 
@@ -196,7 +218,7 @@ def sort_pairs(keys: Tensor, vals: Tensor, end_bit: int = 64, impl: Optional[str
     """Stable ascending radix sort of (int64 key, int32 value) pairs on key bits [0, end_bit)."""
     lib = _lib.load()
     _lib.require_cuda(keys, vals)
-    impl = impl or _SORT_IMPL
+    impl = impl or ("cub" if _SORT_IMPL == "cub" else "own")
     n = keys.numel()
     keys_out = torch.empty_like(keys)
     vals_out = torch.empty_like(vals)

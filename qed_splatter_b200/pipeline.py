@@ -39,11 +39,13 @@ class StepOutput:
 class FusedSplatStep:
     """Holds reusable device buffers; `forward()` renders, `step()` renders + loss + full backward."""
 
-    def __init__(self, device, sort_impl: str = "own"):
+    def __init__(self, device, sort_impl: str = "two_level"):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.sort_impl = sort_impl
         self._total = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._counts_host = torch.zeros(2, dtype=torch.int64).pin_memory()
         self._stats = None
         self._loss = torch.zeros(3, device=self.device)
         self._cap_isects = 0
@@ -102,34 +104,52 @@ class FusedSplatStep:
                                   ptr(conics), ptr(comps), ptr(colors), ptr(opac), ptr(tiles), ptr(geom), stream), "qed_project_fwd")
         self._mark("project_fwd")
         CN = C * N
-        cum = self._get("cum", (CN,), torch.int64)
-        ws_bytes = lib.qed_isect_scan_workspace_bytes(CN)
-        ws = self._get("scan_ws", (ws_bytes,), torch.uint8)
-        check(lib.qed_isect_scan(CN, ptr(tiles), ptr(cum), ptr(self._total), None, ptr(ws), ws_bytes, stream), "qed_isect_scan")
-        M = int(self._total.item())  # the single host sync of the step
-        self._mark("scan+sync")
-        cap = max(M, 1)
-        ids_u = self._get("ids_u", (cap,), torch.int64)[:M]
-        flat_u = self._get("flat_u", (cap,), torch.int32)[:M]
-        ids = self._get("ids", (cap,), torch.int64)[:M]
-        flat = self._get("flat", (cap,), torch.int32)[:M]
         offsets = self._get("offsets", (C, th, tw), torch.int32)
-        if M:
-            check(lib.qed_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(cum), tile, tw, th, ptr(ids_u), ptr(flat_u),
-                                     stream), "qed_isect_emit")
-            self._mark("emit")
-            end_bit = 32 + (tw * th).bit_length() + C.bit_length()
-            if self.sort_impl == "cub":
-                sb = lib.qed_sort_pairs_cub_workspace_bytes(M)
-                sws = self._get("sort_ws", (sb,), torch.uint8)
-                check(lib.qed_sort_pairs_cub(M, ptr(ids_u), ptr(flat_u), ptr(ids), ptr(flat), end_bit, ptr(sws), sb, stream), "qed_sort_pairs_cub")
-            else:
-                sb = lib.qed_sort_pairs_workspace_bytes(M)
-                sws = self._get("sort_ws", (sb,), torch.uint8)
-                check(lib.qed_sort_pairs(M, ptr(ids_u), ptr(flat_u), ptr(ids), ptr(flat), end_bit, ptr(sws), sb, stream), "qed_sort_pairs")
-        self._mark("sort")
-        check(lib.qed_tile_ranges(M, ptr(ids) if M else None, C, tw, th, ptr(offsets), stream), "qed_tile_ranges")
-        self._mark("ranges")
+        if self.sort_impl == "two_level":
+            pws_bytes = lib.qed_isect_prepare_workspace_bytes(CN)
+            pws = self._get("prep_ws", (pws_bytes,), torch.uint8)
+            check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles), ptr(pws), pws_bytes, ptr(self._counts), ptr(self._counts_host), stream),
+                  "qed_isect_prepare")
+            self._mark("isect_prepare")
+            torch.cuda.current_stream().synchronize()  # the single host sync of the step: output sizes
+            n_vis, M = int(self._counts_host[0]), int(self._counts_host[1])
+            self._mark("sync")
+            cap = max(M, 1)
+            ids = self._get("ids", (cap,), torch.int64)[:M]
+            flat = self._get("flat", (cap,), torch.int32)[:M]
+            fws_bytes = lib.qed_isect_fill_workspace_bytes(M)
+            fws = self._get("fill_ws", (fws_bytes,), torch.uint8)
+            check(lib.qed_isect_fill(C, N, n_vis, M, ptr(means2d), ptr(radii), ptr(depths), tile, tw, th, ptr(pws), ptr(fws), fws_bytes,
+                                     ptr(ids) if M else None, ptr(flat) if M else None, ptr(offsets), stream), "qed_isect_fill")
+            self._mark("isect_fill")
+        else:
+            cum = self._get("cum", (CN,), torch.int64)
+            ws_bytes = lib.qed_isect_scan_workspace_bytes(CN)
+            ws = self._get("scan_ws", (ws_bytes,), torch.uint8)
+            check(lib.qed_isect_scan(CN, ptr(tiles), ptr(cum), ptr(self._total), None, ptr(ws), ws_bytes, stream), "qed_isect_scan")
+            M = int(self._total.item())  # the single host sync of the step
+            self._mark("scan+sync")
+            cap = max(M, 1)
+            ids_u = self._get("ids_u", (cap,), torch.int64)[:M]
+            flat_u = self._get("flat_u", (cap,), torch.int32)[:M]
+            ids = self._get("ids", (cap,), torch.int64)[:M]
+            flat = self._get("flat", (cap,), torch.int32)[:M]
+            if M:
+                check(lib.qed_isect_emit(C, N, ptr(means2d), ptr(radii), ptr(depths), ptr(cum), tile, tw, th, ptr(ids_u), ptr(flat_u),
+                                         stream), "qed_isect_emit")
+                self._mark("emit")
+                end_bit = 32 + (tw * th).bit_length() + C.bit_length()
+                if self.sort_impl == "cub":
+                    sb = lib.qed_sort_pairs_cub_workspace_bytes(M)
+                    sws = self._get("sort_ws", (sb,), torch.uint8)
+                    check(lib.qed_sort_pairs_cub(M, ptr(ids_u), ptr(flat_u), ptr(ids), ptr(flat), end_bit, ptr(sws), sb, stream), "qed_sort_pairs_cub")
+                else:
+                    sb = lib.qed_sort_pairs_workspace_bytes(M)
+                    sws = self._get("sort_ws", (sb,), torch.uint8)
+                    check(lib.qed_sort_pairs(M, ptr(ids_u), ptr(flat_u), ptr(ids), ptr(flat), end_bit, ptr(sws), sb, stream), "qed_sort_pairs")
+            self._mark("sort")
+            check(lib.qed_tile_ranges(M, ptr(ids) if M else None, C, tw, th, ptr(offsets), stream), "qed_tile_ranges")
+            self._mark("ranges")
         render = self._get("render", (C, height, width, D))
         alphas = self._get("alphas", (C, height, width, 1))
         last_ids = self._get("last_ids", (C, height, width), torch.int32)
@@ -203,12 +223,19 @@ class FusedSplatStep:
     # -- instrumentation (never inside a timed region) --------------------------------------------
     @property
     def launches_per_step(self) -> int:
-        """Kernel launches of one step(): project 1, scan 3, emit 1, sort (own: 3 per 8-bit pass; cub: 8),
-        ranges 1, composite fwd 1, loss 4 (+1 memset), grad clear 1, composite bwd 1, project bwd 1."""
+        """Kernel launches of one step(): project 1; intersections (two_level: 3 scan + 1 compact + 3 per
+        8-bit pass of the Gaussian sort + 3 scan | 1 emit + 3 per pass of the tile sort + compose + ranges;
+        own/cub: 3 scan + emit + sort + ranges); composite fwd 1, loss 4 (+1 memset), grad clear 1,
+        composite bwd 1, project bwd 1."""
         f = self._fwd
-        end_bit = 32 + (f["tw"] * f["th"]).bit_length() + f["C"].bit_length()
-        sort = 3 * ((end_bit + 7) // 8) if self.sort_impl == "own" else 8
-        return 1 + 3 + 1 + sort + 1 + 1 + 5 + 1 + 1 + 1
+        tile_bits = (f["tw"] * f["th"]).bit_length()
+        if self.sort_impl == "two_level":
+            gauss_bits = 32 + (f["C"] - 1).bit_length()
+            isect = 3 + 1 + 3 * ((gauss_bits + 7) // 8) + 3 + 1 + 3 * ((tile_bits + (f["C"] - 1).bit_length() + 7) // 8) + 2
+        else:
+            end_bit = 32 + tile_bits + f["C"].bit_length()
+            isect = 3 + 1 + (3 * ((end_bit + 7) // 8) if self.sort_impl == "own" else 8) + 1
+        return 1 + isect + 1 + 5 + 1 + 1 + 1
 
     @torch.no_grad()
     def count_pairs(self) -> Dict[str, int]:

@@ -111,7 +111,7 @@ def test_isect_bit_exact(cuda):
     tw, th = ops.tile_grid(s.width, s.height, 16)
     t_o, ids_o, flat_o = oracle.isect_tiles(m_o, r_o, d_o, 16, tw, th)
     off_o = oracle.isect_offset_encode(ids_o, s.C, tw, th)
-    for impl in ("own", "cub"):
+    for impl in ops.SORT_IMPLS:
         ops.set_sort_impl(impl)
         t, ids, flat = ops.isect_tiles(m_o.to(cuda), r_o.to(cuda), d_o.to(cuda), 16, tw, th)
         off = ops.isect_offset_encode(ids, s.C, tw, th)
@@ -120,7 +120,7 @@ def test_isect_bit_exact(cuda):
         assert torch.equal(ids.cpu(), ids_o), f"isect_ids ({impl})"
         assert torch.equal(flat.cpu(), flat_o), f"flatten_ids ({impl})"
         assert torch.equal(off.cpu(), off_o), f"isect_offsets ({impl})"
-    ops.set_sort_impl("own")
+    ops.set_sort_impl("two_level")
 
 
 def test_isect_ties_and_empty(cuda):
@@ -134,13 +134,14 @@ def test_isect_ties_and_empty(cuda):
     tw, th = ops.tile_grid(W, H, 16)
     t_o, ids_o, flat_o = oracle.isect_tiles(means2d, radii, depths, 16, tw, th)
     off_o = oracle.isect_offset_encode(ids_o, C, tw, th)
-    t, ids, flat = ops.isect_tiles(means2d.to(cuda), radii.to(cuda), depths.to(cuda), 16, tw, th)
-    off = ops.isect_offset_encode(ids, C, tw, th)
-    assert torch.equal(ids.cpu(), ids_o) and torch.equal(flat.cpu(), flat_o) and torch.equal(off.cpu(), off_o)
     zero = torch.zeros(C, N, dtype=torch.int32)
-    t, ids, flat = ops.isect_tiles(means2d.to(cuda), zero.to(cuda), depths.to(cuda), 16, tw, th)
-    off = ops.isect_offset_encode(ids, C, tw, th)
-    assert ids.numel() == 0 and flat.numel() == 0 and int(off.abs().sum()) == 0 and int(t.sum()) == 0
+    for impl in ops.SORT_IMPLS:
+        t, ids, flat = ops.isect_tiles(means2d.to(cuda), radii.to(cuda), depths.to(cuda), 16, tw, th, impl=impl)
+        off = ops.isect_offset_encode(ids, C, tw, th)
+        assert torch.equal(ids.cpu(), ids_o) and torch.equal(flat.cpu(), flat_o) and torch.equal(off.cpu(), off_o), impl
+        t, ids, flat = ops.isect_tiles(means2d.to(cuda), zero.to(cuda), depths.to(cuda), 16, tw, th, impl=impl)
+        off = ops.isect_offset_encode(ids, C, tw, th)
+        assert ids.numel() == 0 and flat.numel() == 0 and int(off.abs().sum()) == 0 and int(t.sum()) == 0, impl
 
 
 @pytest.mark.parametrize("n", [1, 31, 4096, 4097, 100_003])
@@ -209,3 +210,28 @@ def test_raster_cull_is_exact(cuda):
     assert torch.equal(outs[True][2], outs[False][2])
     for a, b in zip(outs[True][3], outs[False][3]):
         assert_close_frac(a, b, 1e-4, 1e-6 * float(b.abs().mean() + 1e-12), 1e-3, "grad cull vs no-cull")
+
+
+def test_isect_full_size_paths_agree(cuda):
+    """BASELINE configs[1] size (1M Gaussians, 1080p): the two-level build, the own 64-bit radix sort and the
+    CUB baseline must produce the same bytes; keys must be sorted and ranges consistent."""
+    from qed_splatter_b200.scenes import scene_s1
+
+    s = scene_s1(N=1_000_000, targets=False).to(cuda)
+    radii, means2d, depths, conics, comps, cols, opac, tiles, geom = ops.project_gaussians(
+        s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, sh_degree=3)
+    tw, th = ops.tile_grid(s.width, s.height, 16)
+    res = {impl: ops.isect_tiles(means2d, radii, depths, 16, tw, th, tiles_per_gauss=tiles, impl=impl) for impl in ops.SORT_IMPLS}
+    ids, flat = res["cub"][1], res["cub"][2]
+    assert ids.numel() == int(tiles.sum()) > 1_000_000
+    for impl in ("two_level", "own"):
+        assert torch.equal(res[impl][1], ids), impl
+        assert torch.equal(res[impl][2], flat), impl
+    assert bool((ids[1:] >= ids[:-1]).all()), "sorted"
+    off = ops.isect_offset_encode(ids, 1, tw, th).flatten().long()
+    assert bool((off[1:] >= off[:-1]).all()) and int(off[0]) == 0
+    # every entry's tile id matches the range it sits in
+    tile_of_entry = (ids >> 32) & ((1 << (tw * th).bit_length()) - 1)
+    counts = torch.bincount(tile_of_entry, minlength=tw * th)
+    ends = torch.cat([off[1:], torch.tensor([ids.numel()], device=cuda)])
+    assert torch.equal(ends - off, counts)
