@@ -224,7 +224,7 @@ def main_ours(args):
     def step():
         out = fs.step(means, quats, scales, opac, sh, viewmats, Ks, width, height, 3, gt_rgb, gt_depth, bg, render_mode=args.mode,
                       grad_scale=1.0 / world, grad_out=views)
-        _lib.check(lib.qed_strategy_update(1, N, _lib.ptr(out.packed_grads), 1, _lib.ptr(out.radii), width, height, _lib.ptr(stats[0]),
+        _lib.check(lib.qed_strategy_update(1, N, _lib.ptr(out.packed_grads), 1, _lib.ptr(out.radii), width, height, world, _lib.ptr(stats[0]),
                                            _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.current_stream()), "qed_strategy_update")
         if world > 1:
             dist.all_reduce(arena)

@@ -15,7 +15,8 @@
  *   - plain C: raw device pointers + extents; contiguous row-major tensors; no torch types.
  *   - every function returns int: 0 = ok, < 0 = QED_ERR_* argument error, > 0 = cudaError_t.
  *   - never throws, never exits, never synchronises the device, holds no global mutable
- *     state; all work is enqueued on the `stream` argument (a cudaStream_t).
+ *     state (the qed_debug_* test hooks, which are not declared here, are the only exception);
+ *     all work is enqueued on the `stream` argument (a cudaStream_t).
  *   - caller owns every buffer.  Outputs are fully overwritten unless stated "accumulates".
  *   - float = IEEE binary32.  "flat index" = c*N + n into the [C,N,...] arrays.
  */
@@ -195,7 +196,7 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  *  gt_rgb[C,H,W,3], gt_depth[C,H,W] (<=0 or non-finite = invalid), bg[3].
  *  loss = rgb_weight * mean|clamp(rgb + (1-a) bg) - gt| + depth_lambda * mean_valid|depth - gt_depth|
  *  Two launches: a reduction for n_valid / loss sums, then the per-pixel gradient.
- *  stats_dev[8] (double): {sum|rgb err|, sum|depth err|, n_valid, max depth, 0..}; loss_dev[3] float:
+ *  stats_dev[C*8] (double, per camera): {sum|rgb err|, sum|depth err|, n_valid, (scratch), max depth, 0..}; loss_dev[3] float:
  *  {total, rgb term, depth term}.  grad_scale multiplies every gradient (1/total views for a sharded batch).
  */
 int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
@@ -206,16 +207,23 @@ int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const fl
 /* ------------------------------------------------------------------------------------------------
  * trainer-side kernels
  */
-/* Fused Adam over a flat arena: param/grad/m/v [n]; per-element lr from lr_by_group[group_of(i)] where the
- * arena is G contiguous groups with end offsets group_ends[G] (device, int64).  bias corrections from step. */
+/* Fused Adam (torch.optim.Adam semantics, no weight decay / amsgrad) over a flat arena: param/grad/m/v [n].
+ * The arena is G <= 16 contiguous groups with end offsets group_ends[G] (device, int64); element i of group g
+ * uses lr_by_group[g], or lr_alt_by_group[g] when group_period[g] > 0 and (i - start_g) % group_period[g] >=
+ * group_split[g] (the SH block [N,16,3]: period 48, split 3 -> features_dc vs features_rest learning rates).
+ * lr_alt_by_group / group_period / group_split may be NULL.  Bias corrections use `step` (1-based).
+ * replaces: the six torch Adam groups of qed_splatter/config.py:44-68 with one launch. */
 int qed_adam_arena(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int G,
-                   const int64_t* group_ends, const float* lr_by_group, float beta1, float beta2, float eps,
+                   const int64_t* group_ends, const float* lr_by_group, const float* lr_alt_by_group,
+                   const int32_t* group_period, const int32_t* group_split, double beta1, double beta2, double eps,
                    int step, qed_stream_t stream);
 
-/* gsplat DefaultStrategy._update_state: for radii>0: grad2d[n] += ||absgrad[c,n] * (W/2*C, H/2*C)||,
- * count[n] += 1, radii_max[n] = max(radii_max[n], radii[c,n] / max(W,H)).  packed_grads as above. */
+/* gsplat DefaultStrategy._update_state on the `info` of model.py:267,289-292: for radii>0:
+ *   grad2d[n] += ||g[c,n] * (W/2 * n_cameras, H/2 * n_cameras)||, count[n] += 1,
+ *   radii_max[n] = max(radii_max[n], radii[c,n] / max(W,H)),   g = absgrad (or grad) slots of packed_grads.
+ * n_cameras = size of the view batch the loss was averaged over (<= 0: C).  Accumulates. */
 int qed_strategy_update(int C, int N, const float* packed_grads, int use_absgrad, const int32_t* radii,
-                        int width, int height, float* grad2d, float* count, float* radii_max,
+                        int width, int height, int n_cameras, float* grad2d, float* count, float* radii_max,
                         qed_stream_t stream);
 
 #ifdef __cplusplus

@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(kProjBwdThreads) project_bwd_kernel(const Proj
         m0 = p.means[n * 3 + 0];
         m1 = p.means[n * 3 + 1];
         m2 = p.means[n * 3 + 2];
-        float4 q = *reinterpret_cast<const float4*>(p.quats + (int64_t)n * 4);
+        const float* qp = p.quats + (int64_t)n * 4;  // scalar loads: callers' views are only 4-byte aligned
+        float4 q = make_float4(qp[0], qp[1], qp[2], qp[3]);
         s0 = p.scales[n * 3 + 0];
         s1 = p.scales[n * 3 + 1];
         s2 = p.scales[n * 3 + 2];
@@ -457,7 +458,11 @@ __global__ void __launch_bounds__(kProjBwdThreads) project_bwd_kernel(const Proj
         p.v_means[n * 3 + 0] = vm0;
         p.v_means[n * 3 + 1] = vm1;
         p.v_means[n * 3 + 2] = vm2;
-        *reinterpret_cast<float4*>(p.v_quats + (int64_t)n * 4) = vq;
+        float* vqp = p.v_quats + (int64_t)n * 4;
+        vqp[0] = vq.x;
+        vqp[1] = vq.y;
+        vqp[2] = vq.z;
+        vqp[3] = vq.w;
         p.v_scales[n * 3 + 0] = vs0;
         p.v_scales[n * 3 + 1] = vs1;
         p.v_scales[n * 3 + 2] = vs2;

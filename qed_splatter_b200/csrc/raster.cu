@@ -667,6 +667,8 @@ static int launch_raster(RasterParams p, cudaStream_t stream) {
     return QED_OK;
 }
 
+static inline bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
+
 static int check_raster_args(int C, int N, int64_t n_isects, int D, int width, int height, int tile_size, int tile_width, int tile_height) {
     if (C < 0 || N < 0 || n_isects < 0 || width <= 0 || height <= 0) return QED_ERR_BAD_ARG;
     if (!(D == 1 || D == 3 || D == 4)) return QED_ERR_UNSUPPORTED;
@@ -730,6 +732,7 @@ extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float
     if (C == 0) return QED_OK;
     if (!isect_offsets || !render || !alphas || !last_ids) return QED_ERR_BAD_ARG;
     if (n_isects > 0 && (!geom || !colors || !flatten_ids)) return QED_ERR_BAD_ARG;
+    if (misaligned16(geom) || (D == 4 && (misaligned16(colors) || misaligned16(render)))) return QED_ERR_BAD_ARG;  // float4 access
     RasterParams p = make_params(C, N, n_isects, D, geom, colors, backgrounds, width, height, tile_width, tile_height, isect_offsets,
                                  flatten_ids, normalize_last);
     p.render = render;
@@ -753,6 +756,7 @@ extern "C" int qed_raster_bwd(int C, int N, int64_t n_isects, int D, const float
     if (C == 0 || n_isects == 0) return QED_OK;
     if (!isect_offsets || !render || !alphas || !last_ids || !v_render || !packed_grads || !geom || !colors || !flatten_ids)
         return QED_ERR_BAD_ARG;
+    if (misaligned16(geom) || (D == 4 && (misaligned16(colors) || misaligned16(v_render)))) return QED_ERR_BAD_ARG;  // float4 access
     RasterParams p = make_params(C, N, n_isects, D, geom, colors, backgrounds, width, height, tile_width, tile_height, isect_offsets,
                                  flatten_ids, normalize_last);
     p.render = const_cast<float*>(render);  // read-only in the backward kernel

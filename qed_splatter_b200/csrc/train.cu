@@ -114,25 +114,35 @@ __global__ void loss_finalize_kernel(int C, int64_t HW, float rgb_weight, float 
 
 // ------------------------------------------------------------------------------------------------
 __global__ void adam_arena_kernel(int64_t n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
-                                  int G, const int64_t* __restrict__ group_ends, const float* __restrict__ lr_by_group, float beta1, float beta2,
-                                  float eps, float bias1, float bias2_sqrt) {
+                                  int G, const int64_t* __restrict__ group_ends, const float* __restrict__ lr_by_group,
+                                  const float* __restrict__ lr_alt_by_group, const int32_t* __restrict__ group_period,
+                                  const int32_t* __restrict__ group_split, float beta1, float beta2, float eps, float bias1, float bias2_sqrt) {
     __shared__ int64_t s_ends[16];
-    __shared__ float s_lr[16];
+    __shared__ float s_lr[16], s_lr_alt[16];
+    __shared__ int s_period[16], s_split[16];
     if (threadIdx.x < G) {
         s_ends[threadIdx.x] = group_ends[threadIdx.x];
         s_lr[threadIdx.x] = lr_by_group[threadIdx.x];
+        s_lr_alt[threadIdx.x] = lr_alt_by_group ? lr_alt_by_group[threadIdx.x] : lr_by_group[threadIdx.x];
+        s_period[threadIdx.x] = group_period ? group_period[threadIdx.x] : 0;
+        s_split[threadIdx.x] = group_split ? group_split[threadIdx.x] : 0;
     }
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int g = 0;
         while (g < G - 1 && i >= s_ends[g]) ++g;
+        float lr = s_lr[g];
+        if (s_period[g] > 0) {
+            const int64_t start = g > 0 ? s_ends[g - 1] : 0;
+            if ((int)((i - start) % s_period[g]) >= s_split[g]) lr = s_lr_alt[g];
+        }
         const float gr = grad[i];
         const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
         const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
         m[i] = mi;
         v[i] = vi;
         const float denom = sqrtf(vi) / bias2_sqrt + eps;
-        param[i] -= (s_lr[g] / bias1) * (mi / denom);
+        param[i] -= (lr / bias1) * (mi / denom);
     }
 }
 
@@ -190,30 +200,33 @@ extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* rende
 }
 
 extern "C" int qed_adam_arena(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int G,
-                              const int64_t* group_ends, const float* lr_by_group, float beta1, float beta2, float eps,
+                              const int64_t* group_ends, const float* lr_by_group, const float* lr_alt_by_group,
+                              const int32_t* group_period, const int32_t* group_split, double beta1, double beta2, double eps,
                               int step, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 0 || G <= 0 || G > 16 || step < 1) return QED_ERR_BAD_ARG;
     if (n == 0) return QED_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !group_ends || !lr_by_group) return QED_ERR_BAD_ARG;
-    const float bias1 = 1.0f - powf(beta1, (float)step);
-    const float bias2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+    // bias corrections in double, as torch.optim.Adam computes them on the host
+    const float bias1 = (float)(1.0 - pow(beta1, (double)step));
+    const float bias2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    adam_arena_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group, beta1, beta2, eps, bias1,
-                                                            bias2_sqrt);
+    adam_arena_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group, lr_alt_by_group,
+                                                            group_period, group_split, (float)beta1, (float)beta2, (float)eps, bias1, bias2_sqrt);
     QED_LAUNCH_CHECK();
     return QED_OK;
 }
 
 extern "C" int qed_strategy_update(int C, int N, const float* packed_grads, int use_absgrad, const int32_t* radii,
-                                   int width, int height, float* grad2d, float* count, float* radii_max,
+                                   int width, int height, int n_cameras, float* grad2d, float* count, float* radii_max,
                                    qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (C < 0 || N < 0 || width <= 0 || height <= 0) return QED_ERR_BAD_ARG;
     if (C == 0 || N == 0) return QED_OK;
     if (!packed_grads || !radii || !grad2d || !count) return QED_ERR_BAD_ARG;
-    const float sx = (float)width / 2.0f * (float)C, sy = (float)height / 2.0f * (float)C;
+    if (n_cameras <= 0) n_cameras = C;
+    const float sx = (float)width / 2.0f * (float)n_cameras, sy = (float)height / 2.0f * (float)n_cameras;
     const float inv = 1.0f / (float)(width > height ? width : height);
     strategy_update_kernel<<<(N + 255) / 256, 256, 0, stream>>>(C, N, reinterpret_cast<const float4*>(packed_grads), use_absgrad, radii, sx, sy, inv,
                                                                grad2d, count, radii_max);
