@@ -103,11 +103,12 @@ def test_adam_kernel_and_strategy_kernel(cuda):
         gpu.optimizer_step()
         cpu.step_count += 1
         gpu.step_count += 1
-    # compare the accumulated UPDATES (float32 rounding of lr * m / (sqrt(v) + eps) differs in the last bits)
+    # float32 rounding of lr/bias1 * m / (sqrt(v)/bias2 + eps) and of `param -= update` differs in the last bits
+    # (measured: <= 1.5e-6 absolute on updates of ~0.09): compare updates to 1e-4 relative of their typical size
     for name, p0 in zip(GROUPS, p):
         du_gpu = gpu.arena.view(gpu.arena.param, name).cpu() - p0
         du_cpu = cpu.arena.view(cpu.arena.param, name) - p0
-        assert torch.allclose(du_gpu, du_cpu, rtol=1e-3, atol=1e-4 * float(du_cpu.abs().mean())), name
+        assert float((du_gpu - du_cpu).abs().max()) <= 1e-4 * float(du_cpu.abs().mean()) + 5e-7, name
     assert torch.allclose(gpu.arena.exp_avg_sq.cpu(), cpu.arena.exp_avg_sq, rtol=1e-5, atol=1e-12)
     # strategy statistics
     C, W, H = 3, 640, 360
