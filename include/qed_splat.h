@@ -139,7 +139,8 @@ int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* k
  *            counts_host_pinned[2] when non-NULL (the caller reads it after a stream sync to size outputs).
  *   fill:    warp-cooperative coalesced emission of (camera|tile, flat index) in depth order, stable radix
  *            sort on the camera|tile bits only, then isect_ids = key << 32 | bits(depth) and the per-tile
- *            ranges (isect_offsets may be NULL to skip them).
+ *            ranges (isect_ids and/or isect_offsets may be NULL to skip them; the compositor needs only
+ *            flatten_ids + isect_offsets).
  * `prepare_workspace` must be the buffer qed_isect_prepare filled for the same (C, N). */
 size_t qed_isect_prepare_workspace_bytes(int64_t CN);
 int qed_isect_prepare(int C, int N, const float* depths, const int32_t* tiles_per_gauss, void* workspace,

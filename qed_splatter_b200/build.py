@@ -44,7 +44,8 @@ def _compile_one(src: Path) -> Path:
     r = subprocess.run(cmd, capture_output=True, text=True)
     (BUILD / (src.stem + ".ptxas.log")).write_text(r.stderr)
     if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        errs = "\n".join(ln for ln in (r.stdout + "\n" + r.stderr).splitlines() if "error" in ln.lower() or "fatal" in ln.lower())
+        raise RuntimeError(f"nvcc failed for {src.name}:\n{errs or r.stderr[-4000:]}")
     return obj
 
 

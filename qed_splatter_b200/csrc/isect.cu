@@ -252,7 +252,7 @@ __global__ void compact_visible_kernel(int64_t CN, int N, const int32_t* __restr
 // range by binary search in cum2, stages their (first tile, box width, flat index, start offset) in shared
 // memory, and every entry then finds its Gaussian by a binary search in that shared slice.
 constexpr int kEmitThreads = 256;
-constexpr int kEmitTile = 2048;
+constexpr int kEmitTile = 1024;
 
 // first_j[b] = index (in depth order) of the Gaussian that owns output entry b * kEmitTile
 __global__ void emit_boundaries_kernel(int64_t n_vis, const int64_t* __restrict__ cum2, int32_t* __restrict__ first_j) {
@@ -267,10 +267,14 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
                                                                   const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
                                                                   float tile_size, int tile_w, int tile_h, int tile_n_bits,
                                                                   uint32_t* __restrict__ tkeys, int32_t* __restrict__ tvals) {
-    __shared__ int32_t s_end[kEmitTile + 1];    // cum2[j] - e0 (inclusive end offsets relative to the block)
-    __shared__ int32_t s_first[kEmitTile + 1];  // first tile id (y0 * tile_w + x0) of the Gaussian's box
-    __shared__ int32_t s_bw[kEmitTile + 1];
-    __shared__ int32_t s_idx[kEmitTile + 1];
+    // per staged Gaussian: the part [lo, hi) of its entries that falls into this block (block-relative), the
+    // offset k0 of entry `lo` inside the Gaussian's own tile list, its box and its flat index
+    __shared__ int16_t s_lo[kEmitTile + 1], s_hi[kEmitTile + 1];
+    __shared__ int32_t s_k0[kEmitTile + 1], s_first[kEmitTile + 1], s_idx[kEmitTile + 1];
+    __shared__ int16_t s_bw[kEmitTile + 1], s_large[kEmitTile + 1];  // box width in tiles (<= 32767), staged index
+    __shared__ uint32_t s_okey[kEmitTile];  // the block's output, staged so the global writes are fully coalesced
+    __shared__ int32_t s_oval[kEmitTile];
+    __shared__ int s_nlarge;
     const int64_t e0 = (int64_t)blockIdx.x * kEmitTile;
     const int64_t e1 = min(e0 + kEmitTile, n_isects);
     const int64_t j0 = first_j[blockIdx.x];
@@ -279,35 +283,62 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
         j1 = n_vis - 1;
     } else {
         const int64_t jn = first_j[blockIdx.x + 1];  // owns entry e1
-        j1 = (cum2[jn - (jn > 0 ? 1 : 0)] == e1 && jn > 0) ? jn - 1 : jn;  // jn starts exactly at e1 -> previous one owns e1-1
+        j1 = (jn > 0 && cum2[jn - 1] == e1) ? jn - 1 : jn;  // jn starts exactly at e1 -> the previous one owns e1-1
     }
     const int G = (int)(j1 - j0) + 1;  // every Gaussian has >= 1 entry, so G <= kEmitTile
+    if (threadIdx.x == 0) s_nlarge = 0;
+    __syncthreads();
     for (int g = threadIdx.x; g < G; g += kEmitThreads) {
         const int64_t j = j0 + g;
         const int idx = sorted_vals[j];
         const float2 m = means2d[idx];
         const TileBox tb = tile_box(m.x, m.y, radii[idx], tile_size, tile_w, tile_h);
-        s_end[g] = (int32_t)(min(cum2[j], e1) - e0);
-        s_first[g] = tb.y0 * tile_w + tb.x0;
-        s_bw[g] = tb.x1 - tb.x0;
+        const int64_t gs = j > 0 ? cum2[j - 1] : 0, ge = cum2[j];
+        const int64_t lo = max(gs, e0), hi = min(ge, e1);
+        s_lo[g] = (int16_t)(lo - e0);
+        s_hi[g] = (int16_t)(hi - e0);
+        s_k0[g] = (int32_t)(lo - gs);
+        s_first[g] = (int32_t)(((uint32_t)(idx / N) << tile_n_bits) | (uint32_t)(tb.y0 * tile_w + tb.x0));
+        s_bw[g] = (int16_t)(tb.x1 - tb.x0);
         s_idx[g] = idx;
+        if (hi - lo > 32) s_large[atomicAdd(&s_nlarge, 1)] = (int16_t)g;
     }
     __syncthreads();
-    const int64_t start0 = j0 > 0 ? cum2[j0 - 1] : 0;  // global start offset of the first overlapping Gaussian
-    for (int e = threadIdx.x; e < (int)(e1 - e0); e += kEmitThreads) {
-        // first g with s_end[g] > e
-        int lo = 0, hi = G - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (s_end[mid] > e) hi = mid; else lo = mid + 1;
+    // small pieces (<= 32 entries, the common case): one lane per Gaussian
+    for (int g = threadIdx.x; g < G; g += kEmitThreads) {
+        const int lo = s_lo[g], n = s_hi[g] - lo;
+        if (n > 32) continue;
+        const int bw = s_bw[g], idx = s_idx[g], first = s_first[g];
+        int ry = s_k0[g] / bw, rx = s_k0[g] - ry * bw;
+        for (int t = 0; t < n; ++t) {
+            s_okey[lo + t] = (uint32_t)(first + ry * tile_w + rx);
+            s_oval[lo + t] = idx;
+            if (++rx == bw) {
+                rx = 0;
+                ++ry;
+            }
         }
-        const int64_t gstart = lo > 0 ? (int64_t)s_end[lo - 1] + e0 : start0;  // earlier ones end inside the block: exact
-        const int k = (int)(e0 + e - gstart);
-        const int bw = s_bw[lo];
-        const int ry = k / bw, rx = k - ry * bw;
-        const int idx = s_idx[lo];
-        tkeys[e0 + e] = ((uint32_t)(idx / N) << tile_n_bits) | (uint32_t)(s_first[lo] + ry * tile_w + rx);
-        tvals[e0 + e] = idx;
+    }
+    // large pieces: one warp per Gaussian, coalesced
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nlarge = s_nlarge;
+    for (int i = warp; i < nlarge; i += kEmitThreads / 32) {
+        const int g = s_large[i];
+        const int lo = s_lo[g], n = s_hi[g] - lo, k0 = s_k0[g];
+        const int bw = s_bw[g], idx = s_idx[g], first = s_first[g];
+        const float inv_bw = 1.0f / (float)bw;
+        for (int t = lane; t < n; t += 32) {
+            const int k = k0 + t;
+            const int ry = (int)(((float)k + 0.5f) * inv_bw);  // exact: k < 2^16, margins 0.5/bw >> float error
+            const int rx = k - ry * bw;
+            s_okey[lo + t] = (uint32_t)(first + ry * tile_w + rx);
+            s_oval[lo + t] = idx;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < (int)(e1 - e0); t += kEmitThreads) {
+        tkeys[e0 + t] = s_okey[t];
+        tvals[e0 + t] = s_oval[t];
     }
 }
 
@@ -318,8 +349,10 @@ __global__ void compose_ids_ranges_kernel(int64_t n, const uint32_t* __restrict_
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t key = tkeys[i];
-    const uint32_t db = (uint32_t)__float_as_int(depths[flat[i]]);
-    isect_ids[i] = (int64_t)(((uint64_t)key << 32) | db);
+    if (isect_ids) {
+        const uint32_t db = (uint32_t)__float_as_int(depths[flat[i]]);
+        isect_ids[i] = (int64_t)(((uint64_t)key << 32) | db);
+    }
     if (!offsets) return;
     const uint32_t mask = (1u << tile_n_bits) - 1u;
     const int64_t cur = (int64_t)(key >> tile_n_bits) * n_tiles + (key & mask);
@@ -411,7 +444,7 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
         return QED_OK;
     }
     if (n_isects > 0x7fffffffLL) return QED_ERR_UNSUPPORTED;
-    if (!means2d || !radii || !depths || !prepare_workspace || !workspace || !isect_ids || !flatten_ids) return QED_ERR_BAD_ARG;
+    if (!means2d || !radii || !depths || !prepare_workspace || !workspace || !flatten_ids) return QED_ERR_BAD_ARG;
     if (workspace_bytes < qed_isect_fill_workspace_bytes(n_isects)) return QED_ERR_WORKSPACE;
     const int tile_n_bits = bit_length(n_tiles);
     const int cam_bits = bit_length(C - 1);

@@ -131,7 +131,7 @@ __device__ __forceinline__ void sh_bases_vjp(float x, float y, float z, const fl
 
 // DEG=-1: colours pass through.  VEC: coefficient rows 16-byte aligned and K*3 % 4 == 0.
 template <int DEG, bool VEC>
-__global__ void __launch_bounds__(kProjBwdThreads) project_bwd_kernel(const ProjBwdParams p) {
+__global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const ProjBwdParams p) {
     extern __shared__ float4 smem4[];
     CamB* cams = reinterpret_cast<CamB*>(smem4);
     constexpr int DG = DEG < 0 ? 0 : DEG;

@@ -39,10 +39,11 @@ class StepOutput:
 class FusedSplatStep:
     """Holds reusable device buffers; `forward()` renders, `step()` renders + loss + full backward."""
 
-    def __init__(self, device, sort_impl: str = "two_level"):
+    def __init__(self, device, sort_impl: str = "two_level", want_isect_ids: bool = False):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.sort_impl = sort_impl
+        self.want_isect_ids = want_isect_ids  # the compositor does not need the 64-bit keys; only `info` does
         self._total = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._counts = torch.zeros(2, dtype=torch.int64, device=self.device)
         self._counts_host = torch.zeros(2, dtype=torch.int64).pin_memory()
@@ -120,7 +121,7 @@ class FusedSplatStep:
             fws_bytes = lib.qed_isect_fill_workspace_bytes(M)
             fws = self._get("fill_ws", (fws_bytes,), torch.uint8)
             check(lib.qed_isect_fill(C, N, n_vis, M, ptr(means2d), ptr(radii), ptr(depths), tile, tw, th, ptr(pws), ptr(fws), fws_bytes,
-                                     ptr(ids) if M else None, ptr(flat) if M else None, ptr(offsets), stream), "qed_isect_fill")
+                                     ptr(ids) if (M and self.want_isect_ids) else None, ptr(flat) if M else None, ptr(offsets), stream), "qed_isect_fill")
             self._mark("isect_fill")
         else:
             cum = self._get("cum", (CN,), torch.int64)
