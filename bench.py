@@ -281,18 +281,31 @@ def main_ours(args):
     e2e = None
     if not args.no_e2e:
         params = [t.clone().requires_grad_(True) for t in (means, quats, scales, opac, sh)]
+        # the step's inputs come from pinned host memory on a copy stream (what a data loader does); the loss
+        # waits on the copy event, so the H2D of the ground truth overlaps projection/sort/compositing
+        copy_stream = torch.cuda.Stream()
+        vm_d, K_d = torch.empty_like(viewmats), torch.empty_like(Ks)
+        rgb_d, depth_d = torch.empty_like(gt_rgb), torch.empty_like(gt_depth)
+        cam_ready, gt_ready = torch.cuda.Event(), torch.cuda.Event()
 
         def e2e_step():
-            vm = vm_h.to(dev, non_blocking=True)
-            Kc = K_h.to(dev, non_blocking=True)
-            rgb_gt = gt_rgb_h.to(dev, non_blocking=True)
-            d_gt = gt_depth_h.to(dev, non_blocking=True)
+            copy_stream.wait_stream(torch.cuda.current_stream())  # previous step is done with the buffers
+            with torch.cuda.stream(copy_stream):
+                vm_d.copy_(vm_h, non_blocking=True)
+                K_d.copy_(K_h, non_blocking=True)
+                cam_ready.record(copy_stream)
+                rgb_d.copy_(gt_rgb_h, non_blocking=True)
+                depth_d.copy_(gt_depth_h, non_blocking=True)
+                gt_ready.record(copy_stream)
+            torch.cuda.current_stream().wait_event(cam_ready)
+            vm, Kc, rgb_gt, d_gt = vm_d, K_d, rgb_d, depth_d
             for p_ in params:
                 p_.grad = None
             render, alpha, info = rasterization(params[0], params[1], params[2], params[3], params[4], vm, Kc, width, height,
                                                 tile_size=16, packed=False, near_plane=0.01, far_plane=1e10, render_mode=args.mode,
                                                 sh_degree=3, sparse_grad=False, absgrad=True, rasterize_mode="classic")
             info["means2d"].retain_grad()
+            torch.cuda.current_stream().wait_event(gt_ready)
             # qed_splatter/model.py:295-306 and :87-116 as the reference writes them (torch ops)
             rgb = torch.clamp(render[..., :3] + (1 - alpha) * bg, 0.0, 1.0)
             depth = render[..., 3:4]

@@ -252,7 +252,7 @@ __device__ __forceinline__ int fill_queue(Staging<PX>& sm, int c0, int count, co
         sm.qa[warp][pos] = A;
         sm.qb[warp][pos] = B;
         sm.qc[warp][pos] = sm.sc[q];
-        sm.qm[warp][pos] = mask;
+        if (PX > 1) sm.qm[warp][pos] = mask;
     }
     __syncwarp();
     return __popc(m);
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(Shape<PX>::kThreads) raster_fwd_kernel(const R
             const int nq = fill_queue<PX, CULL, false>(sm, c0, count, sr, alive, nullptr);
             for (int q = 0; q < nq; ++q) {
                 const float4 A = sm.qa[warp][q], B = sm.qb[warp][q], Cc = sm.qc[warp][q];
-                const int mask = sm.qm[warp][q];
+                const int mask = PX > 1 ? sm.qm[warp][q] : 1;
                 if (lane == 0) st.add(2, __popc(mask));
                 float dx[S::kNX], ax[S::kNX], dy[S::kNY], cy[S::kNY];
 #pragma unroll
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(Shape<PX>::kThreads) raster_bwd_kernel(const R
             const int nq = fill_queue<PX, CULL, true>(sm, c0, count, sr, want, sub_max);
             for (int q = 0; q < nq; ++q) {
                 const float4 A = sm.qa[warp][q], B = sm.qb[warp][q], Cc = sm.qc[warp][q];
-                const int mask = sm.qm[warp][q];
+                const int mask = PX > 1 ? sm.qm[warp][q] : 1;
                 if (lane == 0) st.add(2, __popc(mask));
                 const int sid = __float_as_int(A.w);
                 float dx[S::kNX], ax[S::kNX], dy[S::kNY], cy[S::kNY];
