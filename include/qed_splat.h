@@ -195,15 +195,20 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  *           (model.py:83-85), i.e. SURVEY.md §8 rows a11-a13.
  *  render[C,H,W,4] (RGB + depth; depth normalised iff normalize_last), alphas[C,H,W],
  *  gt_rgb[C,H,W,3], gt_depth[C,H,W] (<=0 or non-finite = invalid), bg[3].
- *  loss = rgb_weight * mean|clamp(rgb + (1-a) bg) - gt| + depth_lambda * mean_valid|depth - gt_depth|
- *  Two launches: a reduction for n_valid / loss sums, then the per-pixel gradient.
- *  stats_dev[C*8] (double, per camera): {sum|rgb err|, sum|depth err|, n_valid, (scratch), max depth, 0..}; loss_dev[3] float:
- *  {total, rgb term, depth term}.  grad_scale multiplies every gradient (1/total views for a sharded batch).
+ *  loss = rgb_weight * mean|clamp(rgb + (1-a) bg) - gt| + ssim_lambda * (1 - SSIM(clamped rgb, gt))
+ *         + depth_lambda * mean_valid|depth - gt_depth|,  per camera (one camera = one reference step: its own
+ *         depth fill / n_valid), then the mean over cameras.  splatfacto: rgb_weight = 1 - ssim_lambda = 0.8.
+ *  SSIM = pytorch_msssim.SSIM(data_range=1, channel=3): 11x11 Gaussian window (sigma 1.5), valid convolution,
+ *         mean over channels and pixels; ssim_lambda == 0 skips it (then workspace may be NULL).
+ *  stats_dev[C*8] (double, per camera): {sum|rgb err|, sum|depth err|, n_valid, (scratch), max depth, sum SSIM map, ..};
+ *  loss_dev[3] float: {total, rgb term (L1 + SSIM), depth term}.  grad_scale multiplies every gradient
+ *  (local_views / total_views for a view-sharded batch).  v_render / v_alphas are overwritten.
  */
+size_t qed_loss_workspace_bytes(int C, int width, int height, float ssim_lambda);
 int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
                      const float* gt_rgb, const float* gt_depth, const float* bg, float rgb_weight,
-                     float depth_lambda, float grad_scale, double* stats_dev, float* loss_dev,
-                     float* v_render, float* v_alphas, qed_stream_t stream);
+                     float depth_lambda, float ssim_lambda, float grad_scale, double* stats_dev, float* loss_dev,
+                     float* v_render, float* v_alphas, void* workspace, size_t workspace_bytes, qed_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * trainer-side kernels

@@ -49,6 +49,8 @@ __all__ = [
     "composite_and_fill",
     "depth_l1_loss",
     "rgb_l1_loss",
+    "ssim",
+    "rgb_loss",
     "ALPHA_THRESHOLD",
     "TRANSMITTANCE_THRESHOLD",
     "MAX_ALPHA",
@@ -576,3 +578,35 @@ def rgb_l1_loss(rgb: Tensor, gt: Tensor, ssim_lambda: float = 0.2) -> Tensor:
     """(1-ssim_lambda) * mean|gt - rgb| — the L1 part of splatfacto's RGB loss reached from
     qed_splatter/model.py:83-85 (the SSIM part is SURVEY §8f#1, not on this round's path)."""
     return (1.0 - ssim_lambda) * torch.abs(gt - rgb).mean()
+
+
+def ssim(pred: Tensor, gt: Tensor) -> Tensor:
+    """pytorch_msssim.SSIM(data_range=1.0, size_average=True, channel=3) as nerfstudio's splatfacto uses it
+    (reached from qed_splatter/model.py:83-85): 11x11 Gaussian window (sigma 1.5), separable "valid"
+    convolution per channel, mean of the SSIM map over channels and pixels.  pred/gt: [B,H,W,3] in [0,1]."""
+    import torch.nn.functional as F
+
+    X = gt.permute(0, 3, 1, 2)
+    Y = pred.permute(0, 3, 1, 2)
+    coords = torch.arange(11, dtype=torch.float64) - 5
+    g = torch.exp(-(coords ** 2) / (2 * 1.5 ** 2))
+    g = (g / g.sum()).to(pred.dtype)
+    ch = X.shape[1]
+
+    def filt(t):
+        t = F.conv2d(t, g.view(1, 1, 11, 1).expand(ch, 1, 11, 1), groups=ch)
+        return F.conv2d(t, g.view(1, 1, 1, 11).expand(ch, 1, 1, 11), groups=ch)
+
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    mu1, mu2 = filt(X), filt(Y)
+    s1 = filt(X * X) - mu1 * mu1
+    s2 = filt(Y * Y) - mu2 * mu2
+    s12 = filt(X * Y) - mu1 * mu2
+    cs = (2 * s12 + C2) / (s1 + s2 + C2)
+    ssim_map = ((2 * mu1 * mu2 + C1) / (mu1 * mu1 + mu2 * mu2 + C1)) * cs
+    return ssim_map.flatten(2).mean(-1).mean()
+
+
+def rgb_loss(rgb: Tensor, gt: Tensor, ssim_lambda: float = 0.2) -> Tensor:
+    """splatfacto RGB loss: (1 - ssim_lambda) * L1 + ssim_lambda * (1 - SSIM)."""
+    return (1.0 - ssim_lambda) * torch.abs(gt - rgb).mean() + ssim_lambda * (1.0 - ssim(rgb, gt))

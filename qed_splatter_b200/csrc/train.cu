@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
                                                                 const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth,
                                                                 const float* __restrict__ bg, float rgb_weight, float depth_lambda, float grad_scale,
                                                                 double* __restrict__ stats, float4* __restrict__ v_render, float* __restrict__ v_alphas,
-                                                                int phase) {
+                                                                float* __restrict__ pred_rgb /* phase 0 out, or NULL */,
+                                                                const float* __restrict__ v_rgb_extra /* phase 1 in, or NULL */, int phase) {
     // phase 0: count n_valid + loss sums (needs max depth); phase 1: gradients (needs n_valid)
     const int cam = blockIdx.y;
     const float maxd = __int_as_float(*reinterpret_cast<const int*>(stats + cam * 8 + 3));
@@ -65,16 +66,27 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
         const float d = (a > 0.0f) ? r.w : maxd;
         const bool valid = finitef(d) && finitef(gd) && (gd > 0.0f);
         if (phase == 0) {
+            if (pred_rgb) {
+                pred_rgb[pix * 3 + 0] = c0;
+                pred_rgb[pix * 3 + 1] = c1;
+                pred_rgb[pix * 3 + 2] = c2;
+            }
             s_rgb += (double)(fabsf(e0) + fabsf(e1) + fabsf(e2));
             if (valid) {
                 s_d += (double)fabsf(d - gd);
                 s_n += 1.0;
             }
         } else {
+            float x0 = 0.f, x1 = 0.f, x2 = 0.f;  // gradient of the SSIM term w.r.t. the clamped rgb
+            if (v_rgb_extra) {
+                x0 = v_rgb_extra[pix * 3 + 0];
+                x1 = v_rgb_extra[pix * 3 + 1];
+                x2 = v_rgb_extra[pix * 3 + 2];
+            }
             float4 v;
-            v.x = (pre0 >= 0.0f && pre0 <= 1.0f) ? g_rgb * signf(e0) : 0.0f;
-            v.y = (pre1 >= 0.0f && pre1 <= 1.0f) ? g_rgb * signf(e1) : 0.0f;
-            v.z = (pre2 >= 0.0f && pre2 <= 1.0f) ? g_rgb * signf(e2) : 0.0f;
+            v.x = (pre0 >= 0.0f && pre0 <= 1.0f) ? g_rgb * signf(e0) + x0 : 0.0f;
+            v.y = (pre1 >= 0.0f && pre1 <= 1.0f) ? g_rgb * signf(e1) + x1 : 0.0f;
+            v.z = (pre2 >= 0.0f && pre2 <= 1.0f) ? g_rgb * signf(e2) + x2 : 0.0f;
             v.w = (valid && a > 0.0f) ? g_d * signf(d - gd) : 0.0f;
             v_render[pix] = v;
             v_alphas[pix] = -(v.x * b0 + v.y * b1 + v.z * b2);
@@ -95,17 +107,19 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
     }
 }
 
-__global__ void loss_finalize_kernel(int C, int64_t HW, float rgb_weight, float depth_lambda, double* __restrict__ stats, float* __restrict__ loss) {
+__global__ void loss_finalize_kernel(int C, int64_t HW, float rgb_weight, float depth_lambda, float ssim_lambda, double ssim_count,
+                                     double* __restrict__ stats, float* __restrict__ loss) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double lr = 0.0, ld = 0.0;
+    double lr = 0.0, ld = 0.0, ls = 0.0;
     for (int c = 0; c < C; ++c) {
         double* s = stats + c * 8;
         lr += s[0] / ((double)HW * 3.0);
+        if (ssim_lambda > 0.0f) ls += 1.0 - s[5] / ssim_count;
         ld += s[2] > 0.0 ? s[1] / s[2] : 0.0;
         float maxd = __int_as_float(*reinterpret_cast<const int*>(s + 3));
         s[4] = (double)maxd;
     }
-    lr = rgb_weight * lr / C;
+    lr = rgb_weight * lr / C + ssim_lambda * ls / C;
     ld = depth_lambda * ld / C;
     loss[0] = (float)(lr + ld);
     loss[1] = (float)lr;
@@ -174,27 +188,56 @@ __global__ void strategy_update_kernel(int C, int N, const float4* __restrict__ 
 
 using namespace qed;
 
+int qed_ssim_launch(int C, int W, int H, const float* pred, const float* gt, float* dmaps, double* stats, float scale, float* v_pred,
+                    cudaStream_t stream);  // ssim.cu
+
+extern "C" size_t qed_loss_workspace_bytes(int C, int width, int height, float ssim_lambda) {
+    if (!(ssim_lambda > 0.0f) || C <= 0) return 0;
+    const size_t px = (size_t)C * width * height;
+    return px * 3 * 4 /* clamped rgb */ + px * 9 * 4 /* derivative maps (upper bound) */ + px * 3 * 4 /* v_ssim */;
+}
+
 extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
                                 const float* gt_rgb, const float* gt_depth, const float* bg, float rgb_weight,
-                                float depth_lambda, float grad_scale, double* stats_dev, float* loss_dev,
-                                float* v_render, float* v_alphas, qed_stream_t stream_) {
+                                float depth_lambda, float ssim_lambda, float grad_scale, double* stats_dev, float* loss_dev,
+                                float* v_render, float* v_alphas, void* workspace, size_t workspace_bytes, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (C <= 0 || width <= 0 || height <= 0) return QED_ERR_BAD_ARG;
     if (!render || !alphas || !gt_rgb || !gt_depth || !bg || !stats_dev || !loss_dev || !v_render || !v_alphas) return QED_ERR_BAD_ARG;
-    if (C > 65535) return QED_ERR_UNSUPPORTED;
+    if (C > 21845) return QED_ERR_UNSUPPORTED;
+    const bool use_ssim = ssim_lambda > 0.0f;
+    if (use_ssim) {
+        if (!workspace) return QED_ERR_BAD_ARG;
+        if (workspace_bytes < qed_loss_workspace_bytes(C, width, height, ssim_lambda)) return QED_ERR_WORKSPACE;
+        if (width <= 10 || height <= 10) return QED_ERR_UNSUPPORTED;
+    }
     const int64_t HW = (int64_t)width * height;
+    const size_t px = (size_t)C * HW;
+    float* pred_rgb = use_ssim ? reinterpret_cast<float*>(workspace) : nullptr;
+    float* dmaps = use_ssim ? pred_rgb + px * 3 : nullptr;
+    float* v_ssim = use_ssim ? dmaps + px * 9 : nullptr;
     QED_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, (size_t)C * 8 * sizeof(double), stream));
     int bx = (int)((HW + kLossThreads * 4 - 1) / (kLossThreads * 4));
     if (bx > 148 * 8) bx = 148 * 8;
     dim3 grid(bx, C);
     loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, stats_dev);
     QED_LAUNCH_CHECK();
-    for (int phase = 0; phase < 2; ++phase) {
-        loss_grad_kernel<<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg, rgb_weight,
-                                                            depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render), v_alphas, phase);
-        QED_LAUNCH_CHECK();
+    loss_grad_kernel<<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg, rgb_weight,
+                                                        depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render), v_alphas, pred_rgb,
+                                                        nullptr, 0);
+    QED_LAUNCH_CHECK();
+    const double ssim_count = (double)(width - 10) * (double)(height - 10) * 3.0;
+    if (use_ssim) {
+        // loss term = ssim_lambda * (1 - mean(map)) per camera, mean over cameras
+        const float scale = -ssim_lambda * grad_scale / ((float)C * (float)ssim_count);
+        int rc = qed_ssim_launch(C, width, height, pred_rgb, gt_rgb, dmaps, stats_dev, scale, v_ssim, stream);
+        if (rc != QED_OK) return rc;
     }
-    loss_finalize_kernel<<<1, 32, 0, stream>>>(C, HW, rgb_weight, depth_lambda, stats_dev, loss_dev);
+    loss_grad_kernel<<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg, rgb_weight,
+                                                        depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render), v_alphas, nullptr,
+                                                        v_ssim, 1);
+    QED_LAUNCH_CHECK();
+    loss_finalize_kernel<<<1, 32, 0, stream>>>(C, HW, rgb_weight, depth_lambda, use_ssim ? ssim_lambda : 0.0f, ssim_count, stats_dev, loss_dev);
     QED_LAUNCH_CHECK();
     return QED_OK;
 }

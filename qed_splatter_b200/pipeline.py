@@ -201,8 +201,9 @@ class FusedSplatStep:
     def step(self, means, quats, scales, opacities, sh, viewmats, Ks, width: int, height: int, sh_degree: int,
              gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, render_mode: str = "RGB+ED", rgb_weight: float = 0.8,
              depth_lambda: float = 0.2, grad_scale: float = 1.0, rasterize_mode: str = "classic",
-             grad_out: Optional[Dict[str, Tensor]] = None) -> StepOutput:
-        """`render_mode` RGB+ED (north_star) or RGB+D (what qed_splatter/model.py:257 passes)."""
+             grad_out: Optional[Dict[str, Tensor]] = None, ssim_lambda: float = 0.0) -> StepOutput:
+        """`render_mode` RGB+ED (north_star) or RGB+D (what qed_splatter/model.py:257 passes).
+        loss = rgb_weight * L1 + ssim_lambda * (1 - SSIM) + depth_lambda * masked depth-L1 (splatfacto: 0.8 / 0.2 / 0.2)."""
         assert render_mode in ("RGB+D", "RGB+ED")
         lib, stream = self.lib, current_stream()
         render, alphas = self.forward(means, quats, scales, opacities, sh, viewmats, Ks, width, height, sh_degree, render_mode,
@@ -212,9 +213,11 @@ class FusedSplatStep:
             self._stats = torch.zeros(C * 8, dtype=torch.float64, device=self.device)
         v_render = self._get("v_render", (C, height, width, 4))
         v_alphas = self._get("v_alphas", (C, height, width, 1))
+        lws_bytes = lib.qed_loss_workspace_bytes(C, width, height, ssim_lambda)
+        lws = self._get("loss_ws", (lws_bytes,), torch.uint8) if lws_bytes else None
         check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), ptr(gt_depth), ptr(background), rgb_weight,
-                                   depth_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas), stream),
-              "qed_loss_fwd_bwd")
+                                   depth_lambda, ssim_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas),
+                                   ptr(lws), lws_bytes, stream), "qed_loss_fwd_bwd")
         self._mark("loss")
         grads, packed = self.backward(v_render, v_alphas, grad_out)
         self._last_v = (v_render, v_alphas)

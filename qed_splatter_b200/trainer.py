@@ -375,7 +375,8 @@ class SplatTrainer:
         tmp = {"means": gv["means"], "quats": gv["quats"], "sh": gv["sh"], "scales": torch.empty_like(scales), "opacities": torch.empty_like(opac)}
         out = self._fused.step(pv["means"], pv["quats"], scales, opac, pv["sh"], viewmats, Ks, width, height, self.sh_degree_to_use(),
                                gt_rgb, gt_depth, background, render_mode=c.render_mode, rgb_weight=1.0 - c.ssim_lambda,
-                               depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, grad_out=tmp)
+                               depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, grad_out=tmp,
+                               ssim_lambda=c.ssim_lambda)
         # activations' chain rule straight into the arena (model.py:269-271: exp, sigmoid)
         torch.mul(tmp["scales"], scales, out=gv["scales"])
         torch.mul(tmp["opacities"], opac * (1.0 - opac), out=gv["opacities"])

@@ -68,6 +68,31 @@ def test_fused_step_matches_oracle(cuda, mode, C):
     assert_close_frac(pk[..., :2], io["means2d"].grad, 1e-3, 1e-3 * scale, 5e-3, "packed v_means2d")
 
 
+@pytest.mark.parametrize("size", [80, 53])
+def test_fused_step_with_ssim_matches_oracle(cuda, size):
+    """Full splatfacto RGB loss (0.8 L1 + 0.2 (1 - SSIM)) + depth-L1, gradient through the fused kernels."""
+    s = scene_s0(N=2500, C=2, size=size)
+    s.scales = s.scales * 2.0
+    lo = {k: getattr(s, k).clone().requires_grad_(True) for k in NAMES}
+    bg = torch.tensor([0.3, 0.1, 0.6])
+    ro, ao, io = oracle.rasterization(lo["means"], lo["quats"], lo["scales"], lo["opacities"], lo["sh"], s.viewmats, s.Ks, s.width, s.height,
+                                      sh_degree=3, render_mode="RGB+D")
+    total = 0.0
+    for c in range(s.C):
+        rgb, depth = oracle.composite_and_fill(ro[c:c + 1], ao[c:c + 1], bg)
+        total = total + oracle.rgb_loss(rgb, s.gt_rgb[c:c + 1], 0.2) + oracle.depth_l1_loss(depth, s.gt_depth[c:c + 1], 0.2)
+    loss_o = total / s.C
+    loss_o.backward()
+    g = s.to(cuda)
+    fs = FusedSplatStep(cuda)
+    out = fs.step(g.means, g.quats, g.scales, g.opacities, g.sh, g.viewmats, g.Ks, g.width, g.height, 3, g.gt_rgb, g.gt_depth, bg.to(cuda),
+                  render_mode="RGB+D", rgb_weight=0.8, ssim_lambda=0.2)
+    assert float(out.loss[0]) == pytest.approx(float(loss_o), rel=2e-4)
+    for k in NAMES:
+        scale = float(lo[k].grad.abs().mean()) + 1e-12
+        assert_close_frac(out.grads[k], lo[k].grad, 1e-3, 1e-3 * scale, 5e-3, f"v_{k}")
+
+
 def test_view_sharding_equals_single_rank(cuda):
     """2 'ranks' x 1 view with grad_scale = 1/2, summed (what the all-reduce does) == 1 rank x 2 views."""
     s = scene_s0(N=3000, C=2, size=96).to(cuda)

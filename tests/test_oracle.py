@@ -216,3 +216,27 @@ def test_golden_fixture(name):
     for k in names:
         ref = z["grad_" + k]
         assert np.allclose(leaves[k].grad.numpy(), ref, rtol=1e-3, atol=1e-5 * float(np.abs(ref).mean() + 1e-12) * 100), k
+
+
+def test_ssim_against_direct_window_sum():
+    """Separable conv == direct 11x11 window sum; SSIM(x, x) == 1; range sanity."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(1, 20, 23, 3, generator=g, dtype=torch.float64)
+    y = (x + 0.1 * torch.randn(x.shape, generator=g, dtype=torch.float64)).clamp(0, 1)
+    assert float(oracle.ssim(x, x)) == pytest.approx(1.0, abs=1e-12)
+    c = torch.arange(11, dtype=torch.float64) - 5
+    w1 = torch.exp(-(c ** 2) / (2 * 1.5 ** 2))
+    w1 = w1 / w1.sum()
+    w2 = w1[:, None] * w1[None, :]
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    vals = []
+    for ch in range(3):
+        for i in range(20 - 10):
+            for j in range(23 - 10):
+                px, py = x[0, i:i + 11, j:j + 11, ch], y[0, i:i + 11, j:j + 11, ch]
+                m1, m2 = (w2 * px).sum(), (w2 * py).sum()
+                s1, s2, s12 = (w2 * px * px).sum() - m1 * m1, (w2 * py * py).sum() - m2 * m2, (w2 * px * py).sum() - m1 * m2
+                vals.append(((2 * m1 * m2 + C1) * (2 * s12 + C2)) / ((m1 * m1 + m2 * m2 + C1) * (s1 + s2 + C2)))
+    direct = torch.stack(vals).mean()
+    assert float(oracle.ssim(y, x)) == pytest.approx(float(direct), rel=1e-10)
+    assert 0.0 < float(direct) < 1.0
