@@ -227,9 +227,9 @@ def main_ours(args):
         _lib.check(lib.qed_strategy_update(1, N, _lib.ptr(out.packed_grads), 1, _lib.ptr(out.radii), width, height, world, _lib.ptr(stats[0]),
                                            _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.current_stream()), "qed_strategy_update")
         if world > 1:
+            # gradients every step; the densification accumulators are reduced only when a refine step consumes
+            # them (SUM / MAX are associative), exactly as trainer.SplatTrainer does
             dist.all_reduce(arena)
-            dist.all_reduce(stats[:2])
-            dist.all_reduce(stats[2], op=dist.ReduceOp.MAX)
         return out
 
     def barrier():
@@ -275,7 +275,7 @@ def main_ours(args):
 
     # ---- pair counters for the compositing roofline (instrumented launches, outside any timed region) ----
     counters = fs.count_pairs()
-    launches_per_step = fs.launches_per_step + 1 + (3 if world > 1 else 0)
+    launches_per_step = fs.launches_per_step + 1 + (1 if world > 1 else 0)
 
     # ---- e2e through the public API with host buffers ----
     e2e = None
@@ -383,7 +383,8 @@ def main_ours(args):
             "config": {
                 "workload": f"S1 (BASELINE.json configs[1]): {N} Gaussians (SH degree 3), one {width}x{height} view per GPU, "
                             f"{args.mode} forward + RGB-L1/depth-L1 loss + backward to means/quats/scales/opacities/SH",
-                "parallelism": f"view-sharded x{world}, replicated Gaussians, NCCL all-reduce of the {PARAM_FLOATS * 4} B/Gaussian gradient arena + densification stats",
+                "parallelism": f"view-sharded x{world}, replicated Gaussians, NCCL all-reduce of the {PARAM_FLOATS * 4} B/Gaussian gradient arena every step "
+                               "(densification accumulators are all-reduced when a refine step consumes them, not per step)",
                 "cache": "inputs larger than L2: 236 MB parameters + %.0f MB intermediates per step vs 126 MB L2; no explicit flush" % ((N * 150 + M * 24) / 1e6),
                 "sort": args.sort, "n_visible": n_visible, "n_isects": M, "loss": loss,
                 "mean_gaussians_composited_per_pixel": counters.get("fwd_pairs_contributing", 0) / float(width * height),
