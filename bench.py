@@ -36,6 +36,10 @@ METRIC = "fwd+bwd RGB+depth Mpix/s"
 UNIT = "Mpix/s"
 PARAM_FLOATS = 3 + 4 + 3 + 1 + 48  # means, quats, scales, opacity, SH(16x3) = 59 floats / Gaussian
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
+# workload (profiles/r01_raster_bwd_ncu_summary.txt, profiles/r01_kernel_notes.md); None = not captured
+NCU_DRAM_BYTES = {"raster_bwd": 146.94e6 + 7.76e6, "raster_fwd": 52.36e6 + 18.31e6}
+
 # SURVEY.md §8(d) per-unit figures (D = 4 channels)
 FLOP_PER_PAIR_FWD = 30.0
 FLOP_PER_PAIR_BWD = 100.0
@@ -56,6 +60,7 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--mode", default="RGB+ED", choices=["RGB+ED", "RGB+D"])
     ap.add_argument("--sort", default="two_level", choices=["two_level", "own", "cub"])
+    ap.add_argument("--comm-chunks", type=int, default=1, help="Gaussian ranges of the projection backward whose SH gradients are all-reduced while the next range computes (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -221,15 +226,28 @@ def main_ours(args):
         o += n
     stats = torch.zeros(3, N, device=dev)  # grad2d, count, radii_max (DefaultStrategy state)
 
+    n_chunks = args.comm_chunks if world > 1 else 1
+    sh_begin = 11 * N  # arena = [means 3N | quats 4N | scales 3N | opacities N | sh 48N]
+    pending = []
+
+    def on_chunk(k, n0, n1):
+        # the SH block is 81 % of the gradient bytes: reduce each finished Gaussian range while the projection
+        # backward of the next range is still running (NCCL runs on its own stream)
+        pending.append(dist.all_reduce(arena[sh_begin + 48 * n0: sh_begin + 48 * n1], async_op=True))
+
     def step():
         out = fs.step(means, quats, scales, opac, sh, viewmats, Ks, width, height, 3, gt_rgb, gt_depth, bg, render_mode=args.mode,
-                      grad_scale=1.0 / world, grad_out=views)
+                      grad_scale=1.0 / world, grad_out=views, n_chunks=n_chunks, on_chunk=on_chunk if world > 1 else None)
         _lib.check(lib.qed_strategy_update(1, N, _lib.ptr(out.packed_grads), 1, _lib.ptr(out.radii), width, height, world, _lib.ptr(stats[0]),
                                            _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.current_stream()), "qed_strategy_update")
         if world > 1:
-            # gradients every step; the densification accumulators are reduced only when a refine step consumes
-            # them (SUM / MAX are associative), exactly as trainer.SplatTrainer does
-            dist.all_reduce(arena)
+            # gradients every step (SH ranges already in flight, then the 11 small floats per Gaussian); the
+            # densification accumulators are reduced only when a refine step consumes them (SUM / MAX are
+            # associative), exactly as trainer.SplatTrainer does
+            pending.append(dist.all_reduce(arena[:sh_begin], async_op=True))
+            for w in pending:
+                w.wait()
+            pending.clear()
         return out
 
     def barrier():
@@ -275,7 +293,7 @@ def main_ours(args):
 
     # ---- pair counters for the compositing roofline (instrumented launches, outside any timed region) ----
     counters = fs.count_pairs()
-    launches_per_step = fs.launches_per_step + 1 + (1 if world > 1 else 0)
+    launches_per_step = fs.launches_per_step + 1 + ((n_chunks - 1) + (n_chunks + 1) if world > 1 else 0)
 
     # ---- e2e through the public API with host buffers ----
     e2e = None
@@ -354,7 +372,7 @@ def main_ours(args):
                 return None
             ach = pairs * flop_per_pair / (t_ms * 1e-3) / 1e12
             return {"kernel": name, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-                    "traffic": None, "ms": t_ms, "pairs_evaluated": pairs, "flop_per_pair": flop_per_pair,
+                    "traffic": NCU_DRAM_BYTES.get(name), "ms": t_ms, "pairs_evaluated": pairs, "flop_per_pair": flop_per_pair,
                     "peak_source": f"derived: 148 SM x 128 lanes x 2 FLOP x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)"}
 
         def hbm_roof(name, bytes_):
@@ -363,7 +381,7 @@ def main_ours(args):
                 return None
             ach = bytes_ / (t_ms * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "ms": t_ms, "algorithmic_bytes": bytes_, "peak_source": hbm_src}
+                    "traffic": NCU_DRAM_BYTES.get(name), "ms": t_ms, "algorithmic_bytes": bytes_, "peak_source": hbm_src}
 
         end_bit = 32 + (((width + 15) // 16) * ((height + 15) // 16)).bit_length() + 1
         passes = (end_bit + 7) // 8

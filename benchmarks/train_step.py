@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--refine-every", type=int, default=100)
     ap.add_argument("--start-step", type=int, default=600, help="schedule position (SH degree / densify windows)")
+    ap.add_argument("--comm-chunks", type=int, default=None, help="override TrainConfig.comm_chunks")
+    ap.add_argument("--no-chunk-bwd", action="store_true")
     a = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -39,6 +41,9 @@ def main():
     make = scene_s2 if a.scene == "s2" else scene_s3
     s = make(N=a.gaussians, C=1, view_offset=rank, total_views=world)
     cfg = TrainConfig(refine_every=a.refine_every, render_mode="RGB+D")
+    if a.comm_chunks is not None:
+        cfg.comm_chunks = a.comm_chunks
+    cfg.chunk_project_bwd = not a.no_chunk_bwd
     tr = SplatTrainer(s.means.to(dev), s.quats.to(dev), torch.log(s.scales).to(dev), torch.logit(s.opacities.clamp(1e-4, 1 - 1e-4)).to(dev),
                       s.sh.to(dev), cfg=cfg, rank=rank, world_size=world, backend="cuda")
     tr.step_count = a.start_step
@@ -77,7 +82,7 @@ def main():
     if rank == 0:
         print(json.dumps({"scene": a.scene, "gaussians_start": a.gaussians, "gaussians_end": tr.arena.N, "n_gpus": world, "steps": a.steps,
                           "ms_per_step": ms, "train_iters_per_s": 1e3 / ms, "views_per_s": world * 1e3 / ms,
-                          "mpix_per_s": world * W * H / ms / 1e3, "width": W, "height": H, "refines": refines[:4], "loss": [float(x) for x in loss.tolist()],
+                          "mpix_per_s": world * W * H / ms / 1e3, "comm_chunks": cfg.comm_chunks, "width": W, "height": H, "refines": refines[:4], "loss": [float(x) for x in loss.tolist()],
                           "n_isects_last": tr._fused._fwd["M"]}))
     if world > 1:
         dist.destroy_process_group()

@@ -16,23 +16,16 @@ constexpr int kLossThreads = 256;
 __device__ __forceinline__ float signf(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
 __device__ __forceinline__ bool finitef(float x) { return fabsf(x) <= 3.402823466e38f; }
 
-// pass 1: per camera n_valid and max depth (depth channel >= 0, so int ordering of the bits works)
-__global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, const float4* __restrict__ render, const float* __restrict__ alphas,
-                                                                 const float* __restrict__ gt_depth, double* __restrict__ stats) {
+// pass 1: per camera max of the depth channel (the fill value of model.py:304-306).  The channel is >= 0, so the
+// integer order of the float bits is the float order and atomicMax on the bits works.
+__global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, const float4* __restrict__ render, double* __restrict__ stats) {
     const int cam = blockIdx.y;
     float maxd = 0.0f;
-    int has_neg = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
-        const float d = render[cam * HW + i].w;
-        if (d > maxd) maxd = d;
-        has_neg |= (d != d);
-    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x)
+        maxd = fmaxf(maxd, render[cam * HW + i].w);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats + cam * 8 + 3), __float_as_int(maxd));
-    (void)has_neg;
-    (void)alphas;
-    (void)gt_depth;
 }
 
 // pass 2: gradients + loss sums
@@ -220,7 +213,7 @@ extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* rende
     int bx = (int)((HW + kLossThreads * 4 - 1) / (kLossThreads * 4));
     if (bx > 148 * 8) bx = 148 * 8;
     dim3 grid(bx, C);
-    loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, stats_dev);
+    loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), stats_dev);
     QED_LAUNCH_CHECK();
     loss_grad_kernel<<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg, rgb_weight,
                                                         depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render), v_alphas, pred_rgb,

@@ -49,7 +49,6 @@ class FusedSplatStep:
         self._counts_host = torch.zeros(2, dtype=torch.int64).pin_memory()
         self._stats = None
         self._loss = torch.zeros(3, device=self.device)
-        self._cap_isects = 0
         self._buf: Dict[str, Tensor] = {}
         self.marks = None  # set to [] to record (name, cuda event) after every stage (bench.py stage timing)
 
@@ -165,9 +164,14 @@ class FusedSplatStep:
 
     # -- backward from explicit output gradients ------------------------------------------------
     @torch.no_grad()
-    def backward(self, v_render: Tensor, v_alphas: Optional[Tensor], grad_out: Optional[Dict[str, Tensor]] = None):
+    def backward(self, v_render: Tensor, v_alphas: Optional[Tensor], grad_out: Optional[Dict[str, Tensor]] = None,
+                 n_chunks: int = 1, on_chunk=None):
         """`grad_out`: optional preallocated {means,quats,scales,opacities,sh} (e.g. views into a flat
-        all-reduce arena) that the projection backward writes straight into."""
+        all-reduce arena) that the projection backward writes straight into.
+
+        `n_chunks` > 1 (single-camera calls only) launches the projection backward over `n_chunks` Gaussian
+        ranges and calls `on_chunk(k, n0, n1)` after each launch, so a caller can start the all-reduce of a
+        finished range while the next one is still being computed (view-sharded training)."""
         lib, stream, f = self.lib, current_stream(), self._fwd
         C, N, D, M = f["C"], f["N"], f["D"], f["M"]
         means, quats, scales, opacities, sh, viewmats, Ks = f["inputs"]
@@ -188,10 +192,26 @@ class FusedSplatStep:
             v_scales = torch.empty_like(scales)
             v_opac = torch.empty_like(opacities)
             v_sh = torch.empty_like(sh) if f["n_color"] else None
-        check(lib.qed_project_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh) if f["n_color"] else None, f["K"],
-                                  f["deg"], 0, ptr(viewmats), ptr(Ks), f["width"], f["height"], f["eps2d"], int(f["comp"]), f["n_color"],
-                                  f["append"], ptr(f["radii"]), ptr(f["conics"]), ptr(f["comps"]), None, None, None, None, None,
-                                  ptr(packed), ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_opac), ptr(v_sh), stream), "qed_project_bwd")
+        if C != 1 or n_chunks <= 1 or N < 4 * n_chunks:
+            bounds = [(0, N)]
+        else:
+            step_n = ((N + n_chunks - 1) // n_chunks + 3) // 4 * 4  # multiples of 4 keep every slice 16-byte aligned
+            bounds = [(a, min(a + step_n, N)) for a in range(0, N, step_n)]
+        has_sh = bool(f["n_color"])
+        for k, (n0, n1) in enumerate(bounds):
+            # C == 1 when chunked: flat index == n, so a range is just a pointer offset on every [N,...] / [1,N,...] array
+            sl = slice(n0, n1)
+            check(lib.qed_project_bwd(C, n1 - n0, ptr(means[sl]), ptr(quats[sl]), ptr(scales[sl]), ptr(opacities[sl]),
+                                      ptr(sh[sl]) if has_sh else None, f["K"], f["deg"], 0, ptr(viewmats), ptr(Ks), f["width"], f["height"],
+                                      f["eps2d"], int(f["comp"]), f["n_color"], f["append"],
+                                      ptr(f["radii"][:, sl] if len(bounds) > 1 else f["radii"]),
+                                      ptr(f["conics"][:, sl] if len(bounds) > 1 else f["conics"]),
+                                      ptr((f["comps"][:, sl] if len(bounds) > 1 else f["comps"]) if f["comps"] is not None else None),
+                                      None, None, None, None, None, ptr(packed[n0:n1] if len(bounds) > 1 else packed),
+                                      ptr(v_means[sl]), ptr(v_quats[sl]), ptr(v_scales[sl]), ptr(v_opac[sl]),
+                                      ptr(v_sh[sl]) if has_sh else None, stream), "qed_project_bwd")
+            if on_chunk is not None:
+                on_chunk(k, n0, n1)
         self._mark("project_bwd")
         grads = dict(means=v_means, quats=v_quats, scales=v_scales, opacities=v_opac, sh=v_sh)
         return grads, packed
@@ -201,7 +221,7 @@ class FusedSplatStep:
     def step(self, means, quats, scales, opacities, sh, viewmats, Ks, width: int, height: int, sh_degree: int,
              gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, render_mode: str = "RGB+ED", rgb_weight: float = 0.8,
              depth_lambda: float = 0.2, grad_scale: float = 1.0, rasterize_mode: str = "classic",
-             grad_out: Optional[Dict[str, Tensor]] = None, ssim_lambda: float = 0.0) -> StepOutput:
+             grad_out: Optional[Dict[str, Tensor]] = None, ssim_lambda: float = 0.0, n_chunks: int = 1, on_chunk=None) -> StepOutput:
         """`render_mode` RGB+ED (north_star) or RGB+D (what qed_splatter/model.py:257 passes).
         loss = rgb_weight * L1 + ssim_lambda * (1 - SSIM) + depth_lambda * masked depth-L1 (splatfacto: 0.8 / 0.2 / 0.2)."""
         assert render_mode in ("RGB+D", "RGB+ED")
@@ -219,7 +239,7 @@ class FusedSplatStep:
                                    depth_lambda, ssim_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas),
                                    ptr(lws), lws_bytes, stream), "qed_loss_fwd_bwd")
         self._mark("loss")
-        grads, packed = self.backward(v_render, v_alphas, grad_out)
+        grads, packed = self.backward(v_render, v_alphas, grad_out, n_chunks=n_chunks, on_chunk=on_chunk)
         self._last_v = (v_render, v_alphas)
         return StepOutput(loss=self._loss, grads=grads, packed_grads=packed, radii=self._fwd["radii"], render=render, alphas=alphas,
                           n_isects=self._fwd["M"])

@@ -73,6 +73,8 @@ class TrainConfig:
     use_absgrad: bool = True
     scene_scale: float = 1.0
     seed: int = 42
+    comm_chunks: int = 4  # world_size > 1: Gaussian ranges whose SH gradients are all-reduced / Adam-stepped in a pipeline
+    chunk_project_bwd: bool = True  # also split the projection backward so the first reductions start earlier
 
     def lr_means_at(self, step: int) -> float:
         """nerfstudio ExponentialDecayScheduler (no warmup): log-linear from lr to lr_final over max_steps."""
@@ -319,24 +321,42 @@ class SplatTrainer:
         r = (radii.to(torch.float32) / float(max(width, height))) * sel
         self.state.radii = torch.maximum(self.state.radii, r.max(dim=0).values)
 
-    def optimizer_step(self) -> None:
+    def optimizer_step(self, lo: int = 0, hi: Optional[int] = None) -> None:
+        """Adam on arena elements [lo, hi) (default: everything).  Ranges must not split a Gaussian's SH row."""
         c, a = self.cfg, self.arena
         t = self.step_count + 1
+        hi = a.param.numel() if hi is None else hi
         lrs = {"means": c.lr_means_at(self.step_count), "quats": c.lr_quats, "scales": c.lr_scales, "opacities": c.lr_opacities,
                "sh": c.lr_features_dc}
         if self.backend == "cuda":
             from . import _lib
 
             lib = _lib.load()
-            lr = torch.tensor([lrs[g] for g in GROUPS], device=self.device)
-            lr_alt = torch.tensor([lrs["means"], lrs["quats"], lrs["scales"], lrs["opacities"], c.lr_features_rest], device=self.device)
-            period = torch.tensor([0, 0, 0, 0, 48], dtype=torch.int32, device=self.device)
-            split = torch.tensor([0, 0, 0, 0, 3], dtype=torch.int32, device=self.device)
-            _lib.check(lib.qed_adam_arena(a.param.numel(), _lib.ptr(a.param), _lib.ptr(a.grad), _lib.ptr(a.exp_avg), _lib.ptr(a.exp_avg_sq),
-                                          len(GROUPS), _lib.ptr(a.group_ends), _lib.ptr(lr), _lib.ptr(lr_alt), _lib.ptr(period),
-                                          _lib.ptr(split), c.adam_betas[0], c.adam_betas[1], c.adam_eps, t, _lib.current_stream()),
-                       "qed_adam_arena")
+            if self._lr_dev is None or self._lr_dev[0] != (self.step_count, a.N):
+                lr = torch.tensor([lrs[g] for g in GROUPS], device=self.device)
+                lr_alt = torch.tensor([lrs["means"], lrs["quats"], lrs["scales"], lrs["opacities"], c.lr_features_rest], device=self.device)
+                period = torch.tensor([0, 0, 0, 0, 48], dtype=torch.int32, device=self.device)
+                split = torch.tensor([0, 0, 0, 0, 3], dtype=torch.int32, device=self.device)
+                self._lr_dev = ((self.step_count, a.N), lr, lr_alt, period, split)
+            _, lr, lr_alt, period, split = self._lr_dev
+            sh0 = a.offsets["sh"][0]
+            if lo >= sh0:
+                # a range inside the SH block: one group starting at `lo` (multiple of 48 floats past sh0)
+                assert (lo - sh0) % 48 == 0
+                ends = torch.tensor([hi - lo], dtype=torch.int64, device=self.device)
+                _lib.check(lib.qed_adam_arena(hi - lo, _lib.ptr(a.param[lo:hi]), _lib.ptr(a.grad[lo:hi]), _lib.ptr(a.exp_avg[lo:hi]),
+                                              _lib.ptr(a.exp_avg_sq[lo:hi]), 1, _lib.ptr(ends), _lib.ptr(lr[4:]), _lib.ptr(lr_alt[4:]),
+                                              _lib.ptr(period[4:]), _lib.ptr(split[4:]), c.adam_betas[0], c.adam_betas[1], c.adam_eps, t,
+                                              _lib.current_stream()), "qed_adam_arena")
+            else:
+                assert lo == 0
+                ends = torch.clamp(a.group_ends, max=hi)
+                _lib.check(lib.qed_adam_arena(hi, _lib.ptr(a.param), _lib.ptr(a.grad), _lib.ptr(a.exp_avg), _lib.ptr(a.exp_avg_sq),
+                                              len(GROUPS), _lib.ptr(ends), _lib.ptr(lr), _lib.ptr(lr_alt), _lib.ptr(period),
+                                              _lib.ptr(split), c.adam_betas[0], c.adam_betas[1], c.adam_eps, t, _lib.current_stream()),
+                           "qed_adam_arena")
         else:
+            assert lo == 0 and hi == a.param.numel()
             adam_step_torch(a, lrs, c.lr_features_rest, c, t)
 
     def maybe_refine(self, step: int) -> Optional[Dict[str, int]]:
@@ -373,16 +393,42 @@ class SplatTrainer:
         scales = torch.exp(pv["scales"])
         opac = torch.sigmoid(pv["opacities"])
         tmp = {"means": gv["means"], "quats": gv["quats"], "sh": gv["sh"], "scales": torch.empty_like(scales), "opacities": torch.empty_like(opac)}
+        pipelined = self.world > 1 and C == 1 and c.comm_chunks > 1
+        sh0 = a.offsets["sh"][0]
+        works = []
+
+        def on_chunk(k, n0, n1):
+            # SH rows of a finished Gaussian range: all-reduce them now (NCCL stream) while the next range computes
+            import torch.distributed as dist
+
+            lo, hi = sh0 + 48 * n0, sh0 + 48 * n1
+            works.append((dist.all_reduce(a.grad[lo:hi], group=self.pg, async_op=True), lo, hi))
+
         out = self._fused.step(pv["means"], pv["quats"], scales, opac, pv["sh"], viewmats, Ks, width, height, self.sh_degree_to_use(),
                                gt_rgb, gt_depth, background, render_mode=c.render_mode, rgb_weight=1.0 - c.ssim_lambda,
                                depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, grad_out=tmp,
-                               ssim_lambda=c.ssim_lambda)
+                               ssim_lambda=c.ssim_lambda, n_chunks=c.comm_chunks if (pipelined and c.chunk_project_bwd) else 1,
+                               on_chunk=on_chunk if (pipelined and c.chunk_project_bwd) else None)
         # activations' chain rule straight into the arena (model.py:269-271: exp, sigmoid)
         torch.mul(tmp["scales"], scales, out=gv["scales"])
         torch.mul(tmp["opacities"], opac * (1.0 - opac), out=gv["opacities"])
         self.accumulate_stats(out.packed_grads, out.radii, width, height, packed=True, n_cameras=total)
-        self._all_reduce(a.grad)
-        self.optimizer_step()
+        if pipelined:
+            import torch.distributed as dist
+
+            if not c.chunk_project_bwd:  # one projection-backward launch, then chunked reductions
+                step_n = ((a.N + c.comm_chunks - 1) // c.comm_chunks + 3) // 4 * 4
+                for k, n0 in enumerate(range(0, a.N, step_n)):
+                    on_chunk(k, n0, min(n0 + step_n, a.N))
+            head = dist.all_reduce(a.grad[:sh0], group=self.pg, async_op=True)
+            for w, lo, hi in works:  # Adam on each SH range as soon as its reduction has landed
+                w.wait()
+                self.optimizer_step(lo, hi)
+            head.wait()
+            self.optimizer_step(0, sh0)
+        else:
+            self._all_reduce(a.grad)
+            self.optimizer_step()
         info = self.maybe_refine(self.step_count)
         self.step_count += 1
         return out.loss, info
