@@ -133,13 +133,17 @@ def cpu_sample_step(sample, torch, oracle):
     return float(loss)
 
 
-def make_cpu_sample(args):
+def make_cpu_sample(args, n_steps_total: int = 3):
+    """A bounded sample of the workload for the CPU arm: 1/k of the Gaussians and 1/k of the pixels at the same field
+    of view, with k chosen so that `n_steps_total` oracle steps finish in a few minutes (~5 s per step at k = 16 on
+    16 cores)."""
     from qed_splatter_b200.scenes import scene_s1
 
-    # 1/16 of the Gaussians and 1/16 of the pixels at the same field of view
-    n = max(args.gaussians // 16, 1000)
-    w, h = args.width // 4, args.height // 4
-    return scene_s1(N=n, width=w, height=h, f=1200.0 * w / 1920.0), f"1/16 sample: {n} Gaussians, one {w}x{h} view, RGB+ED fwd+loss+bwd, float32"
+    k = 16 if n_steps_total <= 8 else (64 if n_steps_total <= 40 else 256)
+    r = int(round(k ** 0.5))
+    n = max(args.gaussians // k, 1000)
+    w, h = args.width // r, args.height // r
+    return scene_s1(N=n, width=w, height=h, f=1200.0 * w / 1920.0), f"1/{k} sample: {n} Gaussians, one {w}x{h} view, RGB+ED fwd+loss+bwd, float32"
 
 
 def run_cpu_baseline(args, steps: int, warmup: int):
@@ -149,7 +153,7 @@ def run_cpu_baseline(args, steps: int, warmup: int):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample, desc = make_cpu_sample(args)
+    sample, desc = make_cpu_sample(args, steps + warmup)
     for _ in range(warmup):
         cpu_sample_step(sample, torch, oracle)
     t0 = time.perf_counter()
