@@ -200,7 +200,7 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  *         depth fill / n_valid), then the mean over cameras.  splatfacto: rgb_weight = 1 - ssim_lambda = 0.8.
  *  SSIM = pytorch_msssim.SSIM(data_range=1, channel=3): 11x11 Gaussian window (sigma 1.5), valid convolution,
  *         mean over channels and pixels; ssim_lambda == 0 skips it (then workspace may be NULL).
- *  stats_dev[C*8] (double, per camera): {sum|rgb err|, sum|depth err|, n_valid, (scratch), max depth, sum SSIM map, ..};
+ *  stats_dev[C*8] (double, per camera): {sum|rgb err|, sum|depth err|, n_valid, (scratch), max depth, sum SSIM map, (scratch), 0};
  *  loss_dev[3] float: {total, rgb term (L1 + SSIM), depth term}.  grad_scale multiplies every gradient
  *  (local_views / total_views for a view-sharded batch).  v_render / v_alphas are overwritten.
  */

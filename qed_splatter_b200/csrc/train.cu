@@ -16,35 +16,53 @@ constexpr int kLossThreads = 256;
 __device__ __forceinline__ float signf(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
 __device__ __forceinline__ bool finitef(float x) { return fabsf(x) <= 3.402823466e38f; }
 
-// pass 1: per camera max of the depth channel (the fill value of model.py:304-306).  The channel is >= 0, so the
-// integer order of the float bits is the float order and atomicMax on the bits works.
-__global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, const float4* __restrict__ render, double* __restrict__ stats) {
+// pass 1 (24 B/pixel): per camera max of the depth channel (the fill value of model.py:304-306) and the number of
+// pixels the depth loss averages over (model.py:101-105).  The depth channel is >= 0, so the integer order of the
+// float bits is the float order and atomicMax on the bits works.  stats[2] = valid pixels with alpha > 0,
+// stats[6] = pixels with alpha == 0 whose ground truth is usable (valid iff the fill value is finite).
+__global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, const float4* __restrict__ render, const float* __restrict__ alphas,
+                                                                 const float* __restrict__ gt_depth, double* __restrict__ stats) {
     const int cam = blockIdx.y;
     float maxd = 0.0f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x)
-        maxd = fmaxf(maxd, render[cam * HW + i].w);
+    int na = 0, nb = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = cam * HW + i;
+        const float d = render[pix].w, a = alphas[pix], gd = gt_depth[pix];
+        maxd = fmaxf(maxd, d);
+        const bool gt_ok = finitef(gd) && gd > 0.0f;
+        if (a > 0.0f) na += (gt_ok && finitef(d)) ? 1 : 0;
+        else nb += gt_ok ? 1 : 0;
+    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(stats + cam * 8 + 3), __float_as_int(maxd));
+    for (int o = 16; o > 0; o >>= 1) {
+        maxd = fmaxf(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+        na += __shfl_xor_sync(0xffffffffu, na, o);
+        nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(reinterpret_cast<int*>(stats + cam * 8 + 3), __float_as_int(maxd));
+        if (na) atomicAdd(stats + cam * 8 + 2, (double)na);
+        if (nb) atomicAdd(stats + cam * 8 + 6, (double)nb);
+    }
 }
 
-// pass 2: gradients + loss sums
+__device__ __forceinline__ double n_valid_of(const double* s, float maxd) { return s[2] + (finitef(maxd) ? s[6] : 0.0); }
+
+// pass 2 (68 B/pixel): per-pixel loss terms and their gradient w.r.t. the compositor outputs.
+//   WRITE_PRED : only write the clamped rgb image (input of the SSIM kernels), no sums, no gradients
+//   otherwise  : loss sums + gradients (v_rgb_extra = gradient of the SSIM term w.r.t. the clamped rgb, or NULL)
+template <bool WRITE_PRED>
 __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int C, const float4* __restrict__ render, const float* __restrict__ alphas,
                                                                 const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth,
                                                                 const float* __restrict__ bg, float rgb_weight, float depth_lambda, float grad_scale,
                                                                 double* __restrict__ stats, float4* __restrict__ v_render, float* __restrict__ v_alphas,
-                                                                float* __restrict__ pred_rgb /* phase 0 out, or NULL */,
-                                                                const float* __restrict__ v_rgb_extra /* phase 1 in, or NULL */, int phase) {
-    // phase 0: count n_valid + loss sums (needs max depth); phase 1: gradients (needs n_valid)
+                                                                float* __restrict__ pred_rgb, const float* __restrict__ v_rgb_extra) {
     const int cam = blockIdx.y;
     const float maxd = __int_as_float(*reinterpret_cast<const int*>(stats + cam * 8 + 3));
     const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
-    double s_rgb = 0.0, s_d = 0.0, s_n = 0.0;
-    float inv_nvalid = 0.0f;
-    if (phase == 1) {
-        const double nv = stats[cam * 8 + 2];
-        inv_nvalid = nv > 0.0 ? (float)(1.0 / nv) : 0.0f;
-    }
+    double s_rgb = 0.0, s_d = 0.0;
+    const double nv = n_valid_of(stats + cam * 8, maxd);
+    const float inv_nvalid = nv > 0.0 ? (float)(1.0 / nv) : 0.0f;
     const float g_rgb = rgb_weight * grad_scale / ((float)C * (float)HW * 3.0f);
     const float g_d = depth_lambda * grad_scale * inv_nvalid / (float)C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
@@ -54,48 +72,41 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
         const float om = 1.0f - a;
         const float pre0 = r.x + om * b0, pre1 = r.y + om * b1, pre2 = r.z + om * b2;
         const float c0 = fminf(fmaxf(pre0, 0.0f), 1.0f), c1 = fminf(fmaxf(pre1, 0.0f), 1.0f), c2 = fminf(fmaxf(pre2, 0.0f), 1.0f);
+        if (WRITE_PRED) {
+            pred_rgb[pix * 3 + 0] = c0;
+            pred_rgb[pix * 3 + 1] = c1;
+            pred_rgb[pix * 3 + 2] = c2;
+            continue;
+        }
         const float e0 = c0 - gt_rgb[pix * 3 + 0], e1 = c1 - gt_rgb[pix * 3 + 1], e2 = c2 - gt_rgb[pix * 3 + 2];
         const float gd = gt_depth[pix];
         const float d = (a > 0.0f) ? r.w : maxd;
         const bool valid = finitef(d) && finitef(gd) && (gd > 0.0f);
-        if (phase == 0) {
-            if (pred_rgb) {
-                pred_rgb[pix * 3 + 0] = c0;
-                pred_rgb[pix * 3 + 1] = c1;
-                pred_rgb[pix * 3 + 2] = c2;
-            }
-            s_rgb += (double)(fabsf(e0) + fabsf(e1) + fabsf(e2));
-            if (valid) {
-                s_d += (double)fabsf(d - gd);
-                s_n += 1.0;
-            }
-        } else {
-            float x0 = 0.f, x1 = 0.f, x2 = 0.f;  // gradient of the SSIM term w.r.t. the clamped rgb
-            if (v_rgb_extra) {
-                x0 = v_rgb_extra[pix * 3 + 0];
-                x1 = v_rgb_extra[pix * 3 + 1];
-                x2 = v_rgb_extra[pix * 3 + 2];
-            }
-            float4 v;
-            v.x = (pre0 >= 0.0f && pre0 <= 1.0f) ? g_rgb * signf(e0) + x0 : 0.0f;
-            v.y = (pre1 >= 0.0f && pre1 <= 1.0f) ? g_rgb * signf(e1) + x1 : 0.0f;
-            v.z = (pre2 >= 0.0f && pre2 <= 1.0f) ? g_rgb * signf(e2) + x2 : 0.0f;
-            v.w = (valid && a > 0.0f) ? g_d * signf(d - gd) : 0.0f;
-            v_render[pix] = v;
-            v_alphas[pix] = -(v.x * b0 + v.y * b1 + v.z * b2);
+        s_rgb += (double)(fabsf(e0) + fabsf(e1) + fabsf(e2));
+        if (valid) s_d += (double)fabsf(d - gd);
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;  // gradient of the SSIM term w.r.t. the clamped rgb
+        if (v_rgb_extra) {
+            x0 = v_rgb_extra[pix * 3 + 0];
+            x1 = v_rgb_extra[pix * 3 + 1];
+            x2 = v_rgb_extra[pix * 3 + 2];
         }
+        float4 v;
+        v.x = (pre0 >= 0.0f && pre0 <= 1.0f) ? g_rgb * signf(e0) + x0 : 0.0f;
+        v.y = (pre1 >= 0.0f && pre1 <= 1.0f) ? g_rgb * signf(e1) + x1 : 0.0f;
+        v.z = (pre2 >= 0.0f && pre2 <= 1.0f) ? g_rgb * signf(e2) + x2 : 0.0f;
+        v.w = (valid && a > 0.0f) ? g_d * signf(d - gd) : 0.0f;
+        v_render[pix] = v;
+        v_alphas[pix] = -(v.x * b0 + v.y * b1 + v.z * b2);
     }
-    if (phase == 0) {
+    if (!WRITE_PRED) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s_rgb += __shfl_xor_sync(0xffffffffu, s_rgb, o);
             s_d += __shfl_xor_sync(0xffffffffu, s_d, o);
-            s_n += __shfl_xor_sync(0xffffffffu, s_n, o);
         }
         if ((threadIdx.x & 31) == 0) {
             atomicAdd(stats + cam * 8 + 0, s_rgb);
             atomicAdd(stats + cam * 8 + 1, s_d);
-            atomicAdd(stats + cam * 8 + 2, s_n);
         }
     }
 }
@@ -108,8 +119,10 @@ __global__ void loss_finalize_kernel(int C, int64_t HW, float rgb_weight, float 
         double* s = stats + c * 8;
         lr += s[0] / ((double)HW * 3.0);
         if (ssim_lambda > 0.0f) ls += 1.0 - s[5] / ssim_count;
-        ld += s[2] > 0.0 ? s[1] / s[2] : 0.0;
-        float maxd = __int_as_float(*reinterpret_cast<const int*>(s + 3));
+        const float maxd = __int_as_float(*reinterpret_cast<const int*>(s + 3));
+        const double nv = n_valid_of(s, maxd);
+        ld += nv > 0.0 ? s[1] / nv : 0.0;
+        s[2] = nv;
         s[4] = (double)maxd;
     }
     lr = rgb_weight * lr / C + ssim_lambda * ls / C;
@@ -213,22 +226,21 @@ extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* rende
     int bx = (int)((HW + kLossThreads * 4 - 1) / (kLossThreads * 4));
     if (bx > 148 * 8) bx = 148 * 8;
     dim3 grid(bx, C);
-    loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), stats_dev);
-    QED_LAUNCH_CHECK();
-    loss_grad_kernel<<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg, rgb_weight,
-                                                        depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render), v_alphas, pred_rgb,
-                                                        nullptr, 0);
+    loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, stats_dev);
     QED_LAUNCH_CHECK();
     const double ssim_count = (double)(width - 10) * (double)(height - 10) * 3.0;
     if (use_ssim) {
+        loss_grad_kernel<true><<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg,
+                                                                  rgb_weight, depth_lambda, grad_scale, stats_dev, nullptr, nullptr, pred_rgb, nullptr);
+        QED_LAUNCH_CHECK();
         // loss term = ssim_lambda * (1 - mean(map)) per camera, mean over cameras
         const float scale = -ssim_lambda * grad_scale / ((float)C * (float)ssim_count);
         int rc = qed_ssim_launch(C, width, height, pred_rgb, gt_rgb, dmaps, stats_dev, scale, v_ssim, stream);
         if (rc != QED_OK) return rc;
     }
-    loss_grad_kernel<<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg, rgb_weight,
-                                                        depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render), v_alphas, nullptr,
-                                                        v_ssim, 1);
+    loss_grad_kernel<false><<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg,
+                                                               rgb_weight, depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render),
+                                                               v_alphas, nullptr, v_ssim);
     QED_LAUNCH_CHECK();
     loss_finalize_kernel<<<1, 32, 0, stream>>>(C, HW, rgb_weight, depth_lambda, use_ssim ? ssim_lambda : 0.0f, ssim_count, stats_dev, loss_dev);
     QED_LAUNCH_CHECK();

@@ -249,7 +249,7 @@ class FusedSplatStep:
     def launches_per_step(self) -> int:
         """Kernel launches of one step(): project 1; intersections (two_level: 3 scan + 1 compact + 3 per
         8-bit pass of the Gaussian sort + 3 scan | 1 emit + 3 per pass of the tile sort + compose + ranges;
-        own/cub: 3 scan + emit + sort + ranges); composite fwd 1, loss 4 (+1 memset), grad clear 1,
+        own/cub: 3 scan + emit + sort + ranges); composite fwd 1, loss 3 (+1 memset), grad clear 1,
         composite bwd 1, project bwd 1."""
         f = self._fwd
         tile_bits = (f["tw"] * f["th"]).bit_length()
@@ -259,7 +259,7 @@ class FusedSplatStep:
         else:
             end_bit = 32 + tile_bits + f["C"].bit_length()
             isect = 3 + 1 + (3 * ((end_bit + 7) // 8) if self.sort_impl == "own" else 8) + 1
-        return 1 + isect + 1 + 5 + 1 + 1 + 1
+        return 1 + isect + 1 + 4 + 1 + 1 + 1
 
     @torch.no_grad()
     def count_pairs(self) -> Dict[str, int]:

@@ -96,21 +96,24 @@ def test_culling_is_exact_on_thin_tilted_splats(cuda):
     a["opacities"] = torch.cat([torch.rand(N // 2, generator=g) * 0.02 + 0.003, torch.rand(N - N // 2, generator=g)])
     ga = {k: v.to(cuda) for k, v in a.items()}
     outs = {}
-    for cull in (True, False):
+    for tag, cull in (("cull", True), ("cull_again", True), ("nocull", False)):
         ops.set_raster_cull(cull)
         leaves = {k: ga[k].clone().requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "colors")}
         r, al, info = rasterization(**leaves, viewmats=ga["viewmats"], Ks=ga["Ks"], width=W, height=H, render_mode="RGB+ED", sh_degree=None,
                                     absgrad=True)
         (r.sum() + al.sum()).backward()
-        outs[cull] = (r.detach(), al.detach(), {k: v.grad for k, v in leaves.items()})
+        outs[tag] = (r.detach(), al.detach(), {k: v.grad.double() for k, v in leaves.items()})
     ops.set_raster_cull(True)
-    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
-    # gradients: same terms, different atomic summation order (needle splats give huge cancelling terms), so
-    # compare norm-wise plus a bounded element mismatch fraction
-    for k in outs[True][2]:
-        a_, b_ = outs[True][2][k].double(), outs[False][2][k].double()
-        assert float((a_ - b_).norm() / (b_.norm() + 1e-30)) < 1e-3, k
-        assert_close_frac(a_, b_, 1e-3, 1e-4 * float(b_.abs().mean() + 1e-20), 2e-2, f"grad {k} cull vs no-cull")
+    assert torch.equal(outs["cull"][0], outs["nocull"][0]) and torch.equal(outs["cull"][1], outs["nocull"][1])
+    # gradients: the per-warp sums are identical in both modes; only the order of the float atomics differs, which
+    # also differs between two runs of the SAME mode.  Needle splats make the world-space gradients ill-conditioned
+    # (huge cancelling terms), so the yardstick is the run-to-run noise of the culled kernel itself.
+    for k in outs["cull"][2]:
+        ref = outs["cull"][2][k]
+        noise = float((outs["cull_again"][2][k] - ref).norm() / (ref.norm() + 1e-30))
+        diff = float((outs["nocull"][2][k] - ref).norm() / (ref.norm() + 1e-30))
+        assert diff <= 10.0 * noise + 1e-5, (k, diff, noise)
+    outs[True] = outs["cull"]
     # and against the oracle
     ro, ao, _ = oracle.rasterization(**a, width=W, height=H, render_mode="RGB+ED", sh_degree=None)
     assert_close_frac(outs[True][0], ro, 1e-4, 1e-4, 5e-3, "render vs oracle")
