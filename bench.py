@@ -387,14 +387,24 @@ def main_ours(args):
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                     "traffic": NCU_DRAM_BYTES.get(name), "ms": t_ms, "algorithmic_bytes": bytes_, "peak_source": hbm_src}
 
-        end_bit = 32 + (((width + 15) // 16) * ((height + 15) // 16)).bit_length() + 1
-        passes = (end_bit + 7) // 8
+        tile_bits = (((width + 15) // 16) * ((height + 15) // 16)).bit_length()
+        tile_passes = (tile_bits + 7) // 8
+        # two-level intersection build: algorithmic bytes
+        #   prepare: flags scan (4 r + 8 w + 8 r per (c,n)), compaction (8 w), 4 radix passes over the visible entries
+        #            (4 r upsweep + 8 r + 8 w downsweep each), gather scan (4 + 4 r, 8 w)
+        #   fill   : emit 8 w per isect, tile_passes radix passes (20 B each), ranges pass (4 r key + 4 r flat)
+        bytes_prepare = N * 20.0 + n_visible * (8.0 + 4 * 20.0 + 16.0)
+        bytes_fill = M * (8.0 + tile_passes * 20.0 + 8.0)
         stages = [
             fp32_roof("raster_bwd", counters.get("bwd_pairs_evaluated"), FLOP_PER_PAIR_BWD),
             fp32_roof("raster_fwd", counters.get("fwd_pairs_evaluated"), FLOP_PER_PAIR_FWD),
             hbm_roof("project_fwd", N * BYTES_PROJ_FWD_PER_GAUSS + n_visible * BYTES_PROJ_FWD_PER_VISIBLE),
             hbm_roof("project_bwd", N * BYTES_PROJ_BWD_PER_GAUSS + n_visible * BYTES_PROJ_BWD_PER_VISIBLE),
-            hbm_roof("sort", M * (passes * 24.0 + 8.0)),
+            hbm_roof("isect_prepare", bytes_prepare),
+            hbm_roof("isect_fill", bytes_fill),
+            hbm_roof("loss", width * height * (24.0 + 68.0)),
+            # the reference formulation (gsplat: 64-bit keys, full radix sort), only present with --sort own|cub
+            hbm_roof("sort", M * (((32 + tile_bits + 1 + 7) // 8) * 24.0 + 8.0)),
             hbm_roof("emit", M * 12.0),
         ]
         stages = [s for s in stages if s]

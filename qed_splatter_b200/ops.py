@@ -162,8 +162,11 @@ def fully_fused_projection(means: Tensor, covars, quats: Tensor, scales: Tensor,
 # --------------------------------------------------------------------------------------------- #
 @torch.no_grad()
 def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
-                sort: bool = True, tiles_per_gauss: Optional[Tensor] = None, impl: Optional[str] = None):
-    """gsplat `isect_tiles` -> tiles_per_gauss[C,N] i32, isect_ids[M] i64, flatten_ids[M] i32 (sorted)."""
+                sort: bool = True, tiles_per_gauss: Optional[Tensor] = None, impl: Optional[str] = None,
+                return_offsets: bool = False):
+    """gsplat `isect_tiles` -> tiles_per_gauss[C,N] i32, isect_ids[M] i64, flatten_ids[M] i32 (sorted).
+    `return_offsets=True` additionally returns isect_offsets[C,th,tw] (the two-level build produces the ranges in
+    the same pass that composes the 64-bit ids, so `isect_offset_encode` need not re-read them)."""
     lib = _lib.load()
     _lib.require_cuda(means2d, radii, depths)
     means2d, depths = _f32c(means2d.detach()), _f32c(depths.detach())
@@ -187,12 +190,14 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
         n_visible, n_isects = (int(v) for v in counts.tolist())  # the one host sync of the forward (gsplat has the same one)
         isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
         flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
-        if n_isects:
-            fws_bytes = lib.qed_isect_fill_workspace_bytes(n_isects)
-            fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
-            check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), tile_size, tile_width,
-                                     tile_height, ptr(pws), ptr(fws), fws_bytes, ptr(isect_ids), ptr(flatten_ids), None, stream),
-                  "qed_isect_fill")
+        offsets = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=dev) if return_offsets else None
+        fws_bytes = lib.qed_isect_fill_workspace_bytes(n_isects)
+        fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), tile_size, tile_width,
+                                 tile_height, ptr(pws), ptr(fws), fws_bytes, ptr(isect_ids) if n_isects else None,
+                                 ptr(flatten_ids) if n_isects else None, ptr(offsets), stream), "qed_isect_fill")
+        if return_offsets:
+            return tiles_per_gauss, isect_ids, flatten_ids, offsets
         return tiles_per_gauss, isect_ids, flatten_ids
     cum = torch.empty(CN, dtype=torch.int64, device=dev)
     total = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -210,6 +215,8 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
             cam_n_bits = C.bit_length()
             isect_ids, flatten_ids = sort_pairs(isect_ids, flatten_ids, 32 + tile_n_bits + cam_n_bits,
                                                 impl="cub" if impl == "cub" else "own")
+    if return_offsets:
+        return tiles_per_gauss, isect_ids, flatten_ids, isect_offset_encode(isect_ids, C, tile_width, tile_height)
     return tiles_per_gauss, isect_ids, flatten_ids
 
 

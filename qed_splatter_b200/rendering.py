@@ -82,9 +82,8 @@ def rasterization(
         append_depth=want_depth, tile_size=tile_size)
 
     tile_width, tile_height = ops.tile_grid(width, height, tile_size)
-    _, isect_ids, flatten_ids = ops.isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
-                                                tiles_per_gauss=tiles_per_gauss)
-    isect_offsets = ops.isect_offset_encode(isect_ids, C, tile_width, tile_height)
+    _, isect_ids, flatten_ids, isect_offsets = ops.isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
+                                                               tiles_per_gauss=tiles_per_gauss, return_offsets=True)
 
     if backgrounds is not None and want_rgb and want_depth:
         backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device, dtype=backgrounds.dtype)], dim=-1)
