@@ -12,6 +12,7 @@
 namespace qed {
 
 constexpr int kLossThreads = 256;
+constexpr int kLossUnroll = 4;
 
 __device__ __forceinline__ float signf(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
 __device__ __forceinline__ bool finitef(float x) { return fabsf(x) <= 3.402823466e38f; }
@@ -22,15 +23,27 @@ __device__ __forceinline__ bool finitef(float x) { return fabsf(x) <= 3.40282346
 // stats[6] = pixels with alpha == 0 whose ground truth is usable (valid iff the fill value is finite).
 __global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, const float4* __restrict__ render, const float* __restrict__ alphas,
                                                                  const float* __restrict__ gt_depth, double* __restrict__ stats) {
+    __shared__ float s_max[kLossThreads / 32];
+    __shared__ int s_na[kLossThreads / 32], s_nb[kLossThreads / 32];
     const int cam = blockIdx.y;
     float maxd = 0.0f;
     int na = 0, nb = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t pix = cam * HW + i;
-        const float d = render[pix].w, a = alphas[pix], gd = gt_depth[pix];
-        maxd = fmaxf(maxd, d);
-        const bool gt_ok = finitef(gd) && gd > 0.0f;
-        if (a > 0.0f) na += (gt_ok && finitef(d)) ? 1 : 0;
+    const int64_t base = (int64_t)blockIdx.x * (kLossThreads * kLossUnroll) + threadIdx.x;
+    float d[kLossUnroll], a[kLossUnroll], gd[kLossUnroll];
+#pragma unroll
+    for (int u = 0; u < kLossUnroll; ++u) {  // all loads first: kLossUnroll independent requests in flight per thread
+        const int64_t i = base + (int64_t)u * kLossThreads;
+        const bool in = i < HW;
+        const int64_t pix = cam * HW + (in ? i : 0);
+        d[u] = in ? render[pix].w : 0.0f;
+        a[u] = in ? alphas[pix] : 1.0f;
+        gd[u] = in ? gt_depth[pix] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kLossUnroll; ++u) {
+        maxd = fmaxf(maxd, d[u]);
+        const bool gt_ok = finitef(gd[u]) && gd[u] > 0.0f;
+        if (a[u] > 0.0f) na += (gt_ok && finitef(d[u])) ? 1 : 0;
         else nb += gt_ok ? 1 : 0;
     }
 #pragma unroll
@@ -40,6 +53,17 @@ __global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, co
         nb += __shfl_xor_sync(0xffffffffu, nb, o);
     }
     if ((threadIdx.x & 31) == 0) {
+        s_max[threadIdx.x >> 5] = maxd;
+        s_na[threadIdx.x >> 5] = na;
+        s_nb[threadIdx.x >> 5] = nb;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kLossThreads / 32; ++w) {
+            maxd = fmaxf(maxd, s_max[w]);
+            na += s_na[w];
+            nb += s_nb[w];
+        }
         atomicMax(reinterpret_cast<int*>(stats + cam * 8 + 3), __float_as_int(maxd));
         if (na) atomicAdd(stats + cam * 8 + 2, (double)na);
         if (nb) atomicAdd(stats + cam * 8 + 6, (double)nb);
@@ -65,7 +89,10 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
     const float inv_nvalid = nv > 0.0 ? (float)(1.0 / nv) : 0.0f;
     const float g_rgb = rgb_weight * grad_scale / ((float)C * (float)HW * 3.0f);
     const float g_d = depth_lambda * grad_scale * inv_nvalid / (float)C;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int u = 0; u < kLossUnroll; ++u) {
+        const int64_t i = (int64_t)blockIdx.x * (kLossThreads * kLossUnroll) + (int64_t)u * kLossThreads + threadIdx.x;
+        if (i >= HW) continue;
         const int64_t pix = cam * HW + i;
         const float4 r = render[pix];
         const float a = alphas[pix];
@@ -104,7 +131,17 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
             s_rgb += __shfl_xor_sync(0xffffffffu, s_rgb, o);
             s_d += __shfl_xor_sync(0xffffffffu, s_d, o);
         }
+        __shared__ double s_a[kLossThreads / 32], s_b[kLossThreads / 32];
         if ((threadIdx.x & 31) == 0) {
+            s_a[threadIdx.x >> 5] = s_rgb;
+            s_b[threadIdx.x >> 5] = s_d;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < kLossThreads / 32; ++w) {
+                s_rgb += s_a[w];
+                s_d += s_b[w];
+            }
             atomicAdd(stats + cam * 8 + 0, s_rgb);
             atomicAdd(stats + cam * 8 + 1, s_d);
         }
@@ -223,8 +260,7 @@ extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* rende
     float* dmaps = use_ssim ? pred_rgb + px * 3 : nullptr;
     float* v_ssim = use_ssim ? dmaps + px * 9 : nullptr;
     QED_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, (size_t)C * 8 * sizeof(double), stream));
-    int bx = (int)((HW + kLossThreads * 4 - 1) / (kLossThreads * 4));
-    if (bx > 148 * 8) bx = 148 * 8;
+    const int bx = (int)((HW + kLossThreads * kLossUnroll - 1) / (kLossThreads * kLossUnroll));
     dim3 grid(bx, C);
     loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, stats_dev);
     QED_LAUNCH_CHECK();
