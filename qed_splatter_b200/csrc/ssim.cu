@@ -15,8 +15,10 @@ namespace qed {
 
 constexpr int kWin = 11;
 constexpr int kHalo = kWin - 1;
-constexpr int kSsimTile = 16;
-constexpr int kSsimIn = kSsimTile + kHalo;  // 26
+constexpr int kSsimTile = 32;               // outputs per CTA: 32 x 32
+constexpr int kSsimIn = kSsimTile + kHalo;  // 42
+constexpr int kBlk = 4;                     // outputs per thread along the filtered axis (register sliding window)
+constexpr int kSsimThreads = 256;
 
 struct GaussWin {
     float w[kWin];
@@ -34,17 +36,21 @@ static GaussWin make_window() {
     return g;
 }
 
-// grid (tiles_x, tiles_y, C*3); block 256 threads (16x16)
-__global__ void __launch_bounds__(256) ssim_fwd_kernel(int W, int H, const float* __restrict__ pred /*[C,H,W,3]*/, const float* __restrict__ gt,
-                                                       GaussWin win, float* __restrict__ dmaps /*[C*3][3][OH][OW]*/, double* __restrict__ stats) {
-    __shared__ float sx[kSsimIn][kSsimIn + 1], sy[kSsimIn][kSsimIn + 1];
-    __shared__ float h[5][kSsimIn][kSsimTile + 1];
-    __shared__ double red[8];
+// grid (tiles_x, tiles_y, C*3); 256 threads; every thread produces kBlk adjacent outputs per pass from a register
+// sliding window, so each input is read from shared memory once per kBlk outputs instead of once per output
+__global__ void __launch_bounds__(kSsimThreads) ssim_fwd_kernel(int W, int H, const float* __restrict__ pred /*[C,H,W,3]*/,
+                                                                const float* __restrict__ gt, GaussWin win,
+                                                                float* __restrict__ dmaps /*[C*3][3][OH][OW]*/, double* __restrict__ stats) {
+    extern __shared__ float ssim_smem[];
+    float(*sx)[kSsimIn + 1] = reinterpret_cast<float(*)[kSsimIn + 1]>(ssim_smem);            // [42][43]
+    float(*sy)[kSsimIn + 1] = sx + kSsimIn;                                                   // [42][43]
+    float(*h)[kSsimIn][kSsimTile + 1] = reinterpret_cast<float(*)[kSsimIn][kSsimTile + 1]>(&sy[kSsimIn][0]);  // [5][42][33]
+    __shared__ double red[kSsimThreads / 32];
     const int OW = W - kHalo, OH = H - kHalo;
     const int cam = blockIdx.z / 3, ch = blockIdx.z % 3;
     const int ox0 = blockIdx.x * kSsimTile, oy0 = blockIdx.y * kSsimTile;
     const int64_t img = (int64_t)cam * H * W;
-    for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += 256) {
+    for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += kSsimThreads) {
         const int r = i / kSsimIn, c = i - r * kSsimIn;
         const int y = oy0 + r, x = ox0 + c;
         float a = 0.f, b = 0.f;
@@ -57,51 +63,80 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(int W, int H, const float
         sy[r][c] = b;
     }
     __syncthreads();
-    // horizontal pass: 26 rows x 16 columns
-    for (int i = threadIdx.x; i < kSsimIn * kSsimTile; i += 256) {
-        const int r = i / kSsimTile, c = i - r * kSsimTile;
-        float m1 = 0, m2 = 0, e1 = 0, e2 = 0, e12 = 0;
+    // horizontal pass: 42 rows x (32 / kBlk) column groups
+    for (int i = threadIdx.x; i < kSsimIn * (kSsimTile / kBlk); i += kSsimThreads) {
+        const int r = i / (kSsimTile / kBlk), c0 = (i - r * (kSsimTile / kBlk)) * kBlk;
+        float acc[5][kBlk];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float a = sx[r][c + k], b = sy[r][c + k], w = win.w[k];
-            m1 += w * a;
-            m2 += w * b;
-            e1 += w * a * a;
-            e2 += w * b * b;
-            e12 += w * a * b;
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) acc[q][o] = 0.f;
+#pragma unroll
+        for (int t = 0; t < kWin + kBlk - 1; ++t) {
+            const float a = sx[r][c0 + t], b = sy[r][c0 + t];
+            const float aa = a * a, bb = b * b, ab = a * b;
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) {
+                const int k = t - o;
+                if (k >= 0 && k < kWin) {
+                    const float w = win.w[k];
+                    acc[0][o] += w * a;
+                    acc[1][o] += w * b;
+                    acc[2][o] += w * aa;
+                    acc[3][o] += w * bb;
+                    acc[4][o] += w * ab;
+                }
+            }
         }
-        h[0][r][c] = m1;
-        h[1][r][c] = m2;
-        h[2][r][c] = e1;
-        h[3][r][c] = e2;
-        h[4][r][c] = e12;
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) h[q][r][c0 + o] = acc[q][o];
     }
     __syncthreads();
-    const int ty = threadIdx.x / kSsimTile, tx = threadIdx.x % kSsimTile;
-    const int oy = oy0 + ty, ox = ox0 + tx;
+    // vertical pass: 32 columns x (32 / kBlk) row groups = 256 thread items
     double local = 0.0;
-    if (oy < OH && ox < OW) {
-        float m1 = 0, m2 = 0, e1 = 0, e2 = 0, e12 = 0;
+    {
+        const int tx = threadIdx.x % kSsimTile, y0 = (threadIdx.x / kSsimTile) * kBlk;
+        float acc[5][kBlk];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float w = win.w[k];
-            m1 += w * h[0][ty + k][tx];
-            m2 += w * h[1][ty + k][tx];
-            e1 += w * h[2][ty + k][tx];
-            e2 += w * h[3][ty + k][tx];
-            e12 += w * h[4][ty + k][tx];
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) acc[q][o] = 0.f;
+#pragma unroll
+        for (int t = 0; t < kWin + kBlk - 1; ++t) {
+            float v[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) v[q] = h[q][y0 + t][tx];
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) {
+                const int k = t - o;
+                if (k >= 0 && k < kWin) {
+                    const float w = win.w[k];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) acc[q][o] += w * v[q];
+                }
+            }
         }
         const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
-        const float s1 = e1 - m1 * m1, s2 = e2 - m2 * m2, s12 = e12 - m1 * m2;
-        const float A1 = 2.f * m1 * m2 + C1, A2 = 2.f * s12 + C2, B1 = m1 * m1 + m2 * m2 + C1, B2 = s1 + s2 + C2;
-        const float inv = 1.0f / (B1 * B2);
-        const float map = A1 * A2 * inv;
-        local = (double)map;
         const int64_t plane = (int64_t)OH * OW;
-        float* d = dmaps + ((int64_t)blockIdx.z * 3) * plane + (int64_t)oy * OW + ox;
-        d[0] = (2.f * m1 * (A2 - A1) - 2.f * m2 * map * (B2 - B1)) * inv;  // d map / d mu2 (e2, e12 fixed)
-        d[plane] = -map / B2;                                              // d map / d e2
-        d[2 * plane] = 2.f * A1 * inv;                                     // d map / d e12
+        const int ox = ox0 + tx;
+#pragma unroll
+        for (int o = 0; o < kBlk; ++o) {
+            const int oy = oy0 + y0 + o;
+            if (oy < OH && ox < OW) {
+                const float m1 = acc[0][o], m2 = acc[1][o], e1 = acc[2][o], e2 = acc[3][o], e12 = acc[4][o];
+                const float s1 = e1 - m1 * m1, s2 = e2 - m2 * m2, s12 = e12 - m1 * m2;
+                const float A1 = 2.f * m1 * m2 + C1, A2 = 2.f * s12 + C2, B1 = m1 * m1 + m2 * m2 + C1, B2 = s1 + s2 + C2;
+                const float inv = 1.0f / (B1 * B2);
+                const float map = A1 * A2 * inv;
+                local += (double)map;
+                float* d = dmaps + ((int64_t)blockIdx.z * 3) * plane + (int64_t)oy * OW + ox;
+                d[0] = (2.f * m1 * (A2 - A1) - 2.f * m2 * map * (B2 - B1)) * inv;  // d map / d mu2 (e2, e12 fixed)
+                d[plane] = -map / B2;                                              // d map / d e2
+                d[2 * plane] = 2.f * A1 * inv;                                     // d map / d e12
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
@@ -109,23 +144,25 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(int W, int H, const float
     __syncthreads();
     if (threadIdx.x == 0) {
         double s = 0;
-        for (int i = 0; i < 8; ++i) s += red[i];
+        for (int i = 0; i < kSsimThreads / 32; ++i) s += red[i];
         atomicAdd(stats + cam * 8 + 5, s);
     }
 }
 
-// grid (ceil(W/16), ceil(H/16), C*3): dL/dpred for a 16x16 tile of INPUT pixels
-__global__ void __launch_bounds__(256) ssim_bwd_kernel(int W, int H, const float* __restrict__ pred, const float* __restrict__ gt, GaussWin win,
-                                                       const float* __restrict__ dmaps, float scale, float* __restrict__ v_pred /*[C,H,W,3]*/) {
-    __shared__ float sd[3][kSsimIn][kSsimIn + 1];
-    __shared__ float h[3][kSsimIn][kSsimTile + 1];
+// grid (ceil(W/32), ceil(H/32), C*3): dL/dpred for a 32x32 tile of INPUT pixels
+__global__ void __launch_bounds__(kSsimThreads) ssim_bwd_kernel(int W, int H, const float* __restrict__ pred, const float* __restrict__ gt,
+                                                                GaussWin win, const float* __restrict__ dmaps, float scale,
+                                                                float* __restrict__ v_pred /*[C,H,W,3]*/) {
+    extern __shared__ float ssim_smem[];
+    float(*sd)[kSsimIn][kSsimIn + 1] = reinterpret_cast<float(*)[kSsimIn][kSsimIn + 1]>(ssim_smem);                      // [3][42][43]
+    float(*h)[kSsimIn][kSsimTile + 1] = reinterpret_cast<float(*)[kSsimIn][kSsimTile + 1]>(&sd[3][0][0]);               // [3][42][33]
     const int OW = W - kHalo, OH = H - kHalo;
     const int cam = blockIdx.z / 3, ch = blockIdx.z % 3;
     const int x0 = blockIdx.x * kSsimTile, y0 = blockIdx.y * kSsimTile;
     const int64_t plane = (int64_t)OH * OW;
     const float* d = dmaps + ((int64_t)blockIdx.z * 3) * plane;
-    // output pixel p gets contributions from q in [p-10, p] (valid coords): load q tile starting at (y0-10, x0-10)
-    for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += 256) {
+    // pixel p gets contributions from q in [p-10, p] (valid coords): load the q tile starting at (y0-10, x0-10)
+    for (int i = threadIdx.x; i < kSsimIn * kSsimIn; i += kSsimThreads) {
         const int r = i / kSsimIn, c = i - r * kSsimIn;
         const int qy = y0 - kHalo + r, qx = x0 - kHalo + c;
         float a = 0.f, b = 0.f, e = 0.f;
@@ -140,37 +177,69 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(int W, int H, const float
         sd[2][r][c] = e;
     }
     __syncthreads();
-    // pixel p = x0 + c receives q = p - 10 + k with weight w[10 - k]  (w symmetric)
-    for (int i = threadIdx.x; i < kSsimIn * kSsimTile; i += 256) {
-        const int r = i / kSsimTile, c = i - r * kSsimTile;
-        float a = 0, b = 0, e = 0;
+    // pixel p = x0 + c receives q = p - 10 + k with weight w[10 - k]  (w is symmetric)
+    for (int i = threadIdx.x; i < kSsimIn * (kSsimTile / kBlk); i += kSsimThreads) {
+        const int r = i / (kSsimTile / kBlk), c0 = (i - r * (kSsimTile / kBlk)) * kBlk;
+        float acc[3][kBlk];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float w = win.w[kWin - 1 - k];
-            a += w * sd[0][r][c + k];
-            b += w * sd[1][r][c + k];
-            e += w * sd[2][r][c + k];
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) acc[q][o] = 0.f;
+#pragma unroll
+        for (int t = 0; t < kWin + kBlk - 1; ++t) {
+            const float a = sd[0][r][c0 + t], b = sd[1][r][c0 + t], e = sd[2][r][c0 + t];
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) {
+                const int k = t - o;
+                if (k >= 0 && k < kWin) {
+                    const float w = win.w[kWin - 1 - k];
+                    acc[0][o] += w * a;
+                    acc[1][o] += w * b;
+                    acc[2][o] += w * e;
+                }
+            }
         }
-        h[0][r][c] = a;
-        h[1][r][c] = b;
-        h[2][r][c] = e;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) h[q][r][c0 + o] = acc[q][o];
     }
     __syncthreads();
-    const int ty = threadIdx.x / kSsimTile, tx = threadIdx.x % kSsimTile;
-    const int y = y0 + ty, x = x0 + tx;
-    if (y < H && x < W) {
-        float a = 0, b = 0, e = 0;
+    {
+        const int tx = threadIdx.x % kSsimTile, yb = (threadIdx.x / kSsimTile) * kBlk;
+        float acc[3][kBlk];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float w = win.w[kWin - 1 - k];
-            a += w * h[0][ty + k][tx];
-            b += w * h[1][ty + k][tx];
-            e += w * h[2][ty + k][tx];
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) acc[q][o] = 0.f;
+#pragma unroll
+        for (int t = 0; t < kWin + kBlk - 1; ++t) {
+            const float a = h[0][yb + t][tx], b = h[1][yb + t][tx], e = h[2][yb + t][tx];
+#pragma unroll
+            for (int o = 0; o < kBlk; ++o) {
+                const int k = t - o;
+                if (k >= 0 && k < kWin) {
+                    const float w = win.w[kWin - 1 - k];
+                    acc[0][o] += w * a;
+                    acc[1][o] += w * b;
+                    acc[2][o] += w * e;
+                }
+            }
         }
-        const int64_t o = (((int64_t)cam * H + y) * W + x) * 3 + ch;
-        v_pred[o] = scale * (a + 2.f * pred[o] * b + gt[o] * e);
+        const int x = x0 + tx;
+#pragma unroll
+        for (int o = 0; o < kBlk; ++o) {
+            const int y = y0 + yb + o;
+            if (y < H && x < W) {
+                const int64_t idx = (((int64_t)cam * H + y) * W + x) * 3 + ch;
+                v_pred[idx] = scale * (acc[0][o] + 2.f * pred[idx] * acc[1][o] + gt[idx] * acc[2][o]);
+            }
+        }
     }
 }
+
+constexpr size_t kSsimFwdSmem = (size_t)(2 * kSsimIn * (kSsimIn + 1) + 5 * kSsimIn * (kSsimTile + 1)) * 4;
+constexpr size_t kSsimBwdSmem = (size_t)(3 * kSsimIn * (kSsimIn + 1) + 3 * kSsimIn * (kSsimTile + 1)) * 4;
 
 }  // namespace qed
 
@@ -183,11 +252,13 @@ int qed_ssim_launch(int C, int W, int H, const float* pred, const float* gt, flo
     if (W <= kHalo || H <= kHalo) return QED_ERR_UNSUPPORTED;
     static const GaussWin win = make_window();
     const int OW = W - kHalo, OH = H - kHalo;
+    QED_CUDA_TRY(cudaFuncSetAttribute(ssim_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimFwdSmem));
+    QED_CUDA_TRY(cudaFuncSetAttribute(ssim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimBwdSmem));
     dim3 g1((OW + kSsimTile - 1) / kSsimTile, (OH + kSsimTile - 1) / kSsimTile, C * 3);
-    ssim_fwd_kernel<<<g1, 256, 0, stream>>>(W, H, pred, gt, win, dmaps, stats);
+    ssim_fwd_kernel<<<g1, kSsimThreads, kSsimFwdSmem, stream>>>(W, H, pred, gt, win, dmaps, stats);
     QED_LAUNCH_CHECK();
     dim3 g2((W + kSsimTile - 1) / kSsimTile, (H + kSsimTile - 1) / kSsimTile, C * 3);
-    ssim_bwd_kernel<<<g2, 256, 0, stream>>>(W, H, pred, gt, win, dmaps, scale, v_pred);
+    ssim_bwd_kernel<<<g2, kSsimThreads, kSsimBwdSmem, stream>>>(W, H, pred, gt, win, dmaps, scale, v_pred);
     QED_LAUNCH_CHECK();
     return QED_OK;
 }

@@ -170,10 +170,14 @@ __global__ void loss_finalize_kernel(int C, int64_t HW, float rgb_weight, float 
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void adam_arena_kernel(int64_t n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
-                                  int G, const int64_t* __restrict__ group_ends, const float* __restrict__ lr_by_group,
-                                  const float* __restrict__ lr_alt_by_group, const int32_t* __restrict__ group_period,
-                                  const int32_t* __restrict__ group_split, float beta1, float beta2, float eps, float bias1, float bias2_sqrt) {
+// One float4 (or, in the scalar tail/unaligned variant, one float) per thread: 4 x LDG.128 + 3 x STG.128, everything
+// in flight at once.  28 B/parameter of pure HBM traffic.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) adam_arena_kernel(int64_t n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                                                         float* __restrict__ v, int G, const int64_t* __restrict__ group_ends,
+                                                         const float* __restrict__ lr_by_group, const float* __restrict__ lr_alt_by_group,
+                                                         const int32_t* __restrict__ group_period, const int32_t* __restrict__ group_split, float beta1,
+                                                         float beta2, float eps, float inv_bias1, float inv_bias2_sqrt) {
     __shared__ int64_t s_ends[16];
     __shared__ float s_lr[16], s_lr_alt[16];
     __shared__ int s_period[16], s_split[16];
@@ -185,21 +189,46 @@ __global__ void adam_arena_kernel(int64_t n, float* __restrict__ param, const fl
         s_split[threadIdx.x] = group_split ? group_split[threadIdx.x] : 0;
     }
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int g = 0;
-        while (g < G - 1 && i >= s_ends[g]) ++g;
-        float lr = s_lr[g];
-        if (s_period[g] > 0) {
-            const int64_t start = g > 0 ? s_ends[g - 1] : 0;
-            if ((int)((i - start) % s_period[g]) >= s_split[g]) lr = s_lr_alt[g];
+    constexpr int W = VEC4 ? 4 : 1;
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * W;
+    if (i0 >= n) return;
+    float p[W], g[W], mi[W], vi[W];
+    if (VEC4) {
+        const float4 P = *reinterpret_cast<const float4*>(param + i0), Gd = *reinterpret_cast<const float4*>(grad + i0);
+        const float4 M = *reinterpret_cast<const float4*>(m + i0), V = *reinterpret_cast<const float4*>(v + i0);
+        p[0] = P.x; p[W > 1 ? 1 : 0] = P.y; p[W > 1 ? 2 : 0] = P.z; p[W > 1 ? 3 : 0] = P.w;
+        g[0] = Gd.x; g[W > 1 ? 1 : 0] = Gd.y; g[W > 1 ? 2 : 0] = Gd.z; g[W > 1 ? 3 : 0] = Gd.w;
+        mi[0] = M.x; mi[W > 1 ? 1 : 0] = M.y; mi[W > 1 ? 2 : 0] = M.z; mi[W > 1 ? 3 : 0] = M.w;
+        vi[0] = V.x; vi[W > 1 ? 1 : 0] = V.y; vi[W > 1 ? 2 : 0] = V.z; vi[W > 1 ? 3 : 0] = V.w;
+    } else {
+        p[0] = param[i0];
+        g[0] = grad[i0];
+        mi[0] = m[i0];
+        vi[0] = v[i0];
+    }
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const int64_t i = i0 + k;
+        int gi = 0;
+        while (gi < G - 1 && i >= s_ends[gi]) ++gi;
+        float lr = s_lr[gi];
+        if (s_period[gi] > 0) {
+            const int64_t start = gi > 0 ? s_ends[gi - 1] : 0;
+            if ((int)((i - start) % s_period[gi]) >= s_split[gi]) lr = s_lr_alt[gi];
         }
-        const float gr = grad[i];
-        const float mi = beta1 * m[i] + (1.0f - beta1) * gr;
-        const float vi = beta2 * v[i] + (1.0f - beta2) * gr * gr;
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bias2_sqrt + eps;
-        param[i] -= (lr / bias1) * (mi / denom);
+        mi[k] = beta1 * mi[k] + (1.0f - beta1) * g[k];
+        vi[k] = beta2 * vi[k] + (1.0f - beta2) * g[k] * g[k];
+        const float denom = sqrtf(vi[k]) * inv_bias2_sqrt + eps;
+        p[k] -= (lr * inv_bias1) * (mi[k] / denom);
+    }
+    if (VEC4) {
+        *reinterpret_cast<float4*>(param + i0) = make_float4(p[0], p[W > 1 ? 1 : 0], p[W > 1 ? 2 : 0], p[W > 1 ? 3 : 0]);
+        *reinterpret_cast<float4*>(m + i0) = make_float4(mi[0], mi[W > 1 ? 1 : 0], mi[W > 1 ? 2 : 0], mi[W > 1 ? 3 : 0]);
+        *reinterpret_cast<float4*>(v + i0) = make_float4(vi[0], vi[W > 1 ? 1 : 0], vi[W > 1 ? 2 : 0], vi[W > 1 ? 3 : 0]);
+    } else {
+        param[i0] = p[0];
+        m[i0] = mi[0];
+        v[i0] = vi[0];
     }
 }
 
@@ -292,12 +321,20 @@ extern "C" int qed_adam_arena(int64_t n, float* param, const float* grad, float*
     if (n == 0) return QED_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !group_ends || !lr_by_group) return QED_ERR_BAD_ARG;
     // bias corrections in double, as torch.optim.Adam computes them on the host
-    const float bias1 = (float)(1.0 - pow(beta1, (double)step));
-    const float bias2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
-    int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    adam_arena_kernel<<<(unsigned)blocks, 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group, lr_alt_by_group,
-                                                            group_period, group_split, (float)beta1, (float)beta2, (float)eps, bias1, bias2_sqrt);
+    const float inv_bias1 = (float)(1.0 / (1.0 - pow(beta1, (double)step)));
+    const float inv_bias2_sqrt = (float)(1.0 / sqrt(1.0 - pow(beta2, (double)step)));
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool vec = (n % 4 == 0) && al16(param) && al16(grad) && al16(exp_avg) && al16(exp_avg_sq);
+    if (vec) {
+        const int64_t threads = n / 4;
+        adam_arena_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group,
+                                                                                     lr_alt_by_group, group_period, group_split, (float)beta1,
+                                                                                     (float)beta2, (float)eps, inv_bias1, inv_bias2_sqrt);
+    } else {
+        adam_arena_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group,
+                                                                                lr_alt_by_group, group_period, group_split, (float)beta1,
+                                                                                (float)beta2, (float)eps, inv_bias1, inv_bias2_sqrt);
+    }
     QED_LAUNCH_CHECK();
     return QED_OK;
 }
