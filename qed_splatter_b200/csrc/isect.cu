@@ -154,6 +154,14 @@ extern "C" int qed_tile_ranges(int64_t n_isects, const int64_t* isect_ids_sorted
     return QED_OK;
 }
 
+// test hook (not part of the reference surface): 1 = single-kernel radix passes with decoupled look-back (default),
+// 0 = upsweep / scan / downsweep per pass.  Identical output.
+extern "C" int qed_debug_set_radix_onesweep(int enabled) {
+    int old = g_radix_onesweep;
+    g_radix_onesweep = enabled ? 1 : 0;
+    return old;
+}
+
 // ---- library baseline (what gsplat calls) ----
 extern "C" size_t qed_sort_pairs_cub_workspace_bytes(int64_t n) {
     size_t bytes = 0;

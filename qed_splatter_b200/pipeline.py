@@ -50,6 +50,8 @@ class FusedSplatStep:
         self._stats = None
         self._loss = torch.zeros(3, device=self.device)
         self._buf: Dict[str, Tensor] = {}
+        self._prezero = False
+        self._prezeroed = False
         self.marks = None  # set to [] to record (name, cuda event) after every stage (bench.py stage timing)
 
     def _mark(self, name: str) -> None:
@@ -111,6 +113,10 @@ class FusedSplatStep:
             check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles), ptr(pws), pws_bytes, ptr(self._counts), ptr(self._counts_host), stream),
                   "qed_isect_prepare")
             self._mark("isect_prepare")
+            if self._prezero:
+                # work that does not depend on the counts is queued BEFORE the host waits, so the GPU is busy
+                # while the host reads the counts and launches the rest (the gradient record of the backward)
+                self._get("packed", (C * N, 12)).zero_()
             torch.cuda.current_stream().synchronize()  # the single host sync of the step: output sizes
             n_vis, M = int(self._counts_host[0]), int(self._counts_host[1])
             self._mark("sync")
@@ -176,7 +182,9 @@ class FusedSplatStep:
         C, N, D, M = f["C"], f["N"], f["D"], f["M"]
         means, quats, scales, opacities, sh, viewmats, Ks = f["inputs"]
         packed = self._get("packed", (C * N, 12))
-        packed.zero_()
+        if not self._prezeroed:
+            packed.zero_()
+        self._prezeroed = False
         self._mark("zero_grads")
         if M:
             check(lib.qed_raster_bwd(C, N, M, D, ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]), f["width"], f["height"], 16,
@@ -226,8 +234,10 @@ class FusedSplatStep:
         loss = rgb_weight * L1 + ssim_lambda * (1 - SSIM) + depth_lambda * masked depth-L1 (splatfacto: 0.8 / 0.2 / 0.2)."""
         assert render_mode in ("RGB+D", "RGB+ED")
         lib, stream = self.lib, current_stream()
+        self._prezero = self.sort_impl == "two_level"
         render, alphas = self.forward(means, quats, scales, opacities, sh, viewmats, Ks, width, height, sh_degree, render_mode,
                                       rasterize_mode)
+        self._prezeroed, self._prezero = self._prezero, False
         C = viewmats.shape[0]
         if self._stats is None or self._stats.numel() < C * 8:
             self._stats = torch.zeros(C * 8, dtype=torch.float64, device=self.device)
