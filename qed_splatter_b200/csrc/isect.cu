@@ -158,7 +158,7 @@ extern "C" int qed_tile_ranges(int64_t n_isects, const int64_t* isect_ids_sorted
 // 0 = upsweep / scan / downsweep per pass.  Identical output.
 extern "C" int qed_debug_set_radix_onesweep(int enabled) {
     int old = g_radix_onesweep;
-    g_radix_onesweep = enabled ? 1 : 0;
+    g_radix_onesweep = enabled;  // 0 = three kernels per pass, 1 = look-back passes for small sorts, 2 = for every size
     return old;
 }
 

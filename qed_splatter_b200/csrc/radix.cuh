@@ -343,18 +343,34 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(int64_t
         st_relaxed_u64(my_status, ((uint64_t)(vb == 0 ? FLAG_PFX : FLAG_AGG) << 32) | run);
         uint32_t excl = 0;
         if (vb > 0) {
+            // All blocks of a wave publish their aggregate at about the same time, so the walk back to the last
+            // published prefix can be as long as the number of resident blocks: kLook independent loads are kept
+            // in flight per step instead of one dependent L2 round trip per predecessor.
+            constexpr int kLook = 8;
             int64_t b = (int64_t)vb - 1;
-            while (true) {
-                const uint64_t v = ld_relaxed_u64(status + (size_t)b * kRadix + d);
-                const uint32_t f = (uint32_t)(v >> 32);
-                if (f == FLAG_PFX) {
-                    excl += (uint32_t)v;
-                    break;
+            bool done = false;
+            while (!done) {
+                uint64_t v[kLook];
+#pragma unroll
+                for (int j = 0; j < kLook; ++j) v[j] = (b - j >= 0) ? ld_relaxed_u64(status + (size_t)(b - j) * kRadix + d) : 0ull;
+                int consumed = 0;
+                bool stop = false;
+#pragma unroll
+                for (int j = 0; j < kLook; ++j) {
+                    if (stop || done || b - j < 0) continue;
+                    const uint32_t f = (uint32_t)(v[j] >> 32);
+                    if (f == FLAG_PFX) {
+                        excl += (uint32_t)v[j];
+                        done = true;
+                    } else if (f == FLAG_AGG) {
+                        excl += (uint32_t)v[j];
+                        consumed = j + 1;
+                    } else {
+                        stop = true;  // predecessor b-j has not published yet: retry from there
+                    }
                 }
-                if (f == FLAG_AGG) {
-                    excl += (uint32_t)v;
-                    --b;  // block 0 always publishes a prefix, so b never drops below 0
-                }
+                b -= consumed;
+                // block 0 always publishes a prefix, so the walk ends before b < 0
             }
             st_relaxed_u64(my_status, ((uint64_t)FLAG_PFX << 32) | (uint64_t)(excl + run));
         }
@@ -437,10 +453,7 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
         QED_CUDA_TRY(cudaMemcpyAsync(vals_out, vals_in, (size_t)capacity * 4, cudaMemcpyDeviceToDevice, stream));
         return QED_OK;
     }
-    // Measured (B200): the look-back passes win while every block is resident at once (668 k pairs, 4 passes:
-    // 104 -> 82 us) and lose on large inputs (6.5 M pairs: +11 us per pass, the count is only published after the
-    // ranking), so they are used for small sorts only.
-    if (g_radix_onesweep && passes <= kMaxPasses && nb <= kOnesweepMaxBlocks) {
+    if (g_radix_onesweep && passes <= kMaxPasses && (nb <= kOnesweepMaxBlocks || g_radix_onesweep > 1)) {
         char* ows = reinterpret_cast<char*>(hist_ws) + 2 * hist_bytes + ((kRadix * 4 + 255) / 256 * 256);
         uint64_t* status = reinterpret_cast<uint64_t*>(ows);
         const size_t status_bytes = ((size_t)kRadix * nb * 8 + 255) / 256 * 256;
