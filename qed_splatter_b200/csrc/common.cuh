@@ -40,6 +40,49 @@ __device__ __forceinline__ float mad3(float a, float b, float c, float d, float 
     return add(add(mul(a, b), mul(c, d)), mul(e, f));
 }
 
+// ---- packed float pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot, two IEEE fp32 results) -------------
+// ptxas folds bc2(s) into a scalar-broadcast operand (`R.F32`), neg2/abs2 into operand modifiers and pk2 of
+// two freshly produced scalars into adjacent registers, so these helpers cost no extra instructions.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 bc2(float s) { return pk2(s, s); }
+__device__ __forceinline__ float lo2(f32x2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi2(f32x2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 neg2(f32x2 v) { return pk2(-lo2(v), -hi2(v)); }
+__device__ __forceinline__ f32x2 abs2(f32x2 v) { return pk2(fabsf(lo2(v)), fabsf(hi2(v))); }
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));

@@ -222,12 +222,29 @@ __device__ __forceinline__ SubRects<PX> make_subrects(int ox, int oy, int width,
     return r;
 }
 
+// The two 8x8 pixel blocks of a 16x8 warp footprint (packed kernels: a lane's two pixels of a block, 4 rows
+// apart, share one f32x2 register pair), clipped to the image.
+__device__ __forceinline__ SubRects<2> make_blocks8(int ox, int oy, int width, int height) {
+    SubRects<2> r;
+    r.present = 0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int sx = ox + a * 8;
+        r.x0[a] = (float)sx + 0.5f;
+        r.y0[a] = (float)oy + 0.5f;
+        r.x1[a] = (float)min(sx + 7, width - 1) + 0.5f;
+        r.y1[a] = (float)min(oy + 7, height - 1) + 0.5f;
+        if (sx < width && oy < height) r.present |= 1 << a;
+    }
+    return r;
+}
+
 // Warp-level cull of staged entries [c0, c0+32): every lane tests one entry against the PX sub-rectangles
 // still of interest (`want` bits; backward: additionally sorted index <= max_sid[k]); entries that can
 // touch at least one are copied, compacted and in order, into the warp's queue together with their
 // sub-rectangle mask.  Returns the number of queued entries (warp-uniform).
-template <int PX, bool CULL, bool BWD>
-__device__ __forceinline__ int fill_queue(Staging<PX>& sm, int c0, int count, const SubRects<PX>& sr, int want, const int* max_sid) {
+template <int PX, bool CULL, bool BWD, int NR = PX>
+__device__ __forceinline__ int fill_queue(Staging<PX>& sm, int c0, int count, const SubRects<NR>& sr, int want, const int* max_sid) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = c0 + lane;
     int mask = 0;
@@ -238,7 +255,7 @@ __device__ __forceinline__ int fill_queue(Staging<PX>& sm, int c0, int count, co
         const int sid = __float_as_int(A.w);
         const float tau2 = A.z + kLog2_255;
 #pragma unroll
-        for (int k = 0; k < PX; ++k) {
+        for (int k = 0; k < NR; ++k) {
             bool hit = (want >> k) & 1;
             if (BWD) hit = hit && (sid <= max_sid[k]);
             if (CULL && hit) hit = ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, tau2, sr.x0[k], sr.y0[k], sr.x1[k], sr.y1[k]);
@@ -252,7 +269,7 @@ __device__ __forceinline__ int fill_queue(Staging<PX>& sm, int c0, int count, co
         sm.qa[warp][pos] = A;
         sm.qb[warp][pos] = B;
         sm.qc[warp][pos] = sm.sc[q];
-        if (PX > 1) sm.qm[warp][pos] = mask;
+        if (NR > 1) sm.qm[warp][pos] = mask;
     }
     __syncwarp();
     return __popc(m);
@@ -594,6 +611,213 @@ __global__ void __launch_bounds__(Shape<PX>::kThreads) raster_bwd_kernel(const R
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward, packed: the same algorithm with the per-pixel arithmetic on sm_100's two-wide fp32
+// instructions (FFMA2 / FMUL2 / FADD2 retire two IEEE fp32 results per issue slot; scalar-broadcast,
+// negate and |.| operand forms are free).  Layout = Shape<4> (2 warps per tile, 16x8 footprint, lane
+// pixels at columns j0 + 8a, rows i0 + 4b); a pair is (a, b=0) / (a, b=1): the two pixels of one 8x8
+// block share dx and differ in dy.  Culling masks are per 8x8 block.
+// ------------------------------------------------------------------------------------------------
+// One 8x8 block (column half `a`): the lane's two pixels (rows i0, i0 + 4) in the two halves of every
+// f32x2.  FIRST: v[] is written, else accumulated (no zero-fill, no register shuffling where the paths
+// join).  Returns nonzero if a pixel passed the alpha test.
+template <int D, bool FIRST, bool STATS>
+__device__ __forceinline__ int bwd_pk_block(int a, const float4& A, const float4& B, const float4& Cc, int sid, float px0, f32x2 dy2,
+                                            f32x2 t2, f32x2 cy2, float qc2, f32x2& T2, f32x2& bsum2, const f32x2 (&vout2)[D],
+                                            const int32_t (&bin_final)[2], f32x2 (&v)[12], StatCounters<STATS>& st) {
+    const float dx = A.x - (px0 + 8.0f * a);
+    const float ax = B.x * dx;
+    const f32x2 pw2 = fma2(add2(t2, bc2(ax)), bc2(dx), cy2);  // log2(opacity * exp(-sigma))
+    const float pw0 = lo2(pw2), pw1 = hi2(pw2);
+    const float ar0 = ex2_approx(pw0), ar1 = ex2_approx(pw1);
+    const float am0 = fminf(kMaxAlpha, ar0), am1 = fminf(kMaxAlpha, ar1);
+    const bool valid0 = (sid <= bin_final[0]) && (pw0 <= A.z) && (am0 >= kAlphaThreshold);
+    const bool valid1 = (sid <= bin_final[1]) && (pw1 <= A.z) && (am1 >= kAlphaThreshold);
+    st.add(3, (sid <= bin_final[0] ? 1 : 0) + (sid <= bin_final[1] ? 1 : 0));
+    st.add(4, (valid0 ? 1 : 0) + (valid1 ? 1 : 0));
+    // a pixel that fails the test gets alpha = 0: then 1/(1-alpha) = 1 exactly (rcp.approx is exact at 1),
+    // T and bsum pass through unchanged and every gradient term is 0 -- no selects after the packed ops
+    const float al0 = valid0 ? am0 : 0.0f, al1 = valid1 ? am1 : 0.0f;
+    const f32x2 al2 = pk2(al0, al1);
+    const f32x2 ag2 = pk2(ar0 <= kMaxAlpha ? al0 : 0.0f, ar1 <= kMaxAlpha ? al1 : 0.0f);  // clamped alpha: no gradient
+    const f32x2 oma2 = sub2(bc2(1.0f), al2);
+    const f32x2 ra2 = pk2(rcp_approx(lo2(oma2)), rcp_approx(hi2(oma2)));
+    const f32x2 Tn2 = mul2(T2, ra2);  // transmittance in front of this Gaussian
+    const f32x2 fac2 = mul2(al2, Tn2);
+    f32x2 s1 = mul2(bc2(Cc.x), vout2[0]);
+    if (D >= 3) {
+        s1 = fma2(bc2(Cc.y), vout2[1], s1);
+        s1 = fma2(bc2(Cc.z), vout2[2], s1);
+    }
+    if (D == 4) s1 = fma2(bc2(Cc.w), vout2[3], s1);
+    const f32x2 va2 = fma2(Tn2, s1, neg2(mul2(ra2, bsum2)));
+    bsum2 = fma2(fac2, s1, bsum2);
+    T2 = Tn2;
+    const f32x2 g2 = mul2(ag2, va2);
+    const f32x2 ux2 = add2(t2, bc2(ax + ax));               // 2 qa dx + qb dy
+    const f32x2 uy2 = fma2(dy2, bc2(qc2), bc2(B.y * dx));  // qb dx + 2 qc dy
+    const f32x2 gx2 = mul2(g2, ux2), gy2 = mul2(g2, uy2);
+    const f32x2 gdx2 = mul2(g2, bc2(dx)), gdy2 = mul2(g2, dy2);
+    if (FIRST) {
+        v[0] = gx2;
+        v[1] = gy2;
+        v[2] = abs2(gx2);
+        v[3] = abs2(gy2);
+        v[4] = mul2(gdx2, bc2(dx));
+        v[5] = mul2(gdx2, dy2);
+        v[6] = mul2(gdy2, dy2);
+        v[7] = g2;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) v[8 + d] = d < D ? mul2(fac2, vout2[d < D ? d : 0]) : pk2(0.0f, 0.0f);
+    } else {
+        v[0] = add2(v[0], gx2);
+        v[1] = add2(v[1], gy2);
+        v[2] = add2(v[2], abs2(gx2));
+        v[3] = add2(v[3], abs2(gy2));
+        v[4] = fma2(gdx2, bc2(dx), v[4]);
+        v[5] = fma2(gdx2, dy2, v[5]);
+        v[6] = fma2(gdy2, dy2, v[6]);
+        v[7] = add2(v[7], g2);
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[8 + d] = fma2(fac2, vout2[d], v[8 + d]);
+    }
+    return (valid0 || valid1) ? 1 : 0;
+}
+
+// MINB = resident CTAs per SM asked of ptxas (register cap): occupancy is worth more than the few spills.
+template <int D, bool CULL, bool STATS, int MINB>
+__global__ void __launch_bounds__(Shape<4>::kThreads, MINB) raster_bwd_pk_kernel(const RasterParams p) {
+    constexpr int PX = 4;
+    using S = Shape<PX>;
+    __shared__ Staging<PX> sm;
+    StatCounters<STATS> st;
+    const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ox = tx * kTile, oy = ty * kTile + warp * S::kFootH;
+    const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);
+    const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
+    const f32x2 npy2 = pk2(-py0, -(py0 + 4.0f));
+
+    const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
+    const int64_t range_start = p.offsets[tile_id];
+
+    const float tx0 = (float)(tx * kTile) + 0.5f, ty0 = (float)(ty * kTile) + 0.5f;
+    const float tx1 = (float)min(tx * kTile + kTile - 1, p.width - 1) + 0.5f, ty1 = (float)min(ty * kTile + kTile - 1, p.height - 1) + 0.5f;
+    const SubRects<2> sr = make_blocks8(ox, oy, p.width, p.height);
+
+    const int slot = reduce_slot(lane);
+    const bool slot_active = reduce_lane_active(lane) && slot < 8 + D;
+    const float slot_scale = slot < 4 ? (1.0f / kLog2e) : ((slot == 4 || slot == 6) ? -0.5f : (slot == 5 ? -1.0f : 1.0f));
+
+    // per-pixel state, packed over b (rows i0, i0 + 4): T, bsum, v_out; last composited index per pixel
+    f32x2 T2[2], bsum2[2], vout2[2][D];
+    int32_t bin_final[2][2];
+    int sub_max[2];
+    int want = 0, wmax = -1;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        float Ts[2], bs[2], vo[2][D];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int i = i0 + b * 4, j = j0 + a * 8;
+            Ts[b] = 1.0f;
+            bs[b] = 0.0f;
+            bin_final[a][b] = -1;
+#pragma unroll
+            for (int d = 0; d < D; ++d) vo[b][d] = 0.0f;
+            if (i < p.height && j < p.width) {
+                const int64_t pix = ((int64_t)cam * p.height + i) * p.width + j;
+                const float alpha_out = p.alphas[pix];
+                const float T_final = 1.0f - alpha_out;
+                Ts[b] = T_final;
+                if (T_final < 1.0f) bin_final[a][b] = p.last_ids[pix];
+                if (D == 4) {
+                    const float4 v4 = reinterpret_cast<const float4*>(p.v_render)[pix];
+                    vo[b][0] = v4.x;
+                    vo[b][1] = v4.y;
+                    vo[b][2] = v4.z;
+                    vo[b][3] = v4.w;
+                } else {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) vo[b][d] = p.v_render[pix * D + d];
+                }
+                float v_alpha_out = p.v_alphas ? p.v_alphas[pix] : 0.0f;
+                if (p.normalize_last) {
+                    const float denom = fmaxf(alpha_out, 1e-10f);
+                    const float out_last = p.render[pix * D + D - 1];
+                    const float g = vo[b][D - 1];
+                    vo[b][D - 1] = g / denom;
+                    if (alpha_out > 1e-10f) v_alpha_out += -g * out_last / denom;
+                }
+                if (p.backgrounds) {
+                    float sbg = 0.0f;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) sbg += p.backgrounds[cam * D + d] * vo[b][d];
+                    v_alpha_out -= sbg;
+                }
+                bs[b] = -T_final * v_alpha_out;
+            }
+        }
+        T2[a] = pk2(Ts[0], Ts[1]);
+        bsum2[a] = pk2(bs[0], bs[1]);
+#pragma unroll
+        for (int d = 0; d < D; ++d) vout2[a][d] = pk2(vo[0][d], vo[1][d]);
+        int m = max(bin_final[a][0], bin_final[a][1]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        sub_max[a] = m;
+        if (m >= 0) want |= 1 << a;
+        wmax = max(wmax, m);
+    }
+    if (lane == 0) sm.max_last[warp] = wmax;
+    __syncthreads();
+    int cta_max = -1;
+#pragma unroll
+    for (int w = 0; w < S::kWarps; ++w) cta_max = max(cta_max, sm.max_last[w]);
+    if (cta_max < 0) return;
+
+    for (int64_t b1 = (int64_t)cta_max + 1; b1 > range_start; b1 -= S::kThreads) {
+        const int64_t e = b1 - 1 - threadIdx.x;
+        const int count = stage_batch<D, PX, CULL, STATS>(p, sm, e >= range_start, e, tx0, ty0, tx1, ty1, st);
+        for (int c0 = 0; c0 < count; c0 += 32) {
+            const int nq = fill_queue<PX, CULL, true, 2>(sm, c0, count, sr, want, sub_max);
+            for (int q = 0; q < nq; ++q) {
+                const float4 A = sm.qa[warp][q], B = sm.qb[warp][q], Cc = sm.qc[warp][q];
+                const int mask = sm.qm[warp][q];
+                if (lane == 0) st.add(2, __popc(mask));
+                const int sid = __float_as_int(A.w);
+                // shared by both blocks: dy, qb dy, qc dy^2 + lo
+                const f32x2 dy2 = add2(bc2(A.y), npy2);
+                const f32x2 t2 = mul2(bc2(B.y), dy2);
+                const f32x2 cy2 = fma2(mul2(bc2(B.z), dy2), dy2, bc2(A.z));
+                const float qc2 = B.z + B.z;
+                // lane-local packed sums; slots as in raster_bwd_kernel
+                f32x2 v[12];
+                int any_valid;
+                if (mask & 1) {
+                    any_valid = bwd_pk_block<D, true, STATS>(0, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[0], bsum2[0], vout2[0], bin_final[0], v, st);
+                    if (mask & 2)
+                        any_valid |= bwd_pk_block<D, false, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
+                } else {
+                    any_valid = bwd_pk_block<D, true, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
+                }
+                if (!__any_sync(0xffffffffu, any_valid)) continue;
+                if (lane == 0) st.add(5, 1);
+                float vs[12];
+#pragma unroll
+                for (int s = 0; s < 12; ++s) vs[s] = lo2(v[s]) + hi2(v[s]);
+                const float r = warp_reduce_transpose12(vs, lane);
+                const float inv_opac = ex2_approx(-A.z);
+                if (slot_active) {
+                    const float scale = (slot == 7) ? inv_opac : slot_scale;
+                    atomicAdd(p.packed_grads + (int64_t)__float_as_int(B.w) * kGradFloats + slot, r * scale);
+                }
+            }
+        }
+    }
+    st.flush(p.counters);
+}
+
+// ------------------------------------------------------------------------------------------------
 // pack / unpack helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_geom_kernel(int64_t CN, const float2* __restrict__ means2d, const float* __restrict__ conics,
@@ -629,6 +853,7 @@ __global__ void unpack_grads_kernel(int64_t CN, int D, const float4* __restrict_
 static int g_raster_cull = 1;                           // 0 disables the culling (identical results, slower)
 static unsigned long long* g_raster_counters = nullptr;  // device uint64[6] -> STATS kernels
 static int g_px_fwd = 1, g_px_bwd = 4;                   // pixels per lane
+static int g_raster_packed = 1;                          // f32x2 kernels where they exist (backward, 4 px/lane)
 
 template <int D, int PX, bool BWD>
 static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
@@ -642,6 +867,14 @@ static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
         } else {
             if (cull) raster_fwd_kernel<D, PX, true, false><<<grid, T, 0, stream>>>(p);
             else raster_fwd_kernel<D, PX, false, false><<<grid, T, 0, stream>>>(p);
+        }
+    } else if (PX == 4 && g_raster_packed) {
+        if (stats) {
+            if (cull) raster_bwd_pk_kernel<D, true, true, 8><<<grid, T, 0, stream>>>(p);
+            else raster_bwd_pk_kernel<D, false, true, 8><<<grid, T, 0, stream>>>(p);
+        } else {
+            if (cull) raster_bwd_pk_kernel<D, true, false, 12><<<grid, T, 0, stream>>>(p);
+            else raster_bwd_pk_kernel<D, false, false, 8><<<grid, T, 0, stream>>>(p);
         }
     } else {
         if (stats) {
@@ -713,6 +946,13 @@ extern "C" int qed_debug_set_raster_cull(int enabled) {
 extern "C" int qed_debug_set_raster_counters(void* counters) {
     g_raster_counters = reinterpret_cast<unsigned long long*>(counters);
     return QED_OK;
+}
+
+// nonzero: two-wide fp32 (f32x2) kernels where they exist; 0: scalar kernels only.  Returns the previous value.
+extern "C" int qed_debug_set_raster_packed(int enabled) {
+    int old = g_raster_packed;
+    g_raster_packed = enabled;
+    return old;
 }
 
 // pixels per lane of the forward / backward compositor (1, 2 or 4; 0 keeps the current value)

@@ -347,3 +347,9 @@ def set_raster_px(px_fwd: int = 0, px_bwd: int = 0) -> int:
     """Test/tuning hook: pixels per lane (1, 2 or 4; 0 = keep) of the forward / backward compositor.
     Returns 10*px_fwd + px_bwd now in effect."""
     return int(_lib.load().qed_debug_set_raster_px(int(px_fwd), int(px_bwd)))
+
+
+def set_raster_packed(enabled: bool) -> bool:
+    """Test/tuning hook: use the two-wide fp32 (FFMA2) compositor kernels where they exist (default on).
+    Returns the previous setting."""
+    return bool(_lib.load().qed_debug_set_raster_packed(int(enabled)))
