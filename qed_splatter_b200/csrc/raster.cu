@@ -611,11 +611,15 @@ __global__ void __launch_bounds__(Shape<PX>::kThreads) raster_bwd_kernel(const R
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, packed: the same algorithm with the per-pixel arithmetic on sm_100's two-wide fp32
-// instructions (FFMA2 / FMUL2 / FADD2 retire two IEEE fp32 results per issue slot; scalar-broadcast,
-// negate and |.| operand forms are free).  Layout = Shape<4> (2 warps per tile, 16x8 footprint, lane
-// pixels at columns j0 + 8a, rows i0 + 4b); a pair is (a, b=0) / (a, b=1): the two pixels of one 8x8
-// block share dx and differ in dy.  Culling masks are per 8x8 block.
+// backward, packed (the default): the algorithm of raster_bwd_kernel re-cut for Blackwell's issue limits.
+//   * per-pixel arithmetic on sm_100's two-wide fp32 instructions: FFMA2 / FMUL2 / FADD2 retire two IEEE
+//     fp32 results per issue slot, with free scalar-broadcast, negate and |.| operand forms.  Layout =
+//     Shape<4> (2 warps per tile, 16x8 footprint, lane pixels at columns j0 + 8a, rows i0 + 4b); a pair is
+//     (a, b=0) / (a, b=1): the two pixels of one 8x8 block share dx and differ in dy.  Culling masks are per
+//     8x8 block; when both blocks of a Gaussian are hit they run as one basic block (ILP).
+//   * warp streams: the two warps of a tile never meet (no block barrier), see raster_bwd_ws_kernel.
+//   * the cross-lane gradient sums go through a shared-memory transpose + red.global.add.v4.f32 instead of a
+//     shuffle butterfly (reduce_entries).
 // ------------------------------------------------------------------------------------------------
 // One 8x8 block (column half `a`): the lane's two pixels (rows i0, i0 + 4) in the two halves of every
 // f32x2.  FIRST: v[] is written, else accumulated (no zero-fill, no register shuffling where the paths
@@ -683,36 +687,12 @@ __device__ __forceinline__ int bwd_pk_block(int a, const float4& A, const float4
     return (valid0 || valid1) ? 1 : 0;
 }
 
-// MINB = resident CTAs per SM asked of ptxas (register cap): occupancy is worth more than the few spills.
-template <int D, bool CULL, bool STATS, int MINB>
-__global__ void __launch_bounds__(Shape<4>::kThreads, MINB) raster_bwd_pk_kernel(const RasterParams p) {
-    constexpr int PX = 4;
-    using S = Shape<PX>;
-    __shared__ Staging<PX> sm;
-    StatCounters<STATS> st;
-    const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ox = tx * kTile, oy = ty * kTile + warp * S::kFootH;
-    const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);
-    const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
-    const f32x2 npy2 = pk2(-py0, -(py0 + 4.0f));
-
-    const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
-    const int64_t range_start = p.offsets[tile_id];
-
-    const float tx0 = (float)(tx * kTile) + 0.5f, ty0 = (float)(ty * kTile) + 0.5f;
-    const float tx1 = (float)min(tx * kTile + kTile - 1, p.width - 1) + 0.5f, ty1 = (float)min(ty * kTile + kTile - 1, p.height - 1) + 0.5f;
-    const SubRects<2> sr = make_blocks8(ox, oy, p.width, p.height);
-
-    const int slot = reduce_slot(lane);
-    const bool slot_active = reduce_lane_active(lane) && slot < 8 + D;
-    const float slot_scale = slot < 4 ? (1.0f / kLog2e) : ((slot == 4 || slot == 6) ? -0.5f : (slot == 5 ? -1.0f : 1.0f));
-
-    // per-pixel state, packed over b (rows i0, i0 + 4): T, bsum, v_out; last composited index per pixel
-    f32x2 T2[2], bsum2[2], vout2[2][D];
-    int32_t bin_final[2][2];
-    int sub_max[2];
-    int want = 0, wmax = -1;
+// Per-pixel start state of the packed backward (warp footprint 16x8 at (j0 - lane%8, i0 - lane/8)): final
+// transmittance, bsum = -T_final * dL/dalpha_out (ED normalisation and background folded in), output
+// gradients, last composited index; per 8x8 block the warp-wide last index (sub_max) and `want` bits.
+template <int D>
+__device__ __forceinline__ void bwd_pk_prologue(const RasterParams& p, int cam, int i0, int j0, f32x2 (&T2)[2], f32x2 (&bsum2)[2],
+                                                f32x2 (&vout2)[2][D], int32_t (&bin_final)[2][2], int (&sub_max)[2], int& want, int& wmax) {
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         float Ts[2], bs[2], vo[2][D];
@@ -768,52 +748,178 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, MINB) raster_bwd_pk_kernel
         if (m >= 0) want |= 1 << a;
         wmax = max(wmax, m);
     }
-    if (lane == 0) sm.max_last[warp] = wmax;
-    __syncthreads();
-    int cta_max = -1;
-#pragma unroll
-    for (int w = 0; w < S::kWarps; ++w) cta_max = max(cta_max, sm.max_last[w]);
-    if (cta_max < 0) return;
+}
 
-    for (int64_t b1 = (int64_t)cta_max + 1; b1 > range_start; b1 -= S::kThreads) {
-        const int64_t e = b1 - 1 - threadIdx.x;
-        const int count = stage_batch<D, PX, CULL, STATS>(p, sm, e >= range_start, e, tx0, ty0, tx1, ty1, st);
-        for (int c0 = 0; c0 < count; c0 += 32) {
-            const int nq = fill_queue<PX, CULL, true, 2>(sm, c0, count, sr, want, sub_max);
-            for (int q = 0; q < nq; ++q) {
-                const float4 A = sm.qa[warp][q], B = sm.qb[warp][q], Cc = sm.qc[warp][q];
-                const int mask = sm.qm[warp][q];
-                if (lane == 0) st.add(2, __popc(mask));
-                const int sid = __float_as_int(A.w);
-                // shared by both blocks: dy, qb dy, qc dy^2 + lo
-                const f32x2 dy2 = add2(bc2(A.y), npy2);
-                const f32x2 t2 = mul2(bc2(B.y), dy2);
-                const f32x2 cy2 = fma2(mul2(bc2(B.z), dy2), dy2, bc2(A.z));
-                const float qc2 = B.z + B.z;
-                // lane-local packed sums; slots as in raster_bwd_kernel
-                f32x2 v[12];
-                int any_valid;
-                if (mask & 1) {
-                    any_valid = bwd_pk_block<D, true, STATS>(0, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[0], bsum2[0], vout2[0], bin_final[0], v, st);
-                    if (mask & 2)
-                        any_valid |= bwd_pk_block<D, false, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
-                } else {
-                    any_valid = bwd_pk_block<D, true, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
-                }
-                if (!__any_sync(0xffffffffu, any_valid)) continue;
-                if (lane == 0) st.add(5, 1);
-                float vs[12];
+// Warp streams.  Each warp walks the tile's sorted range on its own, 32 entries per batch, back to front
+// from ITS OWN last contributing index.  The gather (id -> 32-B geom + colour) of batch i+1 is in flight as
+// cp.async into a double-buffered, lane-private landing zone while batch i is composited, and the ids of
+// batch i+2 are loaded one batch ahead of that, so no global-load latency and no block barrier sits on the
+// critical path (ncu on a CTA-staged version of this kernel: long_scoreboard + barrier = 20 % of the stall
+// cycles).  Every lane culls its own entry directly against the warp's two 8x8 blocks.
+struct WarpStream {
+    float4 ra[2][32], rb[2][32], rc[2][32];  // landing zone: geom (2 x 16 B) + colour of the lane's entry, two batches
+    float4 qa[32], qb[32], qc[32];           // queue of the batch being composited (see Staging)
+    int qm[32];
+    float4 red[6][36];                       // gradient transpose: [entry parity * 3 + slot group][lane, 8 + 1 pad]
+};
+
+// Position of lane l in a `red` row: every 8 lanes are followed by one float4 of padding, so that the eight
+// lanes of a shared-memory phase hit eight different 16-B columns on the write AND on the transposed read.
+__device__ __forceinline__ int red_pos(int l) { return (l >> 3) * 9 + (l & 7); }
+
+// Cross-lane sums of the gradient slots of queue entries q0 (even) .. q0+count-1 (count <= 2), whose
+// per-lane values sit in ws.red.  Instead of a shuffle butterfly per Gaussian (16 SHFL + 22 FSEL + 16 FADD),
+// the values are transposed through shared memory: lane = (entry, slot group, quarter) sums 8 lanes' float4
+// with FADD2 and adds its quarter-sum with ONE vector red.global.add.v4.f32.
+__device__ __forceinline__ void reduce_entries(const RasterParams& p, WarpStream& ws, int q0, int count, int lane) {
+    const int item = lane >> 2, quarter = lane & 3;  // item = entry parity * 3 + slot group
+    const int qq = item >= 3 ? 1 : 0, sg = item - qq * 3;
+    if (lane < 24 && qq < count) {
+        const float4* src = &ws.red[item][quarter * 9];
+        f32x2 s01 = pk2(src[0].x, src[0].y), s23 = pk2(src[0].z, src[0].w);
 #pragma unroll
-                for (int s = 0; s < 12; ++s) vs[s] = lo2(v[s]) + hi2(v[s]);
-                const float r = warp_reduce_transpose12(vs, lane);
-                const float inv_opac = ex2_approx(-A.z);
-                if (slot_active) {
-                    const float scale = (slot == 7) ? inv_opac : slot_scale;
-                    atomicAdd(p.packed_grads + (int64_t)__float_as_int(B.w) * kGradFloats + slot, r * scale);
-                }
-            }
+        for (int j = 1; j < 8; ++j) {
+            const float4 x = src[j];
+            s01 = add2(s01, pk2(x.x, x.y));
+            s23 = add2(s23, pk2(x.z, x.w));
+        }
+        // back to the (mean2d, conic, opacity, colour) parametrisation:
+        //   v_mean = g u / log2e ; v_conic = -(g dx^2 / 2, g dx dy, g dy^2 / 2) ; v_opacity = g / opacity
+        const int g = __float_as_int(ws.qb[q0 + qq].w);
+        float k0 = 1.0f, k1 = 1.0f, k3 = 1.0f;
+        if (sg == 0) k0 = k1 = k3 = 1.0f / kLog2e;
+        if (sg == 1) {
+            k0 = -0.5f;
+            k1 = -1.0f;
+            k3 = ex2_approx(-ws.qa[q0 + qq].z);
+        }
+        s01 = mul2(s01, pk2(k0, k1));
+        s23 = mul2(s23, pk2(k0, k3));
+        red_add_v4(p.packed_grads + (int64_t)g * kGradFloats + sg * 4, lo2(s01), hi2(s01), lo2(s23), hi2(s23));
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void stream_fetch(const RasterParams& p, WarpStream& ws, int buf, int lane, bool have, int g) {
+    if (have) {
+        cp_async16(&ws.ra[buf][lane], p.geom + (int64_t)g * 2);
+        cp_async16(&ws.rb[buf][lane], p.geom + (int64_t)g * 2 + 1);
+        if (D == 4) {
+            cp_async16(&ws.rc[buf][lane], p.colors + (int64_t)g * 4);
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) cp_async4(reinterpret_cast<float*>(&ws.rc[buf][lane]) + d, p.colors + (int64_t)g * D + d);
         }
     }
+    cp_async_commit();
+}
+
+// 12 resident CTAs per SM asked of ptxas (80 registers): occupancy is worth more than the 4 bytes it spills.
+template <int D, bool CULL, bool STATS>
+__global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(const RasterParams p) {
+    using S = Shape<4>;
+    __shared__ WarpStream wss[S::kWarps];
+    StatCounters<STATS> st;
+    const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStream& ws = wss[warp];
+    const int ox = tx * kTile, oy = ty * kTile + warp * S::kFootH;
+    const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);
+    const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
+    const f32x2 npy2 = pk2(-py0, -(py0 + 4.0f));
+    const int rpos = red_pos(lane);
+
+    const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
+    const int range_start = p.offsets[tile_id];
+    const SubRects<2> sr = make_blocks8(ox, oy, p.width, p.height);
+
+    f32x2 T2[2], bsum2[2], vout2[2][D];
+    int32_t bin_final[2][2];
+    int sub_max[2];
+    int want = 0, wmax = -1;
+    bwd_pk_prologue<D>(p, cam, i0, j0, T2, bsum2, vout2, bin_final, sub_max, want, wmax);
+    if (wmax < 0) return;  // nothing composited under this warp's footprint (no block-wide barrier below)
+
+    // batch i covers sorted indices (top - 32 i - 31 .. top - 32 i], lane l owns top - 32 i - l
+    const int top = wmax;
+    const int n_batches = (top - range_start) / 32 + 1;
+    int e_cur = top - lane;
+    int g_cur = e_cur >= range_start ? p.flatten_ids[e_cur] : 0;
+    stream_fetch<D>(p, ws, 0, lane, e_cur >= range_start, g_cur);
+    int g_nxt = (e_cur - 32 >= range_start) ? p.flatten_ids[e_cur - 32] : 0;
+
+    for (int i = 0; i < n_batches; ++i, e_cur -= 32) {
+        const int buf = i & 1;
+        stream_fetch<D>(p, ws, buf ^ 1, lane, e_cur - 32 >= range_start, g_nxt);       // batch i+1: geom + colour
+        const int g_n2 = (e_cur - 64 >= range_start) ? p.flatten_ids[e_cur - 64] : 0;  // batch i+2: id
+        cp_async_wait<1>();                                                            // batch i has landed
+        const bool have = e_cur >= range_start;
+        int mask = 0;
+        float4 A = make_float4(0, 0, 0, 0), B = make_float4(0, 0, 0, 0);
+        st.add(0, have ? 1 : 0);
+        if (have && want) {
+            const float4 ga = ws.ra[buf][lane];  // mx, my, opacity, depth
+            const float4 gb = ws.rb[buf][lane];  // conic a, b, c
+            const float lo = __log2f(ga.z);
+            A = make_float4(ga.x, ga.y, lo, __int_as_float(e_cur));
+            B = make_float4(-0.5f * kLog2e * gb.x, -kLog2e * gb.y, -0.5f * kLog2e * gb.z, __int_as_float(g_cur));
+            const float tau2 = lo + kLog2_255;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                bool hit = ((want >> k) & 1) && (e_cur <= sub_max[k]);
+                if (CULL && hit) hit = ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, tau2, sr.x0[k], sr.y0[k], sr.x1[k], sr.y1[k]);
+                if (hit) mask |= 1 << k;
+            }
+        }
+        st.add(1, mask ? 1 : 0);
+        const uint32_t m = __ballot_sync(0xffffffffu, mask != 0);  // also: every lane is done with the previous queue
+        if (mask) {
+            const int pos = __popc(m & ((1u << lane) - 1u));
+            float4 c = ws.rc[buf][lane];
+            if (D < 4) c.w = 0.0f;
+            if (D < 3) c.y = c.z = 0.0f;
+            ws.qa[pos] = A;
+            ws.qb[pos] = B;
+            ws.qc[pos] = c;
+            ws.qm[pos] = mask;
+        }
+        __syncwarp();
+        const int nq = __popc(m);
+        for (int q = 0; q < nq; ++q) {
+            const float4 A = ws.qa[q], B = ws.qb[q], Cc = ws.qc[q];
+            const int mask = ws.qm[q];
+            if (lane == 0) st.add(2, __popc(mask));
+            const int sid = __float_as_int(A.w);
+            const f32x2 dy2 = add2(bc2(A.y), npy2);
+            const f32x2 t2 = mul2(bc2(B.y), dy2);
+            const f32x2 cy2 = fma2(mul2(bc2(B.z), dy2), dy2, bc2(A.z));
+            const float qc2 = B.z + B.z;
+            f32x2 v[12];
+            int any_valid;
+            if (mask == 3) {  // one basic block: the two independent blocks interleave (ILP)
+                any_valid = bwd_pk_block<D, true, STATS>(0, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[0], bsum2[0], vout2[0], bin_final[0], v, st);
+                any_valid |= bwd_pk_block<D, false, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
+            } else if (mask == 1) {
+                any_valid = bwd_pk_block<D, true, STATS>(0, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[0], bsum2[0], vout2[0], bin_final[0], v, st);
+            } else {
+                any_valid = bwd_pk_block<D, true, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
+            }
+            if (STATS && lane == 0 && __any_sync(0xffffffffu, any_valid)) st.add(5, 1);
+            float vs[12];
+#pragma unroll
+            for (int s = 0; s < 12; ++s) vs[s] = lo2(v[s]) + hi2(v[s]);
+#pragma unroll
+            for (int sg = 0; sg < 3; ++sg) ws.red[(q & 1) * 3 + sg][rpos] = make_float4(vs[4 * sg], vs[4 * sg + 1], vs[4 * sg + 2], vs[4 * sg + 3]);
+            if ((q & 1) || q == nq - 1) {
+                __syncwarp();
+                reduce_entries(p, ws, q & ~1, (q & 1) + 1, lane);
+                __syncwarp();
+            }
+        }
+        g_cur = g_nxt;
+        g_nxt = g_n2;
+    }
+    cp_async_wait<0>();
     st.flush(p.counters);
 }
 
@@ -870,11 +976,11 @@ static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
         }
     } else if (PX == 4 && g_raster_packed) {
         if (stats) {
-            if (cull) raster_bwd_pk_kernel<D, true, true, 8><<<grid, T, 0, stream>>>(p);
-            else raster_bwd_pk_kernel<D, false, true, 8><<<grid, T, 0, stream>>>(p);
+            if (cull) raster_bwd_ws_kernel<D, true, true><<<grid, T, 0, stream>>>(p);
+            else raster_bwd_ws_kernel<D, false, true><<<grid, T, 0, stream>>>(p);
         } else {
-            if (cull) raster_bwd_pk_kernel<D, true, false, 12><<<grid, T, 0, stream>>>(p);
-            else raster_bwd_pk_kernel<D, false, false, 8><<<grid, T, 0, stream>>>(p);
+            if (cull) raster_bwd_ws_kernel<D, true, false><<<grid, T, 0, stream>>>(p);
+            else raster_bwd_ws_kernel<D, false, false><<<grid, T, 0, stream>>>(p);
         }
     } else {
         if (stats) {
@@ -951,7 +1057,7 @@ extern "C" int qed_debug_set_raster_counters(void* counters) {
 // nonzero: two-wide fp32 (f32x2) kernels where they exist; 0: scalar kernels only.  Returns the previous value.
 extern "C" int qed_debug_set_raster_packed(int enabled) {
     int old = g_raster_packed;
-    g_raster_packed = enabled;
+    g_raster_packed = enabled ? 1 : 0;
     return old;
 }
 

@@ -352,4 +352,4 @@ def set_raster_px(px_fwd: int = 0, px_bwd: int = 0) -> int:
 def set_raster_packed(enabled: bool) -> bool:
     """Test/tuning hook: use the two-wide fp32 (FFMA2) compositor kernels where they exist (default on).
     Returns the previous setting."""
-    return bool(_lib.load().qed_debug_set_raster_packed(int(enabled)))
+    return bool(_lib.load().qed_debug_set_raster_packed(1 if enabled else 0))

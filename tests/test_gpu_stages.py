@@ -212,6 +212,31 @@ def test_raster_cull_is_exact(cuda):
         assert_close_frac(a, b, 1e-4, 1e-6 * float(b.abs().mean() + 1e-12), 1e-3, "grad cull vs no-cull")
 
 
+@pytest.mark.parametrize("D,bg", [(4, True), (3, False), (1, False)])
+def test_raster_backward_packed_matches_scalar(cuda, D, bg):
+    """The default backward (two-wide fp32 + warp streams + shared-memory transpose) and the scalar kernel it
+    replaced are the same function: identical up to summation order, on a scene with image-edge tiles."""
+    s = scene_s0(N=20000, C=2, size=200)  # 200 = 12.5 tiles: clipped blocks on the right / bottom edge
+    m, c, cols, op, off, flat = [t.to(cuda) for t in _raster_inputs(s)]
+    cols = {4: cols, 3: cols[..., :3].contiguous(), 1: cols[..., 3:].contiguous()}[D]
+    gen = torch.Generator().manual_seed(5)
+    bgs = torch.rand(s.C, D, generator=gen).to(cuda) if bg else None
+    vr = torch.randn(s.C, s.height, s.width, D, generator=gen).to(cuda)
+    va = torch.randn(s.C, s.height, s.width, 1, generator=gen).to(cuda)
+    grads = {}
+    try:
+        for packed in (True, False):
+            ops.set_raster_packed(packed)
+            gl = [t.clone().requires_grad_(True) for t in (m, c, cols, op)]
+            render, alpha = ops.rasterize_to_pixels(*gl, s.width, s.height, 16, off, flat, backgrounds=bgs, absgrad=True)
+            ((render * vr).sum() + (alpha * va).sum()).backward()
+            grads[packed] = [t.grad for t in gl] + [gl[0].absgrad]
+    finally:
+        ops.set_raster_packed(True)
+    for name, a, b in zip(["means2d", "conics", "colors", "opacities", "absgrad"], grads[True], grads[False]):
+        assert_close_frac(a, b, 1e-4, 1e-5 * float(b.abs().mean() + 1e-12), 1e-3, f"packed vs scalar v_{name}")
+
+
 def test_isect_full_size_paths_agree(cuda):
     """BASELINE configs[1] size (1M Gaussians, 1080p): the two-level build, the own 64-bit radix sort and the
     CUB baseline must produce the same bytes; keys must be sorted and ranges consistent."""
