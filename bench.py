@@ -38,7 +38,7 @@ PARAM_FLOATS = 3 + 4 + 3 + 1 + 48  # means, quats, scales, opacity, SH(16x3) = 5
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
 # workload (profiles/r01_raster_bwd_ncu_summary.txt, profiles/r01_kernel_notes.md); None = not captured
-NCU_DRAM_BYTES = {"raster_bwd": 146.94e6 + 7.76e6, "raster_fwd": 52.36e6 + 18.31e6}
+NCU_DRAM_BYTES = {"raster_bwd": 149.16e6 + 10.39e6, "raster_fwd": 47.55e6 + 15.36e6}
 
 # SURVEY.md §8(d) per-unit figures (D = 4 channels)
 FLOP_PER_PAIR_FWD = 30.0
@@ -399,13 +399,16 @@ def main_ours(args):
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the SM clock seen during the timed region
 
-        def fp32_roof(name, pairs, flop_per_pair):
+        def fp32_roof(name, pairs, evaluated, flop_per_pair):
+            # algorithmic work = (pixel, Gaussian) pairs that pass the alpha test and are composited / differentiated:
+            # independent of how well an implementation culls; pairs_evaluated (>= pairs) is what this one touched
             t_ms = stage_ms.get(name)
             if not t_ms or not pairs:
                 return None
             ach = pairs * flop_per_pair / (t_ms * 1e-3) / 1e12
             return {"kernel": name, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-                    "traffic": NCU_DRAM_BYTES.get(name), "ms": t_ms, "pairs_evaluated": pairs, "flop_per_pair": flop_per_pair,
+                    "traffic": NCU_DRAM_BYTES.get(name), "ms": t_ms, "pairs_composited": pairs, "pairs_evaluated": evaluated,
+                    "flop_per_pair": flop_per_pair,
                     "peak_source": f"derived: 148 SM x 128 lanes x 2 FLOP x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)"}
 
         def hbm_roof(name, bytes_):
@@ -425,8 +428,8 @@ def main_ours(args):
         bytes_prepare = N * 20.0 + n_visible * (8.0 + 4 * 20.0 + 16.0)
         bytes_fill = M * (8.0 + tile_passes * 20.0 + 8.0)
         stages = [
-            fp32_roof("raster_bwd", counters.get("bwd_pairs_evaluated"), FLOP_PER_PAIR_BWD),
-            fp32_roof("raster_fwd", counters.get("fwd_pairs_evaluated"), FLOP_PER_PAIR_FWD),
+            fp32_roof("raster_bwd", counters.get("bwd_pairs_contributing"), counters.get("bwd_pairs_evaluated"), FLOP_PER_PAIR_BWD),
+            fp32_roof("raster_fwd", counters.get("fwd_pairs_contributing"), counters.get("fwd_pairs_evaluated"), FLOP_PER_PAIR_FWD),
             hbm_roof("project_fwd", N * BYTES_PROJ_FWD_PER_GAUSS + n_visible * BYTES_PROJ_FWD_PER_VISIBLE),
             hbm_roof("project_bwd", N * BYTES_PROJ_BWD_PER_GAUSS + n_visible * BYTES_PROJ_BWD_PER_VISIBLE),
             hbm_roof("isect_prepare", bytes_prepare),

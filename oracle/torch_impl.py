@@ -44,6 +44,7 @@ __all__ = [
     "isect_offset_encode",
     "rasterize_to_pixels",
     "rasterize_to_pixels_bwd",
+    "count_composited_pairs",
     "rasterization",
     "get_viewmat",
     "composite_and_fill",
@@ -368,6 +369,22 @@ def _tile_forward(px, py, m2d, con, opa):
     alive = torch.cumsum(stop.to(torch.int32), dim=1) == 0
     included = valid & alive
     return dx, dy, sigma, vis, alpha_raw, alpha, T_before, included
+
+
+def count_composited_pairs(means2d, conics, opacities, image_width, image_height, tile_size, isect_offsets, flatten_ids) -> int:
+    """Number of (pixel, Gaussian) pairs that pass the alpha / transmittance tests and are composited: the
+    implementation-independent work unit of the compositing kernels (bench.py `roofline`)."""
+    C, N = opacities.shape
+    th, tw = isect_offsets.shape[1:]
+    m2, cn, op = means2d.reshape(C * N, 2), conics.reshape(C * N, 3), opacities.reshape(C * N)
+    fid = flatten_ids.to(torch.int64)
+    total = 0
+    for c, ty, tx, s, e in _tile_iter(C, th, tw, isect_offsets, flatten_ids.numel()):
+        if e > s:
+            _, _, px, py = _tile_pixels(ty, tx, tile_size, image_width, image_height, means2d.dtype)
+            g = fid[s:e]
+            total += int(_tile_forward(px, py, m2[g], cn[g], op[g])[-1].sum())
+    return total
 
 
 def rasterize_to_pixels(

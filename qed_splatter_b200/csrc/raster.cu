@@ -4,27 +4,29 @@
 // qed_splatter/model.py:267-288; absgrad (model.py:284) is produced by the backward.
 // Semantics: SURVEY.md Appendix A.5 / A.6 == oracle/torch_impl.py::rasterize_to_pixels(_bwd).
 //
-// Design (B200-first, not gsplat's).  Both kernels are FP32-issue bound (ncu: ~86 % issue-active), so the
-// design minimises instructions per evaluated (pixel, Gaussian) pair:
-//   * one CTA per 16x16 tile (tile size is fixed by the bit-exact intersection contract); every lane owns
-//     PX pixels (1, 2 or 4), so a warp covers an 8x4, 16x4 or 16x8 pixel footprint.
-//   * Gaussians of the tile's sorted range are gathered through flatten_ids, one per thread per batch, and
-//     re-expressed in the log2 domain:  log2(alpha) = lo + qa dx^2 + qb dx dy + qc dy^2  with
-//     lo = log2(opacity), (qa,qb,qc) = -log2(e) * (a/2, b, c/2).  The exponential is then a bare
-//     ex2.approx (one MUFU) and the quadratic form shares terms between the pixels of a lane.
-//   * EXACT two-level culling: a Gaussian changes a pixel only if alpha >= 1/255, i.e. the pixel centre is
-//     inside the ellipse Q(d) <= lo + log2(255).  The loader thread tests that ellipse against the whole
-//     tile (survivors compacted in order with ballots); every warp then tests 32 survivors at a time
-//     against its own footprint with one ballot and copies the hits, compacted and in order, into a
-//     private shared-memory queue.  The inner loop is a plain counted loop over that queue (3 broadcast
-//     LDS.128 per Gaussian, no index arithmetic).  The test is conservative (minimum of Q over the
-//     rectangle plus a rounding margin), so results are identical to the un-culled kernel (test hook).
-//   * fully predicated inner loops (no divergent branches); early termination per lane, per warp
-//     (__all_sync) and per CTA (__syncthreads_count).
+// Design (B200-first, not gsplat's).  Both kernels are bound by instruction issue and the fp32 pipes (ncu:
+// 72-82 % issue-active, <10 % L2), so the design minimises instructions per evaluated (pixel, Gaussian) pair:
+//   * one CTA of two warps per 16x16 tile (tile size is fixed by the bit-exact intersection contract); a warp
+//     owns a 16x8 footprint = two 8x8 blocks, a lane owns 4 pixels (columns j0 + 8a, rows i0 + 4b).
+//   * packed fp32: the two pixels of a lane in one 8x8 block share dx and sit in the two halves of an f32x2;
+//     sm_100's FFMA2 / FMUL2 / FADD2 retire both per issue slot (scalar-broadcast, negate, |.| operands free).
+//   * log2 domain: log2(alpha) = lo + qa dx^2 + qb dx dy + qc dy^2 with lo = log2(opacity),
+//     (qa,qb,qc) = -log2(e) * (a/2, b, c/2); the exponential is a bare ex2.approx (one MUFU).
+//   * warp streams: each warp walks the tile's sorted range on its own, 32 entries per batch; the gather
+//     (id -> 32-B geom + colour) of the next batch is in flight as cp.async while the current one is
+//     composited; no block barrier anywhere.
+//   * EXACT culling: a Gaussian changes a pixel only if alpha >= 1/255, i.e. the pixel centre is inside the
+//     ellipse Q(d) <= lo + log2(255).  Every lane tests its entry against the warp's two 8x8 blocks
+//     (conservative: minimum of Q over the rectangle plus a rounding margin) and survivors are compacted, in
+//     order, into a per-warp shared-memory queue with their block mask.  The inner loop is a counted loop over
+//     that queue (3 broadcast LDS.128 per Gaussian).  Results are identical to the un-culled kernel (test hook).
+//   * a pixel that fails the alpha test simply gets alpha = 0 (T * 1, + 0): no selects behind the packed ops.
 //   * backward: back-to-front replay from the stored last index with a scalar running
-//     bsum = sum_k buffer[k] v_out[k]; per Gaussian the 12 gradient values of all PX pixels of a lane are
-//     pre-added, then reduced across the warp with a transposed butterfly (16 shuffles instead of 60) and
-//     added with one red.global.add per value from 12 lanes into the packed [C*N,12] record.
+//     bsum = sum_k buffer[k] v_out[k]; per Gaussian the 12 gradient values of a lane's 4 pixels are pre-added,
+//     transposed through shared memory and summed by 24 lanes, one red.global.add.v4.f32 each, into the
+//     packed [C*N,12] record.
+// The scalar kernels (raster_fwd_kernel / raster_bwd_kernel: CTA-staged, 1/2/4 pixels per lane, shuffle
+// butterfly) are kept as the cross-check the packed ones are tested against (qed_debug_set_raster_packed).
 #include "common.cuh"
 
 namespace qed {
@@ -380,6 +382,197 @@ __global__ void __launch_bounds__(Shape<PX>::kThreads) raster_fwd_kernel(const R
             }
             p.alphas[pix] = alpha_out;
             p.last_ids[pix] = last[k];
+        }
+    }
+    st.flush(p.counters);
+}
+
+// Warp streams.  Each warp walks the tile's sorted range on its own, 32 entries per batch, from ITS OWN
+// start (backward: its last contributing index, walking back to front) to its own end (forward: until all its
+// pixels are opaque).  The gather (id -> 32-B geom + colour) of batch i+1 is in flight as
+// cp.async into a double-buffered, lane-private landing zone while batch i is composited, and the ids of
+// batch i+2 are loaded one batch ahead of that, so no global-load latency and no block barrier sits on the
+// critical path (ncu on a CTA-staged version of this kernel: long_scoreboard + barrier = 20 % of the stall
+// cycles).  Every lane culls its own entry directly against the warp's two 8x8 blocks.
+struct WarpStream {
+    float4 ra[2][32], rb[2][32], rc[2][32];  // landing zone: geom (2 x 16 B) + colour of the lane's entry, two batches
+    float4 qa[32], qb[32], qc[32];           // queue of the batch being composited (see Staging)
+    int qm[32];
+};
+template <int D>
+__device__ __forceinline__ void stream_fetch(const RasterParams& p, WarpStream& ws, int buf, int lane, bool have, int g) {
+    if (have) {
+        cp_async16(&ws.ra[buf][lane], p.geom + (int64_t)g * 2);
+        cp_async16(&ws.rb[buf][lane], p.geom + (int64_t)g * 2 + 1);
+        if (D == 4) {
+            cp_async16(&ws.rc[buf][lane], p.colors + (int64_t)g * 4);
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) cp_async4(reinterpret_cast<float*>(&ws.rc[buf][lane]) + d, p.colors + (int64_t)g * D + d);
+        }
+    }
+    cp_async_commit();
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, packed + warp streams (the default).  Same layout as the packed backward: 2 warps per tile, lane
+// pixels at columns j0 + 8a, rows i0 + 4b, the two rows of an 8x8 block in the two halves of an f32x2.
+// ------------------------------------------------------------------------------------------------
+// `thr` is the per-pixel alpha threshold: 1/255 while the pixel is live, 2 (never reached) once it is opaque
+// or outside the image -- "live" costs no instruction in the test.
+template <int D, bool STATS>
+__device__ __forceinline__ void fwd_pk_block(int a, const float4& A, const float4& B, const float4& Cc, float px0, f32x2 dy2, f32x2 t2,
+                                             f32x2 cy2, f32x2& T2, f32x2 (&acc2)[D], int32_t (&last)[2], float (&thr)[2],
+                                             StatCounters<STATS>& st) {
+    const float dx = A.x - (px0 + 8.0f * a);
+    const float ax = B.x * dx;
+    const f32x2 pw2 = fma2(add2(t2, bc2(ax)), bc2(dx), cy2);  // log2(opacity * exp(-sigma))
+    const float pw0 = lo2(pw2), pw1 = hi2(pw2);
+    const float am0 = fminf(kMaxAlpha, ex2_approx(pw0)), am1 = fminf(kMaxAlpha, ex2_approx(pw1));
+    const bool ok0 = (pw0 <= A.z) && (am0 >= thr[0]);  // pw <= lo  <=>  sigma >= 0
+    const bool ok1 = (pw1 <= A.z) && (am1 >= thr[1]);
+    const f32x2 nT2 = mul2(T2, sub2(bc2(1.0f), pk2(am0, am1)));
+    const bool stop0 = ok0 && (lo2(nT2) <= kTransmittanceThreshold), stop1 = ok1 && (hi2(nT2) <= kTransmittanceThreshold);
+    const bool upd0 = ok0 && !stop0, upd1 = ok1 && !stop1;
+    st.add(3, (thr[0] < 1.0f ? 1 : 0) + (thr[1] < 1.0f ? 1 : 0));
+    st.add(4, (upd0 ? 1 : 0) + (upd1 ? 1 : 0));
+    const f32x2 al2 = pk2(upd0 ? am0 : 0.0f, upd1 ? am1 : 0.0f);  // alpha = 0: the pixel skips this Gaussian
+    const f32x2 w2 = mul2(al2, T2);
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc2[d] = fma2(bc2(d == 0 ? Cc.x : d == 1 ? Cc.y : d == 2 ? Cc.z : Cc.w), w2, acc2[d]);
+    T2 = mul2(T2, sub2(bc2(1.0f), al2));  // == nT2 where updated (same two roundings), T * 1 elsewhere
+    const int sid = __float_as_int(A.w);
+    last[0] = upd0 ? sid : last[0];
+    last[1] = upd1 ? sid : last[1];
+    thr[0] = stop0 ? 2.0f : thr[0];
+    thr[1] = stop1 ? 2.0f : thr[1];
+}
+
+// 14 resident CTAs per SM asked of ptxas (72 registers, no spills; 16 would rematerialise pixel coordinates
+// inside the inner loop).
+template <int D, bool CULL, bool STATS>
+__global__ void __launch_bounds__(Shape<4>::kThreads, 14) raster_fwd_ws_kernel(const RasterParams p) {
+    using S = Shape<4>;
+    __shared__ WarpStream wss[S::kWarps];
+    StatCounters<STATS> st;
+    const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStream& ws = wss[warp];
+    const int ox = tx * kTile, oy = ty * kTile + warp * S::kFootH;
+    const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);
+    const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
+    const f32x2 npy2 = pk2(-py0, -(py0 + 4.0f));
+
+    const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
+    const int range_start = p.offsets[tile_id];
+    const int range_end = (tile_id == (int64_t)p.C * p.tile_h * p.tile_w - 1) ? (int)p.n_isects : p.offsets[tile_id + 1];
+    const SubRects<2> sr = make_blocks8(ox, oy, p.width, p.height);
+
+    f32x2 T2[2], acc2[2][D];
+    int32_t last[2][2];
+    float thr[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        T2[a] = pk2(1.0f, 1.0f);
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc2[a][d] = pk2(0.0f, 0.0f);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            last[a][b] = 0;
+            thr[a][b] = ((i0 + b * 4 < p.height) && (j0 + a * 8 < p.width)) ? kAlphaThreshold : 2.0f;
+        }
+    }
+    int alive = sr.present;  // warp-uniform: 8x8 blocks that still have a live pixel
+
+    // batch i covers sorted indices [range_start + 32 i, + 32), lane l owns range_start + 32 i + l
+    const int n_batches = (range_end - range_start + 31) / 32;
+    int e_cur = range_start + lane;
+    int g_cur = e_cur < range_end ? p.flatten_ids[e_cur] : 0;
+    stream_fetch<D>(p, ws, 0, lane, e_cur < range_end, g_cur);
+    int g_nxt = (e_cur + 32 < range_end) ? p.flatten_ids[e_cur + 32] : 0;
+
+    for (int i = 0; i < n_batches && alive; ++i, e_cur += 32) {
+        const int buf = i & 1;
+        stream_fetch<D>(p, ws, buf ^ 1, lane, e_cur + 32 < range_end, g_nxt);       // batch i+1: geom + colour
+        const int g_n2 = (e_cur + 64 < range_end) ? p.flatten_ids[e_cur + 64] : 0;  // batch i+2: id
+        cp_async_wait<1>();                                                         // batch i has landed
+        const bool have = e_cur < range_end;
+        int mask = 0;
+        float4 A = make_float4(0, 0, 0, 0), B = make_float4(0, 0, 0, 0);
+        st.add(0, have ? 1 : 0);
+        if (have) {
+            const float4 ga = ws.ra[buf][lane];  // mx, my, opacity, depth
+            const float4 gb = ws.rb[buf][lane];  // conic a, b, c
+            const float lo = __log2f(ga.z);
+            A = make_float4(ga.x, ga.y, lo, __int_as_float(e_cur));
+            B = make_float4(-0.5f * kLog2e * gb.x, -kLog2e * gb.y, -0.5f * kLog2e * gb.z, __int_as_float(g_cur));
+            const float tau2 = lo + kLog2_255;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                bool hit = (alive >> k) & 1;
+                if (CULL && hit) hit = ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, tau2, sr.x0[k], sr.y0[k], sr.x1[k], sr.y1[k]);
+                if (hit) mask |= 1 << k;
+            }
+        }
+        st.add(1, mask ? 1 : 0);
+        const uint32_t m = __ballot_sync(0xffffffffu, mask != 0);  // also: every lane is done with the previous queue
+        if (mask) {
+            const int pos = __popc(m & ((1u << lane) - 1u));
+            float4 c = ws.rc[buf][lane];
+            if (D < 4) c.w = 0.0f;
+            if (D < 3) c.y = c.z = 0.0f;
+            ws.qa[pos] = A;
+            ws.qb[pos] = B;
+            ws.qc[pos] = c;
+            ws.qm[pos] = mask;
+        }
+        __syncwarp();
+        const int nq = __popc(m);
+        for (int q = 0; q < nq; ++q) {
+            const float4 A = ws.qa[q], B = ws.qb[q], Cc = ws.qc[q];
+            const int mask = ws.qm[q];
+            if (lane == 0) st.add(2, __popc(mask));
+            const f32x2 dy2 = add2(bc2(A.y), npy2);
+            const f32x2 t2 = mul2(bc2(B.y), dy2);
+            const f32x2 cy2 = fma2(mul2(bc2(B.z), dy2), dy2, bc2(A.z));
+            if (mask == 3) {  // one basic block: the two independent blocks interleave
+                fwd_pk_block<D, STATS>(0, A, B, Cc, px0, dy2, t2, cy2, T2[0], acc2[0], last[0], thr[0], st);
+                fwd_pk_block<D, STATS>(1, A, B, Cc, px0, dy2, t2, cy2, T2[1], acc2[1], last[1], thr[1], st);
+            } else if (mask == 1) {
+                fwd_pk_block<D, STATS>(0, A, B, Cc, px0, dy2, t2, cy2, T2[0], acc2[0], last[0], thr[0], st);
+            } else {
+                fwd_pk_block<D, STATS>(1, A, B, Cc, px0, dy2, t2, cy2, T2[1], acc2[1], last[1], thr[1], st);
+            }
+        }
+        alive = (__any_sync(0xffffffffu, fminf(thr[0][0], thr[0][1]) < 1.0f) ? 1 : 0) | (__any_sync(0xffffffffu, fminf(thr[1][0], thr[1][1]) < 1.0f) ? 2 : 0);
+        g_cur = g_nxt;
+        g_nxt = g_n2;
+    }
+    cp_async_wait<0>();
+
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int i = i0 + b * 4, j = j0 + a * 8;
+            if (i < p.height && j < p.width) {
+                const int64_t pix = ((int64_t)cam * p.height + i) * p.width + j;
+                const float T = b ? hi2(T2[a]) : lo2(T2[a]);
+                const float alpha_out = 1.0f - T;
+                float out[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    out[d] = (b ? hi2(acc2[a][d]) : lo2(acc2[a][d])) + (p.backgrounds ? T * p.backgrounds[cam * D + d] : 0.0f);
+                if (p.normalize_last) out[D - 1] = out[D - 1] / fmaxf(alpha_out, 1e-10f);
+                if (D == 4) {
+                    reinterpret_cast<float4*>(p.render)[pix] = make_float4(out[0], out[1], out[2], out[3]);
+                } else {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) p.render[pix * D + d] = out[d];
+                }
+                p.alphas[pix] = alpha_out;
+                p.last_ids[pix] = last[a][b];
+            }
         }
     }
     st.flush(p.counters);
@@ -750,17 +943,9 @@ __device__ __forceinline__ void bwd_pk_prologue(const RasterParams& p, int cam, 
     }
 }
 
-// Warp streams.  Each warp walks the tile's sorted range on its own, 32 entries per batch, back to front
-// from ITS OWN last contributing index.  The gather (id -> 32-B geom + colour) of batch i+1 is in flight as
-// cp.async into a double-buffered, lane-private landing zone while batch i is composited, and the ids of
-// batch i+2 are loaded one batch ahead of that, so no global-load latency and no block barrier sits on the
-// critical path (ncu on a CTA-staged version of this kernel: long_scoreboard + barrier = 20 % of the stall
-// cycles).  Every lane culls its own entry directly against the warp's two 8x8 blocks.
-struct WarpStream {
-    float4 ra[2][32], rb[2][32], rc[2][32];  // landing zone: geom (2 x 16 B) + colour of the lane's entry, two batches
-    float4 qa[32], qb[32], qc[32];           // queue of the batch being composited (see Staging)
-    int qm[32];
-    float4 red[6][36];                       // gradient transpose: [entry parity * 3 + slot group][lane, 8 + 1 pad]
+// backward only -- gradient transpose: [entry parity * 3 + slot group][lane, 8 + 1 pad]
+struct GradTranspose {
+    float4 v[6][36];
 };
 
 // Position of lane l in a `red` row: every 8 lanes are followed by one float4 of padding, so that the eight
@@ -768,14 +953,14 @@ struct WarpStream {
 __device__ __forceinline__ int red_pos(int l) { return (l >> 3) * 9 + (l & 7); }
 
 // Cross-lane sums of the gradient slots of queue entries q0 (even) .. q0+count-1 (count <= 2), whose
-// per-lane values sit in ws.red.  Instead of a shuffle butterfly per Gaussian (16 SHFL + 22 FSEL + 16 FADD),
+// per-lane values sit in `red`.  Instead of a shuffle butterfly per Gaussian (16 SHFL + 22 FSEL + 16 FADD),
 // the values are transposed through shared memory: lane = (entry, slot group, quarter) sums 8 lanes' float4
 // with FADD2 and adds its quarter-sum with ONE vector red.global.add.v4.f32.
-__device__ __forceinline__ void reduce_entries(const RasterParams& p, WarpStream& ws, int q0, int count, int lane) {
+__device__ __forceinline__ void reduce_entries(const RasterParams& p, const WarpStream& ws, const GradTranspose& red, int q0, int count, int lane) {
     const int item = lane >> 2, quarter = lane & 3;  // item = entry parity * 3 + slot group
     const int qq = item >= 3 ? 1 : 0, sg = item - qq * 3;
     if (lane < 24 && qq < count) {
-        const float4* src = &ws.red[item][quarter * 9];
+        const float4* src = &red.v[item][quarter * 9];
         f32x2 s01 = pk2(src[0].x, src[0].y), s23 = pk2(src[0].z, src[0].w);
 #pragma unroll
         for (int j = 1; j < 8; ++j) {
@@ -799,30 +984,17 @@ __device__ __forceinline__ void reduce_entries(const RasterParams& p, WarpStream
     }
 }
 
-template <int D>
-__device__ __forceinline__ void stream_fetch(const RasterParams& p, WarpStream& ws, int buf, int lane, bool have, int g) {
-    if (have) {
-        cp_async16(&ws.ra[buf][lane], p.geom + (int64_t)g * 2);
-        cp_async16(&ws.rb[buf][lane], p.geom + (int64_t)g * 2 + 1);
-        if (D == 4) {
-            cp_async16(&ws.rc[buf][lane], p.colors + (int64_t)g * 4);
-        } else {
-#pragma unroll
-            for (int d = 0; d < D; ++d) cp_async4(reinterpret_cast<float*>(&ws.rc[buf][lane]) + d, p.colors + (int64_t)g * D + d);
-        }
-    }
-    cp_async_commit();
-}
-
 // 12 resident CTAs per SM asked of ptxas (80 registers): occupancy is worth more than the 4 bytes it spills.
 template <int D, bool CULL, bool STATS>
 __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(const RasterParams p) {
     using S = Shape<4>;
     __shared__ WarpStream wss[S::kWarps];
+    __shared__ GradTranspose reds[S::kWarps];
     StatCounters<STATS> st;
     const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStream& ws = wss[warp];
+    GradTranspose& red = reds[warp];
     const int ox = tx * kTile, oy = ty * kTile + warp * S::kFootH;
     const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);
     const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
@@ -904,15 +1076,18 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(c
             } else {
                 any_valid = bwd_pk_block<D, true, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
             }
-            if (STATS && lane == 0 && __any_sync(0xffffffffu, any_valid)) st.add(5, 1);
+            if (STATS) {  // every lane votes
+                const bool any = __any_sync(0xffffffffu, any_valid);
+                if (lane == 0 && any) st.add(5, 1);
+            }
             float vs[12];
 #pragma unroll
             for (int s = 0; s < 12; ++s) vs[s] = lo2(v[s]) + hi2(v[s]);
 #pragma unroll
-            for (int sg = 0; sg < 3; ++sg) ws.red[(q & 1) * 3 + sg][rpos] = make_float4(vs[4 * sg], vs[4 * sg + 1], vs[4 * sg + 2], vs[4 * sg + 3]);
+            for (int sg = 0; sg < 3; ++sg) red.v[(q & 1) * 3 + sg][rpos] = make_float4(vs[4 * sg], vs[4 * sg + 1], vs[4 * sg + 2], vs[4 * sg + 3]);
             if ((q & 1) || q == nq - 1) {
                 __syncwarp();
-                reduce_entries(p, ws, q & ~1, (q & 1) + 1, lane);
+                reduce_entries(p, ws, red, q & ~1, (q & 1) + 1, lane);
                 __syncwarp();
             }
         }
@@ -958,7 +1133,7 @@ __global__ void unpack_grads_kernel(int64_t CN, int D, const float4* __restrict_
 // test / instrumentation hooks (process-global; not part of the reference surface)
 static int g_raster_cull = 1;                           // 0 disables the culling (identical results, slower)
 static unsigned long long* g_raster_counters = nullptr;  // device uint64[6] -> STATS kernels
-static int g_px_fwd = 1, g_px_bwd = 4;                   // pixels per lane
+static int g_px_fwd = 4, g_px_bwd = 4;                   // pixels per lane
 static int g_raster_packed = 1;                          // f32x2 kernels where they exist (backward, 4 px/lane)
 
 template <int D, int PX, bool BWD>
@@ -966,7 +1141,15 @@ static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
     dim3 grid(p.tile_w, p.tile_h, p.C);
     constexpr int T = Shape<PX>::kThreads;
     const bool cull = g_raster_cull != 0, stats = p.counters != nullptr;
-    if (!BWD) {
+    if (!BWD && PX == 4 && g_raster_packed) {
+        if (stats) {
+            if (cull) raster_fwd_ws_kernel<D, true, true><<<grid, T, 0, stream>>>(p);
+            else raster_fwd_ws_kernel<D, false, true><<<grid, T, 0, stream>>>(p);
+        } else {
+            if (cull) raster_fwd_ws_kernel<D, true, false><<<grid, T, 0, stream>>>(p);
+            else raster_fwd_ws_kernel<D, false, false><<<grid, T, 0, stream>>>(p);
+        }
+    } else if (!BWD) {
         if (stats) {
             if (cull) raster_fwd_kernel<D, PX, true, true><<<grid, T, 0, stream>>>(p);
             else raster_fwd_kernel<D, PX, false, true><<<grid, T, 0, stream>>>(p);

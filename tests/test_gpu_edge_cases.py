@@ -112,7 +112,7 @@ def test_culling_is_exact_on_thin_tilted_splats(cuda):
         ref = outs["cull"][2][k]
         noise = float((outs["cull_again"][2][k] - ref).norm() / (ref.norm() + 1e-30))
         diff = float((outs["nocull"][2][k] - ref).norm() / (ref.norm() + 1e-30))
-        assert diff <= 10.0 * noise + 1e-5, (k, diff, noise)
+        assert diff <= 10.0 * noise + 1e-4, (k, diff, noise)
     outs[True] = outs["cull"]
     # and against the oracle
     ro, ao, _ = oracle.rasterization(**a, width=W, height=H, render_mode="RGB+ED", sh_degree=None)
@@ -120,21 +120,36 @@ def test_culling_is_exact_on_thin_tilted_splats(cuda):
 
 
 def test_pixels_per_lane_variants_agree(cuda):
+    """Scalar compositor kernels with 1, 2 or 4 pixels per lane: bitwise-identical forward.  The default packed
+    (two-wide fp32) kernels round log2(alpha) once more (add, then fma), so they agree to float tolerance."""
     s = scene_s0(N=8000, C=1, size=160).to(cuda)
     a = scene_args(s)
-    ref = None
-    for px_f, px_b in ((1, 1), (2, 2), (4, 4)):
-        ops.set_raster_px(px_f, px_b)
+
+    def run():
         leaves = {k: a[k].clone().requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "colors")}
         r, al, _ = rasterization(**leaves, viewmats=a["viewmats"], Ks=a["Ks"], width=s.width, height=s.height, render_mode="RGB+ED", sh_degree=3)
         (r * r).sum().backward()
-        cur = (r.detach(), al.detach(), leaves["means"].grad)
-        if ref is None:
-            ref = cur
-        else:
-            assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1])  # forward is bitwise identical
-            assert_close_frac(cur[2], ref[2], 1e-3, 1e-5 * float(ref[2].abs().mean()), 1e-3, "means grad")
-    ops.set_raster_px(1, 4)
+        return r.detach(), al.detach(), leaves["means"].grad
+
+    try:
+        ops.set_raster_packed(False)
+        ref = None
+        for px_f, px_b in ((1, 1), (2, 2), (4, 4)):
+            ops.set_raster_px(px_f, px_b)
+            cur = run()
+            if ref is None:
+                ref = cur
+            else:
+                assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1])  # forward is bitwise identical
+                assert_close_frac(cur[2], ref[2], 1e-3, 1e-5 * float(ref[2].abs().mean()), 1e-3, "means grad")
+        ops.set_raster_packed(True)
+        cur = run()
+        assert_close_frac(cur[0], ref[0], 1e-5, 1e-5, 1e-3, "packed render")
+        assert_close_frac(cur[1], ref[1], 1e-5, 1e-5, 1e-3, "packed alpha")
+        assert_close_frac(cur[2], ref[2], 1e-3, 1e-5 * float(ref[2].abs().mean()), 2e-3, "packed means grad")
+    finally:
+        ops.set_raster_packed(True)
+        ops.set_raster_px(4, 4)
 
 
 def test_non_contiguous_and_misaligned_inputs(cuda):

@@ -93,6 +93,30 @@ def test_fused_step_with_ssim_matches_oracle(cuda, size):
         assert_close_frac(out.grads[k], lo[k].grad, 1e-3, 1e-3 * scale, 5e-3, f"v_{k}")
 
 
+@pytest.mark.timeout(120)
+def test_pair_counters_of_instrumented_kernels(cuda):
+    """bench.py's roofline uses the work counters of the instrumented (STATS) compositor kernels: they must run
+    (a divergent warp vote once hung them), leave the results alone and be consistent with the oracle's count."""
+    s = scene_s0(N=4000, C=2, size=120)
+    bg = torch.tensor([0.3, 0.1, 0.6])
+    g = s.to(cuda)
+    fs = FusedSplatStep(cuda)
+    out = fs.step(g.means, g.quats, g.scales, g.opacities, g.sh, g.viewmats, g.Ks, g.width, g.height, 3, g.gt_rgb, g.gt_depth, bg.to(cuda))
+    before = out.packed_grads.clone()
+    c = fs.count_pairs()
+    assert torch.equal(out.packed_grads, before)
+    for w in ("fwd", "bwd"):
+        assert c[f"{w}_entries_loaded"] >= c[f"{w}_entries_staged"] > 0
+        assert c[f"{w}_pairs_evaluated"] >= c[f"{w}_pairs_contributing"] > 0
+    # forward and backward composite the same (pixel, Gaussian) pairs, up to threshold flips
+    assert abs(c["fwd_pairs_contributing"] - c["bwd_pairs_contributing"]) <= 2e-3 * c["fwd_pairs_contributing"]
+    # the oracle's count: pairs with alpha >= 1/255 in front of each pixel's last composited Gaussian
+    ro, ao, io = oracle.rasterization(s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, sh_degree=3,
+                                      render_mode="RGB+ED")
+    n_o = oracle.count_composited_pairs(io["means2d"], io["conics"], io["opacities"], s.width, s.height, 16, io["isect_offsets"], io["flatten_ids"])
+    assert abs(c["fwd_pairs_contributing"] - n_o) <= 2e-3 * n_o, (c["fwd_pairs_contributing"], n_o)
+
+
 def test_view_sharding_equals_single_rank(cuda):
     """2 'ranks' x 1 view with grad_scale = 1/2, summed (what the all-reduce does) == 1 rank x 2 views."""
     s = scene_s0(N=3000, C=2, size=96).to(cuda)
