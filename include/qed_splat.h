@@ -141,15 +141,24 @@ int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* k
  *            sort on the camera|tile bits only, then isect_ids = key << 32 | bits(depth) and the per-tile
  *            ranges (isect_ids and/or isect_offsets may be NULL to skip them; the compositor needs only
  *            flatten_ids + isect_offsets).
- * `prepare_workspace` must be the buffer qed_isect_prepare filled for the same (C, N). */
+ * `prepare_workspace` must be the buffer qed_isect_prepare filled for the same (C, N).
+ *
+ * geom == NULL: gsplat's lists, bit for bit (every tile of each Gaussian's 3-sigma bounding box; n_isects entries).
+ * geom != NULL (the packed [C*N,8] records of qed_project_fwd): EXACT tile lists for the fused step -- every
+ *   candidate (Gaussian, tile) is tested with the compositor's own conservative alpha >= 1/255 ellipse test and
+ *   dropped if it cannot touch a pixel centre of the tile (about half of them; no pixel changes).  The number of
+ *   survivors stays on the device: it is written to n_exact_dev[1] (int64), flatten_ids / isect_ids are filled for
+ *   that many entries (buffers sized for n_isects), and isect_offsets must have C*tile_height*tile_width + 1
+ *   elements, the last one receiving the end of the last range (pass offsets_has_end = 1 to qed_raster_fwd). */
 size_t qed_isect_prepare_workspace_bytes(int64_t CN);
 int qed_isect_prepare(int C, int N, const float* depths, const int32_t* tiles_per_gauss, void* workspace,
                       size_t workspace_bytes, int64_t* counts_dev, int64_t* counts_host_pinned, qed_stream_t stream);
 size_t qed_isect_fill_workspace_bytes(int64_t n_isects);
 int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects, const float* means2d, const int32_t* radii,
-                   const float* depths, int tile_size, int tile_width, int tile_height, const void* prepare_workspace,
-                   void* workspace, size_t workspace_bytes, int64_t* isect_ids, int32_t* flatten_ids,
-                   int32_t* isect_offsets, qed_stream_t stream);
+                   const float* depths, const float* geom, int image_width, int image_height, int tile_size, int tile_width,
+                   int tile_height, const void* prepare_workspace, void* workspace, size_t workspace_bytes,
+                   int64_t* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets, int64_t* n_exact_dev,
+                   qed_stream_t stream);
 
 /* isect_offsets[C*tile_height*tile_width] i32: first sorted index of each (camera,tile); empty tiles get
  * the start of the next non-empty one; tiles after the last entry get n_isects. */
@@ -164,10 +173,12 @@ int qed_tile_ranges(int64_t n_isects, const int64_t* isect_ids_sorted, int C, in
  *  outputs: render[C,H,W,D], alphas[C,H,W], last_ids[C,H,W] i32 (index in sorted list of the last
  *  composited Gaussian; 0 if none).  For normalize_last the un-normalised last channel is
  *  recoverable as render*max(alpha,1e-10) (the backward does so).
+ *  offsets_has_end != 0 : isect_offsets has one more element holding the end of the last range (exact tile
+ *  lists of qed_isect_fill, whose entry count lives on the device); n_isects is then only an upper bound.
  */
 int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
                    const float* backgrounds, int width, int height, int tile_size, int tile_width,
-                   int tile_height, const int32_t* isect_offsets, const int32_t* flatten_ids,
+                   int tile_height, const int32_t* isect_offsets, int offsets_has_end, const int32_t* flatten_ids,
                    int normalize_last, float* render, float* alphas, int32_t* last_ids, qed_stream_t stream);
 
 /* (d) compositing backward.

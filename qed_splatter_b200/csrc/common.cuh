@@ -40,6 +40,59 @@ __device__ __forceinline__ float mad3(float a, float b, float c, float d, float 
     return add(add(mul(a, b), mul(c, d)), mul(e, f));
 }
 
+// ---- log2-domain alpha test shared by the compositor (raster.cu) and the exact tile lists (isect.cu) ----
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLog2_255 = 7.99435343685886f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Conservative test in the log2 domain: Q(d) = A dx^2 + B dx dy + C dy^2 (positive definite,
+// = log2(e) * sigma), d = mean - pixel centre.  A pixel can only be touched if Q <= tau2 = lo + log2(255).
+// Returns false only if the minimum of Q over the rectangle [x0,x1]x[y0,y1] exceeds tau2 by a margin.
+__device__ __forceinline__ bool ellipse_hits_rect(float mx, float my, float A, float B, float C, float tau2, float x0, float y0,
+                                                  float x1, float y1) {
+    if (!(tau2 >= 0.0f)) return false;  // opacity < 1/255 can never pass the alpha test
+    const float dxl = mx - x1, dxh = mx - x0;  // dx in [dxl, dxh]
+    const float dyl = my - y1, dyh = my - y0;
+    if (dxl <= 0.0f && dxh >= 0.0f && dyl <= 0.0f && dyh >= 0.0f) return true;  // centre inside
+    // convex quadratic, centre outside: the minimum over the rectangle lies on an edge
+    float best = 3.0e38f, mag = 0.0f;
+    const float hC = 0.5f * rcp_approx(C), hA = 0.5f * rcp_approx(A);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {  // edges dx = const
+        const float dx = e ? dxh : dxl;
+        const float dy = fminf(fmaxf(-B * dx * hC, dyl), dyh);
+        const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
+        const float s = t0 + t1 + t2;
+        if (s < best) {
+            best = s;
+            mag = t0 + t1 + fabsf(t2);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {  // edges dy = const
+        const float dy = e ? dyh : dyl;
+        const float dx = fminf(fmaxf(-B * dy * hA, dxl), dxh);
+        const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
+        const float s = t0 + t1 + t2;
+        if (s < best) {
+            best = s;
+            mag = t0 + t1 + fabsf(t2);
+        }
+    }
+    // margin: 1 % + absolute + rounding of the three terms (cancellation for thin, tilted ellipses)
+    return !(best > tau2 * 1.01f + 0.03f + 2e-5f * mag);
+}
+
 // ---- packed float pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot, two IEEE fp32 results) -------------
 // ptxas folds bc2(s) into a scalar-broadcast operand (`R.F32`), neg2/abs2 into operand modifiers and pk2 of
 // two freshly produced scalars into adjacent registers, so these helpers cost no extra instructions.

@@ -270,27 +270,46 @@ __global__ void emit_boundaries_kernel(int64_t n_vis, const int64_t* __restrict_
     for (int64_t b = (start + kEmitTile - 1) / kEmitTile; b * kEmitTile < end; ++b) first_j[b] = (int32_t)j;
 }
 
+//
+// EXACT = exact tile lists (the fused pipeline; gsplat's lists hold every tile of the 3-sigma bounding box):
+// every candidate (Gaussian, tile) entry is tested with the compositor's own conservative alpha >= 1/255
+// ellipse test against the tile's pixel-centre rectangle and only survivors are written -- compacted in
+// order at the START of the block's own kEmitTile-slot segment, with the count in seg_counts[block].  There
+// is no global compaction (a decoupled look-back across the ~900 resident blocks cost more than the emit
+// itself): the first pass of the tile sort reads the segments (SegCounts) and scatters densely.  About half
+// of the candidates go (S1: 47 %), which halves the tile sort and the compositor's gather work and changes
+// no pixel: a removed entry cannot pass the alpha test anywhere in its tile.
+struct ExactEmit {
+    const float4* geom;    // [C*N][2]: {mx, my, opacity, depth | conic a, b, c, -}
+    int32_t* seg_counts;   // survivors per block
+    unsigned long long* n_out;  // device scalar: total number of survivors (zeroed by the caller)
+    int width, height;
+};
+
+template <bool EXACT>
 __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis, int64_t n_isects, int N, const int32_t* __restrict__ sorted_vals,
                                                                   const int64_t* __restrict__ cum2, const int32_t* __restrict__ first_j,
                                                                   const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
                                                                   float tile_size, int tile_w, int tile_h, int tile_n_bits,
-                                                                  uint32_t* __restrict__ tkeys, int32_t* __restrict__ tvals) {
+                                                                  uint32_t* __restrict__ tkeys, int32_t* __restrict__ tvals, ExactEmit ex) {
     // per staged Gaussian: the part [lo, hi) of its entries that falls into this block (block-relative), the
     // offset k0 of entry `lo` inside the Gaussian's own tile list, its box and its flat index
     __shared__ int16_t s_lo[kEmitTile + 1], s_hi[kEmitTile + 1];
     __shared__ int32_t s_k0[kEmitTile + 1], s_first[kEmitTile + 1], s_idx[kEmitTile + 1];
     __shared__ int16_t s_bw[kEmitTile + 1], s_large[kEmitTile + 1];  // box width in tiles (<= 32767), staged index
-    __shared__ uint32_t s_okey[kEmitTile];  // the block's output, staged so the global writes are fully coalesced
-    __shared__ int32_t s_oval[kEmitTile];
+    __shared__ __align__(16) uint32_t s_okey[kEmitTile];  // the block's output, staged so the global writes are fully coalesced
+    __shared__ __align__(16) int32_t s_oval[kEmitTile];
     __shared__ int s_nlarge;
-    const int64_t e0 = (int64_t)blockIdx.x * kEmitTile;
+    __shared__ int s_wsum[kEmitThreads / 32];
+    const uint32_t vb = blockIdx.x;
+    const int64_t e0 = (int64_t)vb * kEmitTile;
     const int64_t e1 = min(e0 + kEmitTile, n_isects);
-    const int64_t j0 = first_j[blockIdx.x];
+    const int64_t j0 = first_j[vb];
     int64_t j1;  // Gaussian that owns entry e1 - 1
     if (e1 >= n_isects) {
         j1 = n_vis - 1;
     } else {
-        const int64_t jn = first_j[blockIdx.x + 1];  // owns entry e1
+        const int64_t jn = first_j[vb + 1];  // owns entry e1
         j1 = (jn > 0 && cum2[jn - 1] == e1) ? jn - 1 : jn;  // jn starts exactly at e1 -> the previous one owns e1-1
     }
     const int G = (int)(j1 - j0) + 1;  // every Gaussian has >= 1 entry, so G <= kEmitTile
@@ -344,17 +363,101 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
         }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < (int)(e1 - e0); t += kEmitThreads) {
+    if (!EXACT) {
+        for (int t = threadIdx.x; t < (int)(e1 - e0); t += kEmitThreads) {
+            tkeys[e0 + t] = s_okey[t];
+            tvals[e0 + t] = s_oval[t];
+        }
+        return;
+    }
+    // ---- exact lists: test, compact in order, look back for the block offset, write ----
+    constexpr int kPer = kEmitTile / kEmitThreads;  // consecutive entries per thread
+    const int cnt = (int)(e1 - e0);
+    const uint32_t tile_mask = (1u << tile_n_bits) - 1u;
+    static_assert(kPer == 4, "vector loads of the staged entries");
+    uint32_t key[kPer];
+    int32_t val[kPer];
+    {
+        const uint4 kk = reinterpret_cast<const uint4*>(s_okey)[threadIdx.x];
+        const int4 vv = reinterpret_cast<const int4*>(s_oval)[threadIdx.x];
+        key[0] = kk.x, key[1] = kk.y, key[2] = kk.z, key[3] = kk.w;
+        val[0] = vv.x, val[1] = vv.y, val[2] = vv.z, val[3] = vv.w;
+    }
+    const float inv_tile_w = 1.0f / (float)tile_w;
+    int keep = 0, mine = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int t = threadIdx.x * kPer + k;
+        if (t < cnt) {
+            const int tile = (int)(key[k] & tile_mask);
+            int ty = (int)(((float)tile + 0.5f) * inv_tile_w);  // exact below 2^22 tiles; corrected below anyway
+            int tx = tile - ty * tile_w;
+            if (tx < 0) {
+                --ty;
+                tx += tile_w;
+            } else if (tx >= tile_w) {
+                ++ty;
+                tx -= tile_w;
+            }
+            const float4 ga = ex.geom[(int64_t)val[k] * 2], gb = ex.geom[(int64_t)val[k] * 2 + 1];
+            const float x0 = (float)(tx * (int)tile_size) + 0.5f, y0 = (float)(ty * (int)tile_size) + 0.5f;
+            const float x1 = (float)min(tx * (int)tile_size + (int)tile_size - 1, ex.width - 1) + 0.5f;
+            const float y1 = (float)min(ty * (int)tile_size + (int)tile_size - 1, ex.height - 1) + 0.5f;
+            const bool hit = ellipse_hits_rect(ga.x, ga.y, 0.5f * kLog2e * gb.x, kLog2e * gb.y, 0.5f * kLog2e * gb.z,
+                                               __log2f(ga.z) + kLog2_255, x0, y0, x1, y1);
+            if (hit) {
+                keep |= 1 << k;
+                ++mine;
+            }
+        }
+    }
+    // exclusive scan of the per-thread counts over the block
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();  // also: everyone has read its entries from s_okey / s_oval
+    int before = inc - mine, total = 0;
+#pragma unroll
+    for (int w = 0; w < kEmitThreads / 32; ++w) {
+        if (w < warp) before += s_wsum[w];
+        total += s_wsum[w];
+    }
+    if (threadIdx.x == 0) {
+        ex.seg_counts[vb] = total;
+        if (total) atomicAdd(ex.n_out, (unsigned long long)total);
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        if ((keep >> k) & 1) {
+            s_okey[before] = key[k];
+            s_oval[before] = val[k];
+            ++before;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < total; t += kEmitThreads) {
         tkeys[e0 + t] = s_okey[t];
         tvals[e0 + t] = s_oval[t];
     }
 }
 
 // isect_ids = key << 32 | bits(depth), fused with the per-tile ranges (same rule as tile_ranges_kernel)
-__global__ void compose_ids_ranges_kernel(int64_t n, const uint32_t* __restrict__ tkeys, const int32_t* __restrict__ flat,
-                                          const float* __restrict__ depths, int C, int n_tiles, int tile_n_bits,
-                                          int64_t* __restrict__ isect_ids, int32_t* __restrict__ offsets) {
+// n_dev (exact lists): the number of entries lives on the device and offsets gets one more element, the end
+// of the last range, so that the compositor needs no host-side count.
+__global__ void compose_ids_ranges_kernel(int64_t n_host, const int64_t* __restrict__ n_dev, const uint32_t* __restrict__ tkeys,
+                                          const int32_t* __restrict__ flat, const float* __restrict__ depths, int C, int n_tiles,
+                                          int tile_n_bits, int64_t* __restrict__ isect_ids, int32_t* __restrict__ offsets) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = n_dev ? *n_dev : n_host;
+    if (n_dev && offsets && i == 0) {
+        offsets[(int64_t)C * n_tiles] = (int32_t)n;
+        if (n == 0)
+            for (int64_t t = 0; t < (int64_t)C * n_tiles; ++t) offsets[t] = 0;
+    }
     if (i >= n) return;
     const uint32_t key = tkeys[i];
     if (isect_ids) {
@@ -435,20 +538,26 @@ extern "C" int qed_isect_prepare(int C, int N, const float* depths, const int32_
 
 extern "C" size_t qed_isect_fill_workspace_bytes(int64_t n_isects) {
     if (n_isects <= 0) return 256;
-    return 5 * align_up((size_t)n_isects * 4, 256) + radix_hist_bytes(n_isects) +
-           align_up((size_t)((n_isects + kEmitTile - 1) / kEmitTile + 1) * 4, 256);
+    const size_t nb = (size_t)((n_isects + kEmitTile - 1) / kEmitTile + 1);
+    return 5 * align_up((size_t)n_isects * 4, 256) + radix_hist_bytes(n_isects) + align_up(nb * 4, 256) + align_up(nb * 8 + 8, 256);
 }
 
 extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects, const float* means2d, const int32_t* radii,
-                              const float* depths, int tile_size, int tile_width, int tile_height, const void* prepare_workspace,
-                              void* workspace, size_t workspace_bytes, int64_t* isect_ids, int32_t* flatten_ids,
-                              int32_t* isect_offsets, qed_stream_t stream_) {
+                              const float* depths, const float* geom, int image_width, int image_height, int tile_size, int tile_width,
+                              int tile_height, const void* prepare_workspace, void* workspace, size_t workspace_bytes,
+                              int64_t* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets, int64_t* n_exact_dev,
+                              qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (C < 0 || N < 0 || n_visible < 0 || n_isects < 0 || tile_size <= 0) return QED_ERR_BAD_ARG;
     const int64_t CN = (int64_t)C * N;
     const int n_tiles = tile_width * tile_height;
+    const bool exact = geom != nullptr;  // exact tile lists: offsets has C * n_tiles + 1 elements, the count stays on the device
+    if (exact && (!n_exact_dev || !isect_offsets || image_width <= 0 || image_height <= 0)) return QED_ERR_BAD_ARG;
+    if (exact && (reinterpret_cast<uintptr_t>(geom) & 15)) return QED_ERR_BAD_ARG;
     if (n_isects == 0 || CN == 0) {
-        if (isect_offsets && (int64_t)C * n_tiles > 0) QED_CUDA_TRY(cudaMemsetAsync(isect_offsets, 0, (size_t)C * n_tiles * 4, stream));
+        if (isect_offsets && (int64_t)C * n_tiles > 0)
+            QED_CUDA_TRY(cudaMemsetAsync(isect_offsets, 0, ((size_t)C * n_tiles + (exact ? 1 : 0)) * 4, stream));
+        if (exact) QED_CUDA_TRY(cudaMemsetAsync(n_exact_dev, 0, 8, stream));
         return QED_OK;
     }
     if (n_isects > 0x7fffffffLL) return QED_ERR_UNSUPPORTED;
@@ -469,17 +578,39 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     int32_t* v0 = reinterpret_cast<int32_t*>(ws + 3 * seg);
     int32_t* v2 = reinterpret_cast<int32_t*>(ws + 4 * seg);
     void* hist = ws + 5 * seg;
+    const size_t nb = (size_t)((n_isects + kEmitTile - 1) / kEmitTile);
     int32_t* first_j = reinterpret_cast<int32_t*>(ws + 5 * seg + radix_hist_bytes(n_isects));
+    int32_t* seg_counts = reinterpret_cast<int32_t*>(ws + 5 * seg + radix_hist_bytes(n_isects) + align_up((nb + 1) * 4, 256));
     emit_boundaries_kernel<<<(unsigned)((n_visible + 255) / 256), 256, 0, stream>>>(n_visible, cum2, first_j);
     QED_LAUNCH_CHECK();
-    emit_sorted_kernel<<<(unsigned)((n_isects + kEmitTile - 1) / kEmitTile), kEmitThreads, 0, stream>>>(
-        n_visible, n_isects, N, sorted_vals, cum2, first_j, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width,
-        tile_height, tile_n_bits, k0, v0);
+    ExactEmit ex{};
+    if (exact) {
+        QED_CUDA_TRY(cudaMemsetAsync(n_exact_dev, 0, 8, stream));
+        ex.geom = reinterpret_cast<const float4*>(geom);
+        ex.seg_counts = seg_counts;
+        ex.n_out = reinterpret_cast<unsigned long long*>(n_exact_dev);
+        ex.width = image_width;
+        ex.height = image_height;
+        emit_sorted_kernel<true><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, N, sorted_vals, cum2, first_j,
+                                                                           reinterpret_cast<const float2*>(means2d), radii, (float)tile_size,
+                                                                           tile_width, tile_height, tile_n_bits, k0, v0, ex);
+    } else {
+        emit_sorted_kernel<false><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, N, sorted_vals, cum2, first_j,
+                                                                            reinterpret_cast<const float2*>(means2d), radii, (float)tile_size,
+                                                                            tile_width, tile_height, tile_n_bits, k0, v0, ex);
+    }
     QED_LAUNCH_CHECK();
-    int rc = radix_sort_pairs<uint32_t>(n_isects, nullptr, k0, v0, k1, flatten_ids, k2, v2, hist, tile_n_bits + cam_bits, stream);
+    const int64_t* n_dev = exact ? n_exact_dev : nullptr;
+    SegCounts sc;
+    if (exact) {
+        sc.counts = seg_counts;
+        sc.shift = 10;
+        static_assert(kEmitTile == 1 << 10, "segment size of the exact emit");
+    }
+    int rc = radix_sort_pairs<uint32_t>(n_isects, n_dev, k0, v0, k1, flatten_ids, k2, v2, hist, tile_n_bits + cam_bits, stream, sc);
     if (rc != QED_OK) return rc;
-    compose_ids_ranges_kernel<<<(unsigned)((n_isects + 255) / 256), 256, 0, stream>>>(n_isects, k1, flatten_ids, depths, C, n_tiles, tile_n_bits,
-                                                                                   isect_ids, isect_offsets);
+    compose_ids_ranges_kernel<<<(unsigned)((n_isects + 255) / 256), 256, 0, stream>>>(n_isects, n_dev, k1, flatten_ids, depths, C, n_tiles,
+                                                                                   tile_n_bits, isect_ids, isect_offsets);
     QED_LAUNCH_CHECK();
     return QED_OK;
 }

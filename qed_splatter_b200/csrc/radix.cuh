@@ -16,9 +16,18 @@ constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs per block
 constexpr int kRadix = 256;
 
-template <typename KeyT>
+// Segmented input of the FIRST pass (exact tile lists): the input consists of segments of (1 << shift) slots of
+// which only the first counts[s] hold pairs (a block-local compaction upstream, no global one).  The pass
+// scatters by global digit offsets, so its output -- and every later pass -- is dense.
+struct SegCounts {
+    const int32_t* counts = nullptr;
+    int shift = 0;
+    __device__ __forceinline__ bool ok(int64_t i) const { return !counts || (int)(i & ((1 << shift) - 1)) < counts[i >> shift]; }
+};
+
+template <typename KeyT, bool SEG>
 __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(int64_t n_host, const int64_t* n_dev, const KeyT* __restrict__ keys, int shift,
-                                                                    uint32_t mask, int nblocks, uint32_t* __restrict__ hist /* [kRadix][nblocks] */) {
+                                                                    uint32_t mask, int nblocks, uint32_t* __restrict__ hist /* [kRadix][nblocks] */, SegCounts seg) {
     __shared__ uint32_t sh[kRadix];
     const int64_t n = n_dev ? *n_dev : n_host;
     sh[threadIdx.x] = 0;
@@ -28,7 +37,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(int64_t n_h
 #pragma unroll 4
         for (int k = 0; k < kSortItems; ++k) {
             int64_t i = base + k * kSortThreads + threadIdx.x;
-            if (i < n) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & mask], 1u);
+            if (i < n && (!SEG || seg.ok(i))) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & mask], 1u);
         }
     }
     __syncthreads();
@@ -87,14 +96,15 @@ struct RadixSmem {
     static constexpr size_t kBytes = (size_t)kSortTile * (sizeof(KeyT) + 4) + (size_t)(kSortThreads / 32) * kRadix * 4 + 2 * kRadix * 4 + 16 * 4;
 };
 
-template <typename KeyT>
+template <typename KeyT, bool SEG>
 __global__ void __launch_bounds__(kSortThreads, 3) radix_downsweep_kernel(int64_t n_host, const int64_t* n_dev, const KeyT* __restrict__ keys_in,
                                                                       const int32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                                                       int32_t* __restrict__ vals_out, int shift, uint32_t mask, int nblocks,
                                                                       const uint32_t* __restrict__ hist, const uint32_t* __restrict__ totals,
-                                                                      uint32_t* __restrict__ next_hist, int next_shift, uint32_t next_mask) {
+                                                                      uint32_t* __restrict__ next_hist, int next_shift, uint32_t next_mask, SegCounts seg) {
     constexpr int kWarps = kSortThreads / 32;
     constexpr int kPerWarp = kSortTile / kWarps;  // 512 consecutive pairs per warp
+    __shared__ int s_tile_pairs;
     constexpr int kRounds = kPerWarp / 32;        // 16
     extern __shared__ __align__(16) unsigned char sort_smem[];
     KeyT* skeys = reinterpret_cast<KeyT*>(sort_smem);                                         // [kSortTile]
@@ -116,6 +126,14 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_downsweep_kernel(int64_
     for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
     __syncthreads();
 
+    // segmented input: the present pairs of a segment sit at its start and a warp's 512 slots lie inside one
+    // segment, so the rounds behind the segment's count hold nothing and are skipped (warp-uniform)
+    int rounds_w = kRounds;
+    if (SEG) {
+        const int64_t w0 = base + warp * kPerWarp;  // first slot of this warp
+        const int left = w0 < n ? seg.counts[w0 >> seg.shift] - (int)(w0 & ((1 << seg.shift) - 1)) : 0;
+        rounds_w = left <= 0 ? 0 : (left + 31) / 32 < kRounds ? (left + 31) / 32 : kRounds;
+    }
     // phase 0: all of the tile's loads are issued before anything depends on them (one memory latency)
     KeyT key[kRounds];
     int32_t val[kRounds];
@@ -123,18 +141,22 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_downsweep_kernel(int64_
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const int local = warp * kPerWarp + r * 32 + lane;
-        key[r] = (local < tile_n) ? keys_in[base + local] : (KeyT)0;
+        key[r] = (local < tile_n && (!SEG || seg.ok(base + local))) ? keys_in[base + local] : (KeyT)0;
     }
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const int local = warp * kPerWarp + r * 32 + lane;
-        val[r] = (local < tile_n) ? vals_in[base + local] : 0;
+        val[r] = (local < tile_n && (!SEG || seg.ok(base + local))) ? vals_in[base + local] : 0;
     }
     // phase A: stable rank inside the warp's 512-pair sub-chunk
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const int local = warp * kPerWarp + r * 32 + lane;
-        const bool valid = local < tile_n;
+        if (SEG && r >= rounds_w) {
+            rank[r] = 0;
+            continue;
+        }
+        const bool valid = local < tile_n && (!SEG || seg.ok(base + local));
         const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
         const uint32_t peers = peers_by_ballot(d, valid);
         const int leader = __ffs(peers) - 1;
@@ -188,13 +210,14 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_downsweep_kernel(int64_
         __syncthreads();
         digit_start[d] = sscan[warp] + inc - run;
         global_base[d] = (sscan[8 + warp] + ginc - tot) + my_hist;
+        if (d == kRadix - 1) s_tile_pairs = (int)(sscan[warp] + inc);  // pairs actually present in this tile
     }
     __syncthreads();
     // phase C: place into block-sorted order in smem
 #pragma unroll
     for (int r = 0; r < kRounds; ++r) {
         const int local = warp * kPerWarp + r * 32 + lane;
-        if (local < tile_n) {
+        if (local < tile_n && (!SEG || seg.ok(base + local))) {
             const uint32_t d = (uint32_t)(key[r] >> shift) & mask;
             const uint32_t pos = digit_start[d] + warp_hist[warp][d] + rank[r];
             skeys[pos] = key[r];
@@ -204,9 +227,10 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_downsweep_kernel(int64_
     __syncthreads();
     // phase D: coalesced run writes (+ the histogram of the NEXT pass: the destination index decides which block
     // of the next pass the pair lands in, so the next pass needs no upsweep)
-    for (int i0 = 0; i0 < tile_n; i0 += kSortThreads) {
+    const int tile_pairs = s_tile_pairs;
+    for (int i0 = 0; i0 < tile_pairs; i0 += kSortThreads) {
         const int i = i0 + threadIdx.x;
-        const bool valid = i < tile_n;
+        const bool valid = i < tile_pairs;
         uint32_t bin = 0xffffffffu;
         if (valid) {
             const KeyT k = skeys[i];
@@ -439,7 +463,8 @@ inline size_t radix_hist_bytes(int64_t capacity) {
 // ping-pong buffer; `hist` = radix_hist_bytes(capacity) scratch.  keys_in/vals_in are not modified.
 template <typename KeyT>
 inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* keys_in, const int32_t* vals_in, KeyT* keys_out,
-                            int32_t* vals_out, KeyT* tmp_keys, int32_t* tmp_vals, void* hist_ws, int end_bit, cudaStream_t stream) {
+                            int32_t* vals_out, KeyT* tmp_keys, int32_t* tmp_vals, void* hist_ws, int end_bit, cudaStream_t stream,
+                            SegCounts seg = SegCounts()) {
     if (capacity <= 0) return QED_OK;
     const int nb = (int)((capacity + kSortTile - 1) / kSortTile);
     const size_t hist_bytes = ((size_t)kRadix * nb * 4 + 255) / 256 * 256;
@@ -453,7 +478,7 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
         QED_CUDA_TRY(cudaMemcpyAsync(vals_out, vals_in, (size_t)capacity * 4, cudaMemcpyDeviceToDevice, stream));
         return QED_OK;
     }
-    if (g_radix_onesweep && passes <= kMaxPasses && (nb <= kOnesweepMaxBlocks || g_radix_onesweep > 1)) {
+    if (!seg.counts && g_radix_onesweep && passes <= kMaxPasses && (nb <= kOnesweepMaxBlocks || g_radix_onesweep > 1)) {
         char* ows = reinterpret_cast<char*>(hist_ws) + 2 * hist_bytes + ((kRadix * 4 + 255) / 256 * 256);
         uint64_t* status = reinterpret_cast<uint64_t*>(ows);
         const size_t status_bytes = ((size_t)kRadix * nb * 8 + 255) / 256 * 256;
@@ -479,8 +504,10 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
         }
         return QED_OK;
     }
-    auto down = radix_downsweep_kernel<KeyT>;
+    auto down = radix_downsweep_kernel<KeyT, false>;
+    auto down_seg = radix_downsweep_kernel<KeyT, true>;
     QED_CUDA_TRY(cudaFuncSetAttribute(down, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RadixSmem<KeyT>::kBytes));
+    if (seg.counts) QED_CUDA_TRY(cudaFuncSetAttribute(down_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RadixSmem<KeyT>::kBytes));
     auto pass_mask = [&](int pass) {
         const int bits = (end_bit - pass * 8) < 8 ? (end_bit - pass * 8) : 8;
         return (uint32_t)((1u << bits) - 1u);
@@ -496,12 +523,19 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
         const bool to_out = ((passes - 1 - pass) % 2) == 0;  // destinations alternate, ending on *_out
         KeyT* dst_k = to_out ? keys_out : tmp_keys;
         int32_t* dst_v = to_out ? vals_out : tmp_vals;
-        radix_upsweep_kernel<KeyT><<<nb, kSortThreads, 0, stream>>>(capacity, n_dev, src_k, pass * 8, pass_mask(pass), nb, hist);
+        // segmented input: the first pass walks all `capacity` slots and keeps the present pairs; from then on the
+        // data is dense and n_dev (the number of present pairs) applies
+        const SegCounts sg = pass == 0 ? seg : SegCounts();
+        const int64_t* nd = (pass == 0 && seg.counts) ? nullptr : n_dev;
+        if (sg.counts)
+            radix_upsweep_kernel<KeyT, true><<<nb, kSortThreads, 0, stream>>>(capacity, nd, src_k, pass * 8, pass_mask(pass), nb, hist, sg);
+        else
+            radix_upsweep_kernel<KeyT, false><<<nb, kSortThreads, 0, stream>>>(capacity, nd, src_k, pass * 8, pass_mask(pass), nb, hist, sg);
         QED_LAUNCH_CHECK();
         radix_scan_kernel<<<kRadix, 256, 0, stream>>>(nb, hist, totals);
         QED_LAUNCH_CHECK();
-        down<<<nb, kSortThreads, RadixSmem<KeyT>::kBytes, stream>>>(capacity, n_dev, src_k, src_v, dst_k, dst_v, pass * 8, pass_mask(pass), nb, hist,
-                                                                    totals, nullptr, 0, 0u);
+        (sg.counts ? down_seg : down)<<<nb, kSortThreads, RadixSmem<KeyT>::kBytes, stream>>>(capacity, nd, src_k, src_v, dst_k, dst_v, pass * 8,
+                                                                                          pass_mask(pass), nb, hist, totals, nullptr, 0, 0u, sg);
         QED_LAUNCH_CHECK();
         src_k = dst_k;
         src_v = dst_v;

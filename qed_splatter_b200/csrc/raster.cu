@@ -32,11 +32,9 @@
 namespace qed {
 
 constexpr int kTile = 16;
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLog2_255 = 7.99435343685886f;
 
 struct RasterParams {
-    int C, N, D, width, height, tile_w, tile_h, normalize_last;
+    int C, N, D, width, height, tile_w, tile_h, normalize_last, offsets_has_end;
     int64_t n_isects;
     const float4* geom;
     const float* colors;
@@ -74,55 +72,6 @@ struct StatCounters {
         }
     }
 };
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// Conservative test in the log2 domain: Q(d) = A dx^2 + B dx dy + C dy^2 (positive definite,
-// = log2(e) * sigma), d = mean - pixel centre.  A pixel can only be touched if Q <= tau2 = lo + log2(255).
-// Returns false only if the minimum of Q over the rectangle [x0,x1]x[y0,y1] exceeds tau2 by a margin.
-__device__ __forceinline__ bool ellipse_hits_rect(float mx, float my, float A, float B, float C, float tau2, float x0, float y0,
-                                                  float x1, float y1) {
-    if (!(tau2 >= 0.0f)) return false;  // opacity < 1/255 can never pass the alpha test
-    const float dxl = mx - x1, dxh = mx - x0;  // dx in [dxl, dxh]
-    const float dyl = my - y1, dyh = my - y0;
-    if (dxl <= 0.0f && dxh >= 0.0f && dyl <= 0.0f && dyh >= 0.0f) return true;  // centre inside
-    // convex quadratic, centre outside: the minimum over the rectangle lies on an edge
-    float best = 3.0e38f, mag = 0.0f;
-    const float hC = 0.5f * rcp_approx(C), hA = 0.5f * rcp_approx(A);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {  // edges dx = const
-        const float dx = e ? dxh : dxl;
-        const float dy = fminf(fmaxf(-B * dx * hC, dyl), dyh);
-        const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
-        const float s = t0 + t1 + t2;
-        if (s < best) {
-            best = s;
-            mag = t0 + t1 + fabsf(t2);
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {  // edges dy = const
-        const float dy = e ? dyh : dyl;
-        const float dx = fminf(fmaxf(-B * dy * hA, dxl), dxh);
-        const float t0 = A * dx * dx, t1 = C * dy * dy, t2 = B * dx * dy;
-        const float s = t0 + t1 + t2;
-        if (s < best) {
-            best = s;
-            mag = t0 + t1 + fabsf(t2);
-        }
-    }
-    // margin: 1 % + absolute + rounding of the three terms (cancellation for thin, tilted ellipses)
-    return !(best > tau2 * 1.01f + 0.03f + 2e-5f * mag);
-}
 
 // Geometry of the thread block: PX pixels per lane -> warps per tile and warp footprint.
 template <int PX>
@@ -293,7 +242,7 @@ __global__ void __launch_bounds__(Shape<PX>::kThreads) raster_fwd_kernel(const R
 
     const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
     const int64_t range_start = p.offsets[tile_id];
-    const int64_t range_end = (tile_id == (int64_t)p.C * p.tile_h * p.tile_w - 1) ? p.n_isects : (int64_t)p.offsets[tile_id + 1];
+    const int64_t range_end = (!p.offsets_has_end && tile_id == (int64_t)p.C * p.tile_h * p.tile_w - 1) ? p.n_isects : (int64_t)p.offsets[tile_id + 1];
 
     // pixel-centre rectangles for the culling tests (clipped to the image)
     const float tx0 = (float)(tx * kTile) + 0.5f, ty0 = (float)(ty * kTile) + 0.5f;
@@ -465,7 +414,7 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 14) raster_fwd_ws_kernel(c
 
     const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
     const int range_start = p.offsets[tile_id];
-    const int range_end = (tile_id == (int64_t)p.C * p.tile_h * p.tile_w - 1) ? (int)p.n_isects : p.offsets[tile_id + 1];
+    const int range_end = (!p.offsets_has_end && tile_id == (int64_t)p.C * p.tile_h * p.tile_w - 1) ? (int)p.n_isects : p.offsets[tile_id + 1];
     const SubRects<2> sr = make_blocks8(ox, oy, p.width, p.height);
 
     f32x2 T2[2], acc2[2][D];
@@ -535,14 +484,10 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 14) raster_fwd_ws_kernel(c
             const f32x2 dy2 = add2(bc2(A.y), npy2);
             const f32x2 t2 = mul2(bc2(B.y), dy2);
             const f32x2 cy2 = fma2(mul2(bc2(B.z), dy2), dy2, bc2(A.z));
-            if (mask == 3) {  // one basic block: the two independent blocks interleave
-                fwd_pk_block<D, STATS>(0, A, B, Cc, px0, dy2, t2, cy2, T2[0], acc2[0], last[0], thr[0], st);
-                fwd_pk_block<D, STATS>(1, A, B, Cc, px0, dy2, t2, cy2, T2[1], acc2[1], last[1], thr[1], st);
-            } else if (mask == 1) {
-                fwd_pk_block<D, STATS>(0, A, B, Cc, px0, dy2, t2, cy2, T2[0], acc2[0], last[0], thr[0], st);
-            } else {
-                fwd_pk_block<D, STATS>(1, A, B, Cc, px0, dy2, t2, cy2, T2[1], acc2[1], last[1], thr[1], st);
-            }
+            // two separate basic blocks: with a fused both-blocks path ptxas no longer updates the accumulators in
+            // place (18 register moves per Gaussian), and the forward has the occupancy to hide the latency instead
+            if (mask & 1) fwd_pk_block<D, STATS>(0, A, B, Cc, px0, dy2, t2, cy2, T2[0], acc2[0], last[0], thr[0], st);
+            if (mask & 2) fwd_pk_block<D, STATS>(1, A, B, Cc, px0, dy2, t2, cy2, T2[1], acc2[1], last[1], thr[1], st);
         }
         alive = (__any_sync(0xffffffffu, fminf(thr[0][0], thr[0][1]) < 1.0f) ? 1 : 0) | (__any_sync(0xffffffffu, fminf(thr[1][0], thr[1][1]) < 1.0f) ? 2 : 0);
         g_cur = g_nxt;
@@ -1253,7 +1198,7 @@ extern "C" int qed_debug_set_raster_px(int px_fwd, int px_bwd) {
 
 extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
                               const float* backgrounds, int width, int height, int tile_size, int tile_width,
-                              int tile_height, const int32_t* isect_offsets, const int32_t* flatten_ids,
+                              int tile_height, const int32_t* isect_offsets, int offsets_has_end, const int32_t* flatten_ids,
                               int normalize_last, float* render, float* alphas, int32_t* last_ids, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_raster_args(C, N, n_isects, D, width, height, tile_size, tile_width, tile_height);
@@ -1267,6 +1212,7 @@ extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float
     p.render = render;
     p.alphas = alphas;
     p.last_ids = last_ids;
+    p.offsets_has_end = offsets_has_end ? 1 : 0;
     switch (D) {
         case 1: return launch_raster<1, false>(p, stream);
         case 3: return launch_raster<3, false>(p, stream);

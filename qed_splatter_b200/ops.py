@@ -193,9 +193,10 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
         offsets = torch.empty(C, tile_height, tile_width, dtype=torch.int32, device=dev) if return_offsets else None
         fws_bytes = lib.qed_isect_fill_workspace_bytes(n_isects)
         fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), tile_size, tile_width,
+        # geom = NULL: gsplat's lists bit for bit (the exact tile lists are the fused pipeline's business)
+        check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), None, 0, 0, tile_size, tile_width,
                                  tile_height, ptr(pws), ptr(fws), fws_bytes, ptr(isect_ids) if n_isects else None,
-                                 ptr(flatten_ids) if n_isects else None, ptr(offsets), stream), "qed_isect_fill")
+                                 ptr(flatten_ids) if n_isects else None, ptr(offsets), None, stream), "qed_isect_fill")
         if return_offsets:
             return tiles_per_gauss, isect_ids, flatten_ids, offsets
         return tiles_per_gauss, isect_ids, flatten_ids
@@ -277,7 +278,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         alphas = torch.empty(C, height, width, 1, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         check(lib.qed_raster_fwd(C, N, n_isects, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile_size,
-                                 tile_width, tile_height, ptr(isect_offsets), ptr(flatten_ids), int(normalize_last),
+                                 tile_width, tile_height, ptr(isect_offsets), 0, ptr(flatten_ids), int(normalize_last),
                                  ptr(render), ptr(alphas), ptr(last_ids), current_stream()), "qed_raster_fwd")
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, geom, isect_offsets, flatten_ids, render,
                               alphas, last_ids)

@@ -39,11 +39,16 @@ class StepOutput:
 class FusedSplatStep:
     """Holds reusable device buffers; `forward()` renders, `step()` renders + loss + full backward."""
 
-    def __init__(self, device, sort_impl: str = "two_level", want_isect_ids: bool = False):
+    def __init__(self, device, sort_impl: str = "two_level", want_isect_ids: bool = False, exact_tile_lists: bool = True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.sort_impl = sort_impl
         self.want_isect_ids = want_isect_ids  # the compositor does not need the 64-bit keys; only `info` does
+        # exact tile lists (two_level only): (Gaussian, tile) candidates that cannot reach alpha >= 1/255 at any pixel
+        # centre of the tile are dropped before the tile sort (about half of gsplat's bounding-box lists); pixels are
+        # unchanged.  The public `rasterization()` keeps gsplat's lists bit for bit (`info` contract).
+        self.exact_tile_lists = exact_tile_lists
+        self._n_exact = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._total = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._counts = torch.zeros(2, dtype=torch.int64, device=self.device)
         self._counts_host = torch.zeros(2, dtype=torch.int64).pin_memory()
@@ -106,7 +111,9 @@ class FusedSplatStep:
                                   ptr(conics), ptr(comps), ptr(colors), ptr(opac), ptr(tiles), ptr(geom), stream), "qed_project_fwd")
         self._mark("project_fwd")
         CN = C * N
-        offsets = self._get("offsets", (C, th, tw), torch.int32)
+        # exact tile lists: one more element (the end of the last range), the entry count stays on the device
+        exact = self.exact_tile_lists and self.sort_impl == "two_level"
+        offsets = self._get("offsets", (C * th * tw + 1,), torch.int32)
         if self.sort_impl == "two_level":
             pws_bytes = lib.qed_isect_prepare_workspace_bytes(CN)
             pws = self._get("prep_ws", (pws_bytes,), torch.uint8)
@@ -125,8 +132,9 @@ class FusedSplatStep:
             flat = self._get("flat", (cap,), torch.int32)[:M]
             fws_bytes = lib.qed_isect_fill_workspace_bytes(M)
             fws = self._get("fill_ws", (fws_bytes,), torch.uint8)
-            check(lib.qed_isect_fill(C, N, n_vis, M, ptr(means2d), ptr(radii), ptr(depths), tile, tw, th, ptr(pws), ptr(fws), fws_bytes,
-                                     ptr(ids) if (M and self.want_isect_ids) else None, ptr(flat) if M else None, ptr(offsets), stream), "qed_isect_fill")
+            check(lib.qed_isect_fill(C, N, n_vis, M, ptr(means2d), ptr(radii), ptr(depths), ptr(geom) if exact else None, width, height,
+                                     tile, tw, th, ptr(pws), ptr(fws), fws_bytes, ptr(ids) if (M and self.want_isect_ids) else None,
+                                     ptr(flat) if M else None, ptr(offsets), ptr(self._n_exact) if exact else None, stream), "qed_isect_fill")
             self._mark("isect_fill")
         else:
             cum = self._get("cum", (CN,), torch.int64)
@@ -159,10 +167,10 @@ class FusedSplatStep:
         render = self._get("render", (C, height, width, D))
         alphas = self._get("alphas", (C, height, width, 1))
         last_ids = self._get("last_ids", (C, height, width), torch.int32)
-        check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets),
+        check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets), int(exact),
                                  ptr(flat) if M else None, normalize, ptr(render), ptr(alphas), ptr(last_ids), stream), "qed_raster_fwd")
         self._mark("raster_fwd")
-        self._fwd = dict(C=C, N=N, D=D, M=M, K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
+        self._fwd = dict(C=C, N=N, D=D, M=M, exact=exact, K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
                          th=th, width=width, height=height, eps2d=eps2d, radii=radii, conics=conics, comps=comps, colors=colors,
                          geom=geom, offsets=offsets, flat=flat, render=render, alphas=alphas, last_ids=last_ids, backgrounds=backgrounds,
                          inputs=(means, quats, scales, opacities, sh, viewmats, Ks))
@@ -255,6 +263,12 @@ class FusedSplatStep:
                           n_isects=self._fwd["M"])
 
     # -- instrumentation (never inside a timed region) --------------------------------------------
+    def n_isects_exact(self) -> int:
+        """Entries of the exact tile lists of the last forward (device -> host read: not for timed regions);
+        equals StepOutput.n_isects (gsplat's bounding-box count) when exact_tile_lists is off."""
+        f = self._fwd
+        return int(self._n_exact.item()) if (f.get("exact") and f["M"]) else int(f["M"])
+
     @property
     def launches_per_step(self) -> int:
         """Kernel launches of one step(): project 1; intersections (two_level: 3 scan + 1 compact + 3 per
@@ -286,8 +300,8 @@ class FusedSplatStep:
             try:
                 if which == "fwd":
                     check(lib.qed_raster_fwd(f["C"], f["N"], f["M"], f["D"], ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]),
-                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"],
-                                             ptr(f["render"]), ptr(f["alphas"]), ptr(f["last_ids"]), stream), "qed_raster_fwd(stats)")
+                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), int(f["exact"]), ptr(f["flat"]),
+                                             f["normalize"], ptr(f["render"]), ptr(f["alphas"]), ptr(f["last_ids"]), stream), "qed_raster_fwd(stats)")
                 else:
                     v_render, v_alphas = self._last_v
                     scratch = torch.zeros(f["C"] * f["N"], 12, device=self.device)

@@ -117,6 +117,56 @@ def test_pair_counters_of_instrumented_kernels(cuda):
     assert abs(c["fwd_pairs_contributing"] - n_o) <= 2e-3 * n_o, (c["fwd_pairs_contributing"], n_o)
 
 
+@pytest.mark.parametrize("size,scale", [(120, 1.0), (100, 0.3)])
+def test_exact_tile_lists(cuda, size, scale):
+    """The fused step's exact tile lists: an order-preserving subset of gsplat's bounding-box lists, every dropped
+    (Gaussian, tile) entry stays below alpha = 1/255 at every pixel centre of its tile, and so the image is
+    bit-identical and the gradients differ by summation order only."""
+    s = scene_s0(N=5000, C=2, size=size)
+    s.scales = s.scales * scale
+    g = s.to(cuda)
+    bg = torch.tensor([0.3, 0.1, 0.6], device=cuda)
+    res = {}
+    for exact in (False, True):
+        fs = FusedSplatStep(cuda, exact_tile_lists=exact)
+        out = fs.step(g.means, g.quats, g.scales, g.opacities, g.sh, g.viewmats, g.Ks, g.width, g.height, 3, g.gt_rgb, g.gt_depth, bg)
+        f = fs._fwd
+        n = fs.n_isects_exact()
+        n_tiles = s.C * f["tw"] * f["th"]
+        off = f["offsets"][:n_tiles].tolist() + [n]
+        res[exact] = dict(render=out.render.clone(), alphas=out.alphas.clone(), loss=out.loss.clone(), grads={k: v.clone() for k, v in out.grads.items()},
+                          flat=f["flat"][:n].tolist(), off=off, n=n, M=out.n_isects, geom=f["geom"].clone(), tw=f["tw"], th=f["th"])
+    a, b = res[False], res[True]
+    assert a["n"] == a["M"] == b["M"] and 0 < b["n"] < a["n"]
+    assert torch.equal(a["render"], b["render"]) and torch.equal(a["alphas"], b["alphas"]) and torch.equal(a["loss"], b["loss"])
+    for k in a["grads"]:
+        sc = float(a["grads"][k].abs().mean()) + 1e-12
+        assert_close_frac(b["grads"][k], a["grads"][k], 1e-4, 1e-4 * sc, 1e-3, f"v_{k}")
+    geom = a["geom"].view(-1, 8).cpu()
+    tw, th = a["tw"], a["th"]
+    dropped = 0
+    for t in range(s.C * tw * th):
+        full, kept = a["flat"][a["off"][t]:a["off"][t + 1]], b["flat"][b["off"][t]:b["off"][t + 1]]
+        it = iter(full)
+        assert all(any(x == y for y in it) for x in kept), f"tile {t}: not an ordered subset"
+        gone = sorted(set(full) - set(kept))  # a Gaussian appears at most once per tile
+        assert len(gone) == len(full) - len(kept)
+        if not gone:
+            continue
+        dropped += len(gone)
+        tile = t % (tw * th)
+        ty, tx = divmod(tile, tw)
+        ys = torch.arange(ty * 16, min(ty * 16 + 16, s.height)).float() + 0.5
+        xs = torch.arange(tx * 16, min(tx * 16 + 16, s.width)).float() + 0.5
+        gg = geom[gone].double()  # mx, my, opacity, depth, a, b, c, -
+        dx = gg[:, 0, None, None] - xs[None, None, :].double()
+        dy = gg[:, 1, None, None] - ys[None, :, None].double()
+        sigma = 0.5 * (gg[:, 4, None, None] * dx * dx + gg[:, 6, None, None] * dy * dy) + gg[:, 5, None, None] * dx * dy
+        alpha = gg[:, 2, None, None] * torch.exp(-sigma)
+        assert float(alpha.max()) < 1.0 / 255.0, f"tile {t}: a dropped entry reaches alpha {float(alpha.max())}"
+    assert dropped == a["n"] - b["n"]
+
+
 def test_view_sharding_equals_single_rank(cuda):
     """2 'ranks' x 1 view with grad_scale = 1/2, summed (what the all-reduce does) == 1 rank x 2 views."""
     s = scene_s0(N=3000, C=2, size=96).to(cuda)
