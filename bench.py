@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--comm-chunks", type=int, default=1, help="Gaussian ranges of the projection backward whose SH gradients are all-reduced while the next range computes (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--torch-loss", action="store_true", help="e2e: write the loss with torch ops as the reference does instead of depth_supervised_loss")
     ap.add_argument("--no-train", action="store_true")
     return ap.parse_args()
 
@@ -190,7 +191,7 @@ def main_ours(args):
     import torch
     import torch.distributed as dist
 
-    from qed_splatter_b200 import _lib, ops, rasterization
+    from qed_splatter_b200 import _lib, depth_supervised_loss, ops, rasterization
     from qed_splatter_b200.pipeline import FusedSplatStep
     from qed_splatter_b200.scenes import scene_s1
 
@@ -357,14 +358,18 @@ def main_ours(args):
                                                 sh_degree=3, sparse_grad=False, absgrad=True, rasterize_mode="classic")
             info["means2d"].retain_grad()
             torch.cuda.current_stream().wait_event(gt_ready)
-            # qed_splatter/model.py:295-306 and :87-116 as the reference writes them (torch ops)
-            rgb = torch.clamp(render[..., :3] + (1 - alpha) * bg, 0.0, 1.0)
-            depth = render[..., 3:4]
-            depth = torch.where(alpha > 0, depth, depth.detach().max())
-            valid = torch.isfinite(depth) & torch.isfinite(d_gt) & (d_gt > 0)
-            l_rgb = 0.8 * (rgb_gt - rgb).abs().mean()
-            l_d = 0.2 * ((depth - d_gt).abs() * valid).sum() / valid.sum().clamp(min=1)
-            loss_t = (l_rgb + l_d) / world
+            if args.torch_loss:
+                # qed_splatter/model.py:295-306 and :87-116 as the reference writes them (a dozen torch element-wise ops)
+                rgb = torch.clamp(render[..., :3] + (1 - alpha) * bg, 0.0, 1.0)
+                depth = render[..., 3:4]
+                depth = torch.where(alpha > 0, depth, depth.detach().max())
+                valid = torch.isfinite(depth) & torch.isfinite(d_gt) & (d_gt > 0)
+                l_rgb = 0.8 * (rgb_gt - rgb).abs().mean()
+                l_d = 0.2 * ((depth - d_gt).abs() * valid).sum() / valid.sum().clamp(min=1)
+                loss_t = (l_rgb + l_d) / world
+            else:
+                # the same lines through the package's drop-in for them (losses.depth_supervised_loss)
+                loss_t = depth_supervised_loss(render, alpha, rgb_gt, d_gt, bg, rgb_weight=0.8, depth_lambda=0.2)[0] / world
             loss_t.backward()
             if world > 1:
                 for p_ in params:
@@ -386,7 +391,9 @@ def main_ours(args):
         h2d = vm_h.numel() * 4 + K_h.numel() * 4 + gt_rgb_h.numel() * 4 + gt_depth_h.numel() * 4
         e2e = {"value": world * width * height / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": e2e_ms, "loss": e2e_loss,
-               "api": "qed_splatter_b200.rasterization (gsplat surface) + torch autograd loss as in qed_splatter/model.py"}
+               "api": "qed_splatter_b200.rasterization (gsplat surface) + " +
+                      ("torch autograd loss as qed_splatter/model.py writes it" if args.torch_loss else
+                       "qed_splatter_b200.depth_supervised_loss (model.py:295-306, 73-118 as one autograd op)") + " + backward()"}
 
     if rank == 0:
         peaks = {}

@@ -6,6 +6,7 @@ loss-gradient / trainer step built on the same kernels.  Hand-written CUDA behin
 (`include/qed_splat.h`, `libqedsplat.so`); no CPU fallback.
 """
 from .rendering import rasterization  # noqa: F401
+from .losses import depth_supervised_loss  # noqa: F401
 from . import ops, scenes  # noqa: F401
 
 __version__ = "0.1.0"

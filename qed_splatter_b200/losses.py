@@ -1,0 +1,75 @@
+"""`depth_supervised_loss` — the tail of `QEDSplatterModel.get_outputs` and its `get_loss_dict` as ONE call.
+
+Replaces, for a render produced by `rasterization(..., render_mode="RGB+D" | "RGB+ED")`:
+  * /root/reference/qed_splatter/model.py:295-306 — background composite, clamp to [0,1], depth fill of
+    never-hit pixels with the maximum rendered depth;
+  * /root/reference/qed_splatter/model.py:73-118 (+ splatfacto's RGB loss it inherits) —
+    rgb_weight * L1 + ssim_lambda * (1 - SSIM) + depth_lambda * masked depth-L1 (22-38: `depth_loss`),
+with a torch.autograd.Function over the C-ABI `qed_loss_fwd_bwd`: the forward launch computes the loss AND its
+gradient with respect to (render, alphas); backward only scales it.  The dozen element-wise torch kernels of the
+reference formulation (each a full pass over the image) become four launches.
+
+Semantics are per camera (one camera = one reference step: its own depth fill and valid-pixel count) and the
+mean over cameras; for the reference's single-camera steps that is the reference's number.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, current_stream, ptr
+
+
+class _DepthSupervisedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, render: Tensor, alphas: Tensor, gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, rgb_weight: float,
+                depth_lambda: float, ssim_lambda: float) -> Tuple[Tensor, Tensor, Tensor]:
+        if not render.is_cuda:
+            raise RuntimeError("qed_splatter_b200 has no CPU path: tensors must live on a CUDA device")
+        C, H, W, D = render.shape
+        if D != 4:
+            raise ValueError("depth_supervised_loss needs a 4-channel render (render_mode 'RGB+D' or 'RGB+ED')")
+        if gt_rgb.shape != (C, H, W, 3) or gt_depth.numel() != C * H * W or alphas.numel() != C * H * W or background.numel() != 3:
+            raise ValueError("shapes: render [C,H,W,4], alphas [C,H,W,1], gt_rgb [C,H,W,3], gt_depth [C,H,W(,1)], background [3]")
+        lib = _lib.load()
+        dev = render.device
+        r = render.detach().contiguous().float()
+        a = alphas.detach().contiguous().float()
+        rgb = gt_rgb.detach().contiguous().float()
+        dep = gt_depth.detach().contiguous().float()
+        bg = background.detach().contiguous().float()
+        stats = torch.zeros(C * 8, dtype=torch.float64, device=dev)
+        loss = torch.empty(3, device=dev)
+        v_render = torch.empty_like(r)
+        v_alphas = torch.empty_like(a)
+        ws_bytes = lib.qed_loss_workspace_bytes(C, W, H, float(ssim_lambda))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        check(lib.qed_loss_fwd_bwd(C, W, H, ptr(r), ptr(a), ptr(rgb), ptr(dep), ptr(bg), float(rgb_weight), float(depth_lambda),
+                                   float(ssim_lambda), 1.0, ptr(stats), ptr(loss), ptr(v_render), ptr(v_alphas), ptr(ws), ws_bytes,
+                                   current_stream()), "qed_loss_fwd_bwd")
+        ctx.save_for_backward(v_render, v_alphas)
+        total, l_rgb, l_depth = loss.unbind(0)
+        ctx.mark_non_differentiable(l_rgb, l_depth)
+        return total, l_rgb, l_depth
+
+    @staticmethod
+    def backward(ctx, g_total, g_rgb, g_depth):
+        v_render, v_alphas = ctx.saved_tensors
+        # d(total)/d(render, alphas) was computed by the forward launch; the components are reported for logging only
+        return v_render * g_total, v_alphas * g_total, None, None, None, None, None, None
+
+
+def depth_supervised_loss(render: Tensor, alphas: Tensor, gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, rgb_weight: float = 0.8,
+                          depth_lambda: float = 0.2, ssim_lambda: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> (total, rgb_term, depth_term), 0-dim tensors; `total` carries the gradient to `render` and `alphas`.
+
+    render [C,H,W,4] (RGB + depth; expected depth for 'RGB+ED'), alphas [C,H,W,1], gt_rgb [C,H,W,3] in [0,1],
+    gt_depth [C,H,W] or [C,H,W,1] (<= 0 or non-finite = no supervision), background [3].
+    total = rgb_weight * mean|clamp(rgb + (1 - alpha) bg, 0, 1) - gt| + ssim_lambda * (1 - SSIM) + depth_lambda *
+    mean_valid|depth_filled - gt_depth|  (qed-splatter: depth_lambda = 0.2; splatfacto: rgb_weight = 0.8, ssim_lambda = 0.2).
+    """
+    total, l_rgb, l_depth = _DepthSupervisedLoss.apply(render, alphas, gt_rgb, gt_depth, background, rgb_weight, depth_lambda, ssim_lambda)
+    return total, l_rgb, l_depth

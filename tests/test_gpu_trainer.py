@@ -93,6 +93,40 @@ def test_fused_step_with_ssim_matches_oracle(cuda, size):
         assert_close_frac(out.grads[k], lo[k].grad, 1e-3, 1e-3 * scale, 5e-3, f"v_{k}")
 
 
+@pytest.mark.parametrize("mode,C,ssim", [("RGB+ED", 1, 0.0), ("RGB+D", 2, 0.2)])
+def test_depth_supervised_loss_is_the_reference_loss(cuda, mode, C, ssim):
+    """`rasterization()` + `depth_supervised_loss()` (one fused launch group, autograd-visible) == the reference's
+    torch formulation (model.py:295-306, 73-118) on the oracle's render: same number, same parameter gradients,
+    and the gradient scales with whatever the caller multiplies the loss by."""
+    from qed_splatter_b200 import depth_supervised_loss
+
+    s = scene_s0(N=2500, C=C, size=72)
+    s.scales = s.scales * 1.5
+    bg = torch.tensor([0.3, 0.1, 0.6])
+    lo = {k: getattr(s, k).clone().requires_grad_(True) for k in NAMES}
+    ro, ao, _ = oracle.rasterization(lo["means"], lo["quats"], lo["scales"], lo["opacities"], lo["sh"], s.viewmats, s.Ks, s.width, s.height,
+                                     sh_degree=3, render_mode=mode)
+    total = 0.0
+    for c in range(C):
+        rgb, depth = oracle.composite_and_fill(ro[c:c + 1], ao[c:c + 1], bg)
+        total = total + oracle.rgb_loss(rgb, s.gt_rgb[c:c + 1], ssim) + oracle.depth_l1_loss(depth, s.gt_depth[c:c + 1], 0.2)
+    loss_o = 0.5 * total / C
+    loss_o.backward()
+
+    g = s.to(cuda)
+    lg = {k: getattr(g, k).clone().requires_grad_(True) for k in NAMES}
+    render, alpha, info = rasterization(lg["means"], lg["quats"], lg["scales"], lg["opacities"], lg["sh"], g.viewmats, g.Ks, g.width, g.height,
+                                        sh_degree=3, render_mode=mode, absgrad=True)
+    tot, l_rgb, l_depth = depth_supervised_loss(render, alpha, g.gt_rgb, g.gt_depth, bg.to(cuda), rgb_weight=1.0 - ssim, depth_lambda=0.2,
+                                                ssim_lambda=ssim)
+    (0.5 * tot).backward()
+    assert float(0.5 * tot) == pytest.approx(float(loss_o), rel=2e-4)
+    assert float(l_rgb + l_depth) == pytest.approx(float(tot), rel=1e-5)
+    for k in NAMES:
+        scale = float(lo[k].grad.abs().mean()) + 1e-12
+        assert_close_frac(lg[k].grad, lo[k].grad, 1e-3, 1e-3 * scale, 5e-3, f"v_{k}")
+
+
 @pytest.mark.timeout(120)
 def test_pair_counters_of_instrumented_kernels(cuda):
     """bench.py's roofline uses the work counters of the instrumented (STATS) compositor kernels: they must run
