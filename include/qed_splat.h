@@ -143,8 +143,9 @@ int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* k
  *            flatten_ids + isect_offsets).
  * `prepare_workspace` must be the buffer qed_isect_prepare filled for the same (C, N).
  *
- * geom == NULL: gsplat's lists, bit for bit (every tile of each Gaussian's 3-sigma bounding box; n_isects entries).
- * geom != NULL (the packed [C*N,8] records of qed_project_fwd): EXACT tile lists for the fused step -- every
+ * n_exact_dev == NULL (and geom == NULL): gsplat's lists, bit for bit (every tile of each Gaussian's 3-sigma
+ *   bounding box; n_isects entries).
+ * n_exact_dev != NULL, geom = the packed [C*N,8] records of qed_project_fwd: EXACT tile lists -- every
  *   candidate (Gaussian, tile) is tested with the compositor's own conservative alpha >= 1/255 ellipse test and
  *   dropped if it cannot touch a pixel centre of the tile (about half of them; no pixel changes).  The number of
  *   survivors stays on the device: it is written to n_exact_dev[1] (int64), flatten_ids / isect_ids are filled for

@@ -551,9 +551,12 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     if (C < 0 || N < 0 || n_visible < 0 || n_isects < 0 || tile_size <= 0) return QED_ERR_BAD_ARG;
     const int64_t CN = (int64_t)C * N;
     const int n_tiles = tile_width * tile_height;
-    const bool exact = geom != nullptr;  // exact tile lists: offsets has C * n_tiles + 1 elements, the count stays on the device
-    if (exact && (!n_exact_dev || !isect_offsets || image_width <= 0 || image_height <= 0)) return QED_ERR_BAD_ARG;
-    if (exact && (reinterpret_cast<uintptr_t>(geom) & 15)) return QED_ERR_BAD_ARG;
+    // exact tile lists are requested by passing n_exact_dev (geom may legitimately be NULL for an empty scene):
+    // offsets has C * n_tiles + 1 elements, the count stays on the device
+    const bool exact = n_exact_dev != nullptr;
+    if (exact && (!isect_offsets || image_width <= 0 || image_height <= 0)) return QED_ERR_BAD_ARG;
+    if (exact && n_isects > 0 && CN > 0 && (!geom || (reinterpret_cast<uintptr_t>(geom) & 15))) return QED_ERR_BAD_ARG;
+    if (!exact && geom) return QED_ERR_BAD_ARG;  // geom without n_exact_dev: the caller would not learn the count
     if (n_isects == 0 || CN == 0) {
         if (isect_offsets && (int64_t)C * n_tiles > 0)
             QED_CUDA_TRY(cudaMemsetAsync(isect_offsets, 0, ((size_t)C * n_tiles + (exact ? 1 : 0)) * 4, stream));

@@ -244,6 +244,35 @@ def sort_pairs(keys: Tensor, vals: Tensor, end_bit: int = 64, impl: Optional[str
 
 
 @torch.no_grad()
+def isect_tiles_exact(means2d: Tensor, radii: Tensor, depths: Tensor, geom: Tensor, width: int, height: int, tile_size: int,
+                      tile_width: int, tile_height: int, tiles_per_gauss: Tensor):
+    """EXACT tile lists for the compositor (not gsplat's `info` lists): every (Gaussian, tile) candidate of gsplat's
+    bounding-box lists that cannot reach alpha = 1/255 at a pixel centre of the tile is dropped before the tile sort
+    (DESIGN.md section 5).  -> flatten_ids[M] i32 (M = gsplat's count; only the first n_exact entries are filled),
+    isect_offsets[C*th*tw + 1] i32 (last element = n_exact = end of the last range), n_exact[1] i64 on the device."""
+    lib = _lib.load()
+    _lib.require_cuda(means2d, radii, depths, geom)
+    means2d, depths = _f32c(means2d.detach()), _f32c(depths.detach())
+    C, N = radii.shape
+    dev = means2d.device
+    stream = current_stream()
+    pws_bytes = lib.qed_isect_prepare_workspace_bytes(C * N)
+    pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles_per_gauss), ptr(pws), pws_bytes, ptr(counts), None, stream),
+          "qed_isect_prepare")
+    n_visible, n_isects, _ = (int(v) for v in counts.tolist())  # the one host sync of the forward (gsplat has the same one)
+    flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+    offsets = torch.empty(C * tile_height * tile_width + 1, dtype=torch.int32, device=dev)
+    fws_bytes = lib.qed_isect_fill_workspace_bytes(n_isects)
+    fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), ptr(geom), width, height, tile_size,
+                             tile_width, tile_height, ptr(pws), ptr(fws), fws_bytes, None, ptr(flatten_ids) if n_isects else None,
+                             ptr(offsets), ptr(counts[2:]), stream), "qed_isect_fill")
+    return flatten_ids, offsets, counts[2:]
+
+
+@torch.no_grad()
 def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height: int) -> Tensor:
     """gsplat `isect_offset_encode` -> isect_offsets[C,tile_height,tile_width] i32."""
     lib = _lib.load()
@@ -272,13 +301,15 @@ class _RasterizeToPixels(torch.autograd.Function):
             geom = torch.empty(C, N, GEOM_FLOATS, device=dev)
             check(lib.qed_pack_geom(C * N, ptr(_f32c(means2d)), ptr(_f32c(conics)), ptr(_f32c(opacities)), None, ptr(geom),
                                     current_stream()), "qed_pack_geom")
-        tile_height, tile_width = isect_offsets.shape[1:]
+        has_end = isect_offsets.dim() == 1  # exact tile lists: [C*th*tw + 1], last element = end of the last range
+        tile_width, tile_height = tile_grid(width, height, tile_size)
+        assert isect_offsets.numel() == C * tile_height * tile_width + int(has_end), isect_offsets.shape
         n_isects = flatten_ids.numel()
         render = torch.empty(C, height, width, D, device=dev)
         alphas = torch.empty(C, height, width, 1, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
         check(lib.qed_raster_fwd(C, N, n_isects, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile_size,
-                                 tile_width, tile_height, ptr(isect_offsets), 0, ptr(flatten_ids), int(normalize_last),
+                                 tile_width, tile_height, ptr(isect_offsets), int(has_end), ptr(flatten_ids), int(normalize_last),
                                  ptr(render), ptr(alphas), ptr(last_ids), current_stream()), "qed_raster_fwd")
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, geom, isect_offsets, flatten_ids, render,
                               alphas, last_ids)
@@ -294,7 +325,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         C, N = opacities.shape
         D = colors.shape[-1]
         dev = means2d.device
-        tile_height, tile_width = isect_offsets.shape[1:]
+        tile_width, tile_height = tile_grid(width, height, tile_size)
         packed = torch.zeros(C * N, GRAD_FLOATS, device=dev)
         v_render = _f32c(v_render) if v_render is not None else torch.zeros_like(render)
         check(lib.qed_raster_bwd(C, N, flatten_ids.numel(), D, ptr(geom), ptr(colors), ptr(backgrounds), width, height,

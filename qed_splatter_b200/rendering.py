@@ -19,6 +19,56 @@ from . import ops
 RENDER_MODES = ("RGB", "D", "ED", "RGB+D", "RGB+ED")
 
 
+class _Pending:
+    """Placeholder of an `info` entry that is computed on first access."""
+
+
+class LazyInfo(dict):
+    """gsplat's `info` dict.  The compositor runs on EXACT tile lists, so gsplat's own
+    bounding-box lists -- `isect_ids`, `flatten_ids`, `isect_offsets`, which neither qed_splatter/model.py nor
+    gsplat's strategies read -- are built, bit for bit, the first time one of them is looked up."""
+
+    LAZY = ("isect_ids", "flatten_ids", "isect_offsets")
+
+    def __init__(self, eager: Dict, build_lists):
+        super().__init__(eager)
+        self._build_lists = build_lists
+        for k in self.LAZY:
+            dict.__setitem__(self, k, _Pending)
+
+    def _resolve(self) -> None:
+        if self._build_lists is not None:
+            build, self._build_lists = self._build_lists, None
+            for k, v in zip(self.LAZY, build()):
+                if dict.__getitem__(self, k) is _Pending:
+                    dict.__setitem__(self, k, v)
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if v is _Pending:
+            self._resolve()
+            v = dict.__getitem__(self, key)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __iter__(self):  # (also keeps dict(info) / {**info} off CPython's raw-storage fast path)
+        return iter(list(dict.keys(self)))
+
+    def values(self):
+        self._resolve()
+        return dict.values(self)
+
+    def items(self):
+        self._resolve()
+        return dict.items(self)
+
+    def copy(self):
+        self._resolve()
+        return dict(dict.items(self))
+
+
 def rasterization(
     means: Tensor,  # [N,3]
     quats: Tensor,  # [N,4] wxyz
@@ -82,8 +132,13 @@ def rasterization(
         append_depth=want_depth, tile_size=tile_size)
 
     tile_width, tile_height = ops.tile_grid(width, height, tile_size)
-    _, isect_ids, flatten_ids, isect_offsets = ops.isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
-                                                               tiles_per_gauss=tiles_per_gauss, return_offsets=True)
+    # the compositor's lists (exact: about half of gsplat's entries, no pixel changes); gsplat's own lists are built
+    # on demand by LazyInfo from the same projection outputs
+    flatten_ids, isect_offsets, _ = ops.isect_tiles_exact(means2d, radii, depths, geom, width, height, tile_size, tile_width, tile_height,
+                                                          tiles_per_gauss)
+
+    def gsplat_lists(m=means2d.detach(), r=radii, d=depths.detach(), t=tiles_per_gauss):
+        return ops.isect_tiles(m, r, d, tile_size, tile_width, tile_height, tiles_per_gauss=t, return_offsets=True)[1:]
 
     if backgrounds is not None and want_rgb and want_depth:
         backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device, dtype=backgrounds.dtype)], dim=-1)
@@ -92,7 +147,7 @@ def rasterization(
         means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
         absgrad=absgrad, geom=geom, normalize_last=normalize)
 
-    info = {
+    info = LazyInfo({
         "camera_ids": None,
         "gaussian_ids": None,
         "radii": radii,
@@ -103,12 +158,9 @@ def rasterization(
         "tile_width": tile_width,
         "tile_height": tile_height,
         "tiles_per_gauss": tiles_per_gauss,
-        "isect_ids": isect_ids,
-        "flatten_ids": flatten_ids,
-        "isect_offsets": isect_offsets,
         "width": width,
         "height": height,
         "tile_size": tile_size,
         "n_cameras": C,
-    }
+    }, gsplat_lists)
     return render_colors, render_alphas, info

@@ -96,23 +96,27 @@ def test_culling_is_exact_on_thin_tilted_splats(cuda):
     a["opacities"] = torch.cat([torch.rand(N // 2, generator=g) * 0.02 + 0.003, torch.rand(N - N // 2, generator=g)])
     ga = {k: v.to(cuda) for k, v in a.items()}
     outs = {}
-    for tag, cull in (("cull", True), ("cull_again", True), ("nocull", False)):
+    for tag, cull in (("cull", True), ("nocull", False)):
         ops.set_raster_cull(cull)
         leaves = {k: ga[k].clone().requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "colors")}
         r, al, info = rasterization(**leaves, viewmats=ga["viewmats"], Ks=ga["Ks"], width=W, height=H, render_mode="RGB+ED", sh_degree=None,
                                     absgrad=True)
+        info["means2d"].retain_grad()
         (r.sum() + al.sum()).backward()
-        outs[tag] = (r.detach(), al.detach(), {k: v.grad.double() for k, v in leaves.items()})
+        outs[tag] = (r.detach(), al.detach(), {k: v.grad.double() for k, v in leaves.items()}, info["means2d"].grad.double(),
+                     info["means2d"].absgrad.double())
     ops.set_raster_cull(True)
     assert torch.equal(outs["cull"][0], outs["nocull"][0]) and torch.equal(outs["cull"][1], outs["nocull"][1])
-    # gradients: the per-warp sums are identical in both modes; only the order of the float atomics differs, which
-    # also differs between two runs of the SAME mode.  Needle splats make the world-space gradients ill-conditioned
-    # (huge cancelling terms), so the yardstick is the run-to-run noise of the culled kernel itself.
+    # gradients: the per-warp sums are identical in both modes; only the order of the float atomics differs.  The
+    # screen-space gradients are well conditioned and must agree tightly; the world-space gradients of needle splats
+    # are huge cancelling sums (run-to-run noise of the SAME mode reaches 1e-2 of the norm), so they get a loose,
+    # element-wise check.
+    for i, name in ((3, "v_means2d"), (4, "absgrad")):
+        ref = outs["nocull"][i]
+        assert_close_frac(outs["cull"][i], ref, 1e-4, 1e-5 * float(ref.abs().mean() + 1e-30), 1e-3, name)
     for k in outs["cull"][2]:
-        ref = outs["cull"][2][k]
-        noise = float((outs["cull_again"][2][k] - ref).norm() / (ref.norm() + 1e-30))
-        diff = float((outs["nocull"][2][k] - ref).norm() / (ref.norm() + 1e-30))
-        assert diff <= 10.0 * noise + 1e-4, (k, diff, noise)
+        ref = outs["nocull"][2][k]
+        assert_close_frac(outs["cull"][2][k], ref, 5e-2, 1e-3 * float(ref.abs().mean() + 1e-30), 2e-2, f"v_{k}")
     outs[True] = outs["cull"]
     # and against the oracle
     ro, ao, _ = oracle.rasterization(**a, width=W, height=H, render_mode="RGB+ED", sh_degree=None)

@@ -27,3 +27,23 @@ def test_reference_import_resolves_to_b200_rasterization():
         sys.path.remove(shim)
         for m in [k for k in sys.modules if k == "gsplat" or k.startswith("gsplat.")]:
             del sys.modules[m]
+
+
+def test_lazy_info_builds_gsplat_lists_on_first_access():
+    """`rasterization()` composites on exact tile lists; gsplat's own lists in `info` are built on demand, once."""
+    from qed_splatter_b200.rendering import LazyInfo
+
+    calls = []
+
+    def build():
+        calls.append(1)
+        return "ids", "flat", "off"
+
+    info = LazyInfo({"radii": 1, "width": 5}, build)
+    assert "isect_ids" in info and set(info.keys()) == {"radii", "width", "isect_ids", "flatten_ids", "isect_offsets"} and not calls
+    assert info["radii"] == 1 and info.get("width") == 5 and info.get("nope", 7) == 7 and not calls
+    assert info["flatten_ids"] == "flat" and info["isect_ids"] == "ids" and info.get("isect_offsets") == "off" and calls == [1]
+    assert dict(LazyInfo({"radii": 1}, build))["isect_ids"] == "ids"
+    assert {**LazyInfo({"radii": 1}, build)}["isect_offsets"] == "off"
+    assert "flat" in list(LazyInfo({"radii": 1}, build).values())
+    assert LazyInfo({"radii": 1}, build).copy()["flatten_ids"] == "flat"
