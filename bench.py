@@ -333,6 +333,15 @@ def main_ours(args):
     e2e = None
     if not args.no_e2e:
         params = [t.clone().requires_grad_(True) for t in (means, quats, scales, opac, sh)]
+        # N > 1: the parameter gradients are views of ONE flat bucket (what DDP's gradient_as_bucket_view does), so the
+        # step needs one 236 MB all-reduce instead of five calls of 4..192 MB
+        grad_bucket, grad_views = None, None
+        if world > 1:
+            grad_bucket = torch.zeros(sum(p_.numel() for p_ in params), device=dev)
+            grad_views, o_ = [], 0
+            for p_ in params:
+                grad_views.append(grad_bucket[o_:o_ + p_.numel()].view_as(p_))
+                o_ += p_.numel()
         # the step's inputs come from pinned host memory on a copy stream (what a data loader does); the loss
         # waits on the copy event, so the H2D of the ground truth overlaps projection/sort/compositing
         copy_stream = torch.cuda.Stream()
@@ -351,8 +360,13 @@ def main_ours(args):
                 gt_ready.record(copy_stream)
             torch.cuda.current_stream().wait_event(cam_ready)
             vm, Kc, rgb_gt, d_gt = vm_d, K_d, rgb_d, depth_d
-            for p_ in params:
-                p_.grad = None
+            if grad_bucket is None:
+                for p_ in params:
+                    p_.grad = None
+            else:
+                grad_bucket.zero_()
+                for p_, g_ in zip(params, grad_views):
+                    p_.grad = g_  # autograd accumulates in place
             render, alpha, info = rasterization(params[0], params[1], params[2], params[3], params[4], vm, Kc, width, height,
                                                 tile_size=16, packed=False, near_plane=0.01, far_plane=1e10, render_mode=args.mode,
                                                 sh_degree=3, sparse_grad=False, absgrad=True, rasterize_mode="classic")
@@ -372,8 +386,7 @@ def main_ours(args):
                 loss_t = depth_supervised_loss(render, alpha, rgb_gt, d_gt, bg, rgb_weight=0.8, depth_lambda=0.2)[0] / world
             loss_t.backward()
             if world > 1:
-                for p_ in params:
-                    dist.all_reduce(p_.grad)
+                dist.all_reduce(grad_bucket)
             return float(loss_t.item())  # D2H read of the step's result
 
         for _ in range(W_):
