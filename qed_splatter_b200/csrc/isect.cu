@@ -270,8 +270,7 @@ __global__ void emit_boundaries_kernel(int64_t n_vis, const int64_t* __restrict_
     for (int64_t b = (start + kEmitTile - 1) / kEmitTile; b * kEmitTile < end; ++b) first_j[b] = (int32_t)j;
 }
 
-//
-// EXACT = exact tile lists (the fused pipeline; gsplat's lists hold every tile of the 3-sigma bounding box):
+// EXACT = exact tile lists for the compositor (gsplat's own lists hold every tile of the 3-sigma bounding box):
 // every candidate (Gaussian, tile) entry is tested with the compositor's own conservative alpha >= 1/255
 // ellipse test against the tile's pixel-centre rectangle and only survivors are written -- compacted in
 // order at the START of the block's own kEmitTile-slot segment, with the count in seg_counts[block].  There
