@@ -170,8 +170,12 @@ __global__ void loss_finalize_kernel(int C, int64_t HW, float rgb_weight, float 
 }
 
 // ------------------------------------------------------------------------------------------------
-// One float4 (or, in the scalar tail/unaligned variant, one float) per thread: 4 x LDG.128 + 3 x STG.128, everything
-// in flight at once.  28 B/parameter of pure HBM traffic.
+// Two float4 (or, in the scalar tail/unaligned variant, one float) per thread: 8 x LDG.128 issued before anything
+// depends on them, streaming loads/stores (read once, written once: keep them out of L2's way), 3 x 2 STG.128.
+// 28 B/parameter of pure HBM traffic.
+__device__ __forceinline__ float4 ld_stream4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st_stream4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
 template <bool VEC4>
 __global__ void __launch_bounds__(256) adam_arena_kernel(int64_t n, float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
                                                          float* __restrict__ v, int G, const int64_t* __restrict__ group_ends,
@@ -189,46 +193,60 @@ __global__ void __launch_bounds__(256) adam_arena_kernel(int64_t n, float* __res
         s_split[threadIdx.x] = group_split ? group_split[threadIdx.x] : 0;
     }
     __syncthreads();
-    constexpr int W = VEC4 ? 4 : 1;
-    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * W;
-    if (i0 >= n) return;
-    float p[W], g[W], mi[W], vi[W];
-    if (VEC4) {
-        const float4 P = *reinterpret_cast<const float4*>(param + i0), Gd = *reinterpret_cast<const float4*>(grad + i0);
-        const float4 M = *reinterpret_cast<const float4*>(m + i0), V = *reinterpret_cast<const float4*>(v + i0);
-        p[0] = P.x; p[W > 1 ? 1 : 0] = P.y; p[W > 1 ? 2 : 0] = P.z; p[W > 1 ? 3 : 0] = P.w;
-        g[0] = Gd.x; g[W > 1 ? 1 : 0] = Gd.y; g[W > 1 ? 2 : 0] = Gd.z; g[W > 1 ? 3 : 0] = Gd.w;
-        mi[0] = M.x; mi[W > 1 ? 1 : 0] = M.y; mi[W > 1 ? 2 : 0] = M.z; mi[W > 1 ? 3 : 0] = M.w;
-        vi[0] = V.x; vi[W > 1 ? 1 : 0] = V.y; vi[W > 1 ? 2 : 0] = V.z; vi[W > 1 ? 3 : 0] = V.w;
-    } else {
-        p[0] = param[i0];
-        g[0] = grad[i0];
-        mi[0] = m[i0];
-        vi[0] = v[i0];
+    constexpr int W = VEC4 ? 4 : 1;   // consecutive parameters per chunk
+    constexpr int U = VEC4 ? 2 : 1;   // chunks per thread, blockDim apart (coalesced)
+    const int64_t base = ((int64_t)blockIdx.x * (blockDim.x * U) + threadIdx.x) * W;
+    float p[U][W], g[U][W], mi[U][W], vi[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t i0 = base + (int64_t)u * blockDim.x * W;
+        if (i0 >= n) continue;
+        if (VEC4) {
+            const float4 P = ld_stream4(param + i0), Gd = ld_stream4(grad + i0), M = ld_stream4(m + i0), V = ld_stream4(v + i0);
+            p[u][0] = P.x; p[u][W > 1 ? 1 : 0] = P.y; p[u][W > 1 ? 2 : 0] = P.z; p[u][W > 1 ? 3 : 0] = P.w;
+            g[u][0] = Gd.x; g[u][W > 1 ? 1 : 0] = Gd.y; g[u][W > 1 ? 2 : 0] = Gd.z; g[u][W > 1 ? 3 : 0] = Gd.w;
+            mi[u][0] = M.x; mi[u][W > 1 ? 1 : 0] = M.y; mi[u][W > 1 ? 2 : 0] = M.z; mi[u][W > 1 ? 3 : 0] = M.w;
+            vi[u][0] = V.x; vi[u][W > 1 ? 1 : 0] = V.y; vi[u][W > 1 ? 2 : 0] = V.z; vi[u][W > 1 ? 3 : 0] = V.w;
+        } else {
+            p[u][0] = param[i0];
+            g[u][0] = grad[i0];
+            mi[u][0] = m[i0];
+            vi[u][0] = v[i0];
+        }
     }
 #pragma unroll
-    for (int k = 0; k < W; ++k) {
-        const int64_t i = i0 + k;
+    for (int u = 0; u < U; ++u) {
+        const int64_t i0 = base + (int64_t)u * blockDim.x * W;
+        if (i0 >= n) continue;
+        // group and position inside its lr period, once per chunk (groups are 16-B aligned, but a period need not be:
+        // the position is advanced per element)
         int gi = 0;
-        while (gi < G - 1 && i >= s_ends[gi]) ++gi;
-        float lr = s_lr[gi];
-        if (s_period[gi] > 0) {
-            const int64_t start = gi > 0 ? s_ends[gi - 1] : 0;
-            if ((int)((i - start) % s_period[gi]) >= s_split[gi]) lr = s_lr_alt[gi];
+        while (gi < G - 1 && i0 >= s_ends[gi]) ++gi;
+        int period = s_period[gi], pos = 0;
+        if (period > 0) pos = (int)((uint64_t)(i0 - (gi > 0 ? s_ends[gi - 1] : 0)) % (uint32_t)period);
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            if (W > 1 && i0 + k >= s_ends[gi] && gi < G - 1) {  // chunk straddles a group boundary (unaligned callers only)
+                ++gi;
+                period = s_period[gi];
+                pos = 0;
+            }
+            const float lr = (period > 0 && pos >= s_split[gi]) ? s_lr_alt[gi] : s_lr[gi];
+            if (period > 0 && ++pos == period) pos = 0;
+            mi[u][k] = beta1 * mi[u][k] + (1.0f - beta1) * g[u][k];
+            vi[u][k] = beta2 * vi[u][k] + (1.0f - beta2) * g[u][k] * g[u][k];
+            const float denom = sqrtf(vi[u][k]) * inv_bias2_sqrt + eps;
+            p[u][k] -= (lr * inv_bias1) * (mi[u][k] / denom);
         }
-        mi[k] = beta1 * mi[k] + (1.0f - beta1) * g[k];
-        vi[k] = beta2 * vi[k] + (1.0f - beta2) * g[k] * g[k];
-        const float denom = sqrtf(vi[k]) * inv_bias2_sqrt + eps;
-        p[k] -= (lr * inv_bias1) * (mi[k] / denom);
-    }
-    if (VEC4) {
-        *reinterpret_cast<float4*>(param + i0) = make_float4(p[0], p[W > 1 ? 1 : 0], p[W > 1 ? 2 : 0], p[W > 1 ? 3 : 0]);
-        *reinterpret_cast<float4*>(m + i0) = make_float4(mi[0], mi[W > 1 ? 1 : 0], mi[W > 1 ? 2 : 0], mi[W > 1 ? 3 : 0]);
-        *reinterpret_cast<float4*>(v + i0) = make_float4(vi[0], vi[W > 1 ? 1 : 0], vi[W > 1 ? 2 : 0], vi[W > 1 ? 3 : 0]);
-    } else {
-        param[i0] = p[0];
-        m[i0] = mi[0];
-        v[i0] = vi[0];
+        if (VEC4) {
+            st_stream4(param + i0, make_float4(p[u][0], p[u][W > 1 ? 1 : 0], p[u][W > 1 ? 2 : 0], p[u][W > 1 ? 3 : 0]));
+            st_stream4(m + i0, make_float4(mi[u][0], mi[u][W > 1 ? 1 : 0], mi[u][W > 1 ? 2 : 0], mi[u][W > 1 ? 3 : 0]));
+            st_stream4(v + i0, make_float4(vi[u][0], vi[u][W > 1 ? 1 : 0], vi[u][W > 1 ? 2 : 0], vi[u][W > 1 ? 3 : 0]));
+        } else {
+            param[i0] = p[u][0];
+            m[i0] = mi[u][0];
+            v[i0] = vi[u][0];
+        }
     }
 }
 
@@ -326,7 +344,7 @@ extern "C" int qed_adam_arena(int64_t n, float* param, const float* grad, float*
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool vec = (n % 4 == 0) && al16(param) && al16(grad) && al16(exp_avg) && al16(exp_avg_sq);
     if (vec) {
-        const int64_t threads = n / 4;
+        const int64_t threads = (n / 4 + 1) / 2;  // two float4 per thread
         adam_arena_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group,
                                                                                      lr_alt_by_group, group_period, group_split, (float)beta1,
                                                                                      (float)beta2, (float)eps, inv_bias1, inv_bias2_sqrt);
