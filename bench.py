@@ -12,9 +12,14 @@ gradient arena and of the densification statistics (weak scaling).
 
 metric  = fwd+bwd RGB+depth Mpix/s (whole job: N*H*W*K / time, device-timed, max over ranks).
 value   = fused C-ABI pipeline with everything resident in HBM.
-e2e     = the same work through the public `rasterization()` call + torch autograd, with the step's
-          inputs (camera, ground-truth RGB + depth) copied from pinned host memory and the loss read back
-          every step.  The Gaussian parameters are model state and stay resident, as in the reference.
+e2e     = the same work through the public API a qed-splatter maintainer binds: `rasterization()`
+          (gsplat surface, torch autograd) + `depth_supervised_loss()` (model.py:295-306, 73-118 as one autograd op;
+          `--torch-loss` writes those lines with torch ops as the reference does) + `backward()`, with the step's
+          inputs (camera, ground-truth RGB + depth) copied from pinned host memory and the loss read back every
+          step.  The Gaussian parameters are model state and stay resident, as in the reference.  For N>1 the
+          parameter gradients are views of one flat bucket (DDP's gradient_as_bucket_view) -> one all-reduce.
+train   = full trainer iterations/s (trainer.SplatTrainer: 0.8 L1 + 0.2 (1-SSIM) + 0.2 depth-L1, Adam, strategy
+          statistics, pipelined gradient all-reduce) -- the second half of BASELINE.json's metric.
 --impl reference = the CPU arm: the oracle (`oracle/`, a port — the reference's own arithmetic lives in the
           un-vendored gsplat and cannot be run here) on the host cores on a bounded 1/16 sample.
 """

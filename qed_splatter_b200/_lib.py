@@ -104,9 +104,14 @@ def ptr(t) -> c_void_p:
 
 
 def current_stream() -> c_void_p:
+    """Raw handle of torch's current stream on the current device.  (torch.cuda.current_stream() builds a Stream
+    object and costs ~20 us per call -- seven calls per step were 8 % of the host side of a 1080p step.)"""
     import torch
 
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    try:
+        return c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    except AttributeError:  # private binding moved: fall back to the public, slower path
+        return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def require_cuda(*tensors) -> None:
