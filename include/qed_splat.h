@@ -44,6 +44,10 @@ int qed_abi_version(void);
 /* Static string for a return code of any function here (cudaGetErrorString for > 0). */
 const char* qed_error_string(int code);
 
+/* `activations` bits of qed_project_fwd / qed_project_bwd */
+#define QED_ACT_LOG_SCALES 1
+#define QED_ACT_LOGIT_OPACITIES 2
+
 /* ------------------------------------------------------------------------------------------------
  * (a) fused projection + EWA 2-D covariance + SH colour + tile count
  * replaces: gsplat fully_fused_projection (fwd) + spherical_harmonics (fwd) + the
@@ -53,6 +57,10 @@ const char* qed_error_string(int code);
  *           colors, viewmats, Ks, width, height, near_plane, far_plane, sh_degree, rasterize_mode).
  *
  *  means[N,3] quats[N,4](wxyz) scales[N,3] opacities[N]
+ *  activations: 0 = scales / opacities are the activated values gsplat takes; QED_ACT_LOG_SCALES and/or
+ *             QED_ACT_LOGIT_OPACITIES = they are the stored parameters and exp / sigmoid
+ *             (qed_splatter/model.py:269-271) are applied inside the kernel; qed_project_bwd then returns the
+ *             gradients with respect to the stored parameters (chain rule folded in).
  *  colors_in: sh_degree >= 0 : SH coefficients [N,K,3], uses the first (sh_degree+1)^2 of K
  *             sh_degree <  0 : colours [N,3] (colors_per_camera=0) or [C,N,3] (=1); ignored when n_color==0
  *  viewmats[C,4,4] world->camera, Ks[C,3,3]
@@ -65,7 +73,7 @@ const char* qed_error_string(int code);
  *  Culled entries (radii == 0) get zeros everywhere.
  */
 int qed_project_fwd(int C, int N, const float* means, const float* quats, const float* scales,
-                    const float* opacities, const float* colors_in, int K, int sh_degree,
+                    const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
                     int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
                     float eps2d, float near_plane, float far_plane, float radius_clip,
                     int calc_compensations, int tile_size, int n_color, int append_depth,
@@ -84,7 +92,7 @@ int qed_project_fwd(int C, int N, const float* means, const float* quats, const 
  *  Gradients are summed over the C cameras in a fixed order (deterministic).
  */
 int qed_project_bwd(int C, int N, const float* means, const float* quats, const float* scales,
-                    const float* opacities, const float* colors_in, int K, int sh_degree,
+                    const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
                     int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
                     float eps2d, int calc_compensations, int n_color, int append_depth,
                     const int32_t* radii, const float* conics, const float* compensations,

@@ -29,7 +29,7 @@ struct CamB {
 struct ProjBwdParams {
     int C, N, K, sh_degree, colors_per_camera, width, height;
     float eps2d;
-    int calc_comp, n_color, append_depth;
+    int calc_comp, n_color, append_depth, activations;
     const float *means, *quats, *scales, *opacities, *colors_in, *viewmats, *Ks;
     const int32_t* radii;
     const float *conics, *comps;
@@ -163,6 +163,12 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         s1 = p.scales[n * 3 + 1];
         s2 = p.scales[n * 3 + 2];
         opac = p.opacities ? p.opacities[n] : 0.0f;
+        if (p.activations & QED_ACT_LOG_SCALES) {
+            s0 = expf(s0);
+            s1 = expf(s1);
+            s2 = expf(s2);
+        }
+        if ((p.activations & QED_ACT_LOGIT_OPACITIES) && p.opacities) opac = 1.0f / (1.0f + expf(-opac));
         qn = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
         qw = q.x / qn;
         qx = q.y / qn;
@@ -463,6 +469,12 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         vqp[1] = vq.y;
         vqp[2] = vq.z;
         vqp[3] = vq.w;
+        if (p.activations & QED_ACT_LOG_SCALES) {  // d/d log s = s d/ds
+            vs0 *= s0;
+            vs1 *= s1;
+            vs2 *= s2;
+        }
+        if (p.activations & QED_ACT_LOGIT_OPACITIES) vopac *= opac * (1.0f - opac);  // sigmoid'
         p.v_scales[n * 3 + 0] = vs0;
         p.v_scales[n * 3 + 1] = vs1;
         p.v_scales[n * 3 + 2] = vs2;
@@ -503,7 +515,7 @@ static int launch_project_bwd(const ProjBwdParams& p, cudaStream_t stream) {
 using namespace qed;
 
 extern "C" int qed_project_bwd(int C, int N, const float* means, const float* quats, const float* scales,
-                               const float* opacities, const float* colors_in, int K, int sh_degree,
+                               const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
                                int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
                                float eps2d, int calc_compensations, int n_color, int append_depth,
                                const int32_t* radii, const float* conics, const float* compensations,
@@ -533,6 +545,7 @@ extern "C" int qed_project_bwd(int C, int N, const float* means, const float* qu
     p.height = height;
     p.eps2d = eps2d;
     p.calc_comp = calc_compensations;
+    p.activations = activations;
     p.n_color = n_color;
     p.append_depth = append_depth;
     p.means = means;

@@ -32,7 +32,7 @@ static_assert(sizeof(Cam) == kCamFloats * 4, "Cam layout");
 struct ProjFwdParams {
     int C, c0, Cc, N, K, sh_degree, colors_per_camera, width, height;
     float eps2d, near_plane, far_plane, radius_clip;
-    int calc_comp;
+    int calc_comp, activations;
     float tile_size;
     int tile_w, tile_h, n_color, append_depth;
     const float *means, *quats, *scales, *opacities, *colors_in, *viewmats, *Ks;
@@ -155,6 +155,13 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
         float w = p.quats[n * 4 + 0], x = p.quats[n * 4 + 1], y = p.quats[n * 4 + 2], z = p.quats[n * 4 + 3];
         float s0 = p.scales[n * 3 + 0], s1 = p.scales[n * 3 + 1], s2 = p.scales[n * 3 + 2];
         opac = p.opacities ? p.opacities[n] : 0.0f;
+        // parameters as the model stores them (qed_splatter/model.py:269-271): exp / sigmoid folded in
+        if (p.activations & QED_ACT_LOG_SCALES) {
+            s0 = expf(s0);
+            s1 = expf(s1);
+            s2 = expf(s2);
+        }
+        if ((p.activations & QED_ACT_LOGIT_OPACITIES) && p.opacities) opac = dvd(1.0f, add(1.0f, expf(-opac)));
         float nrm = fmaxf(sqr(add(add(add(mul(w, w), mul(x, x)), mul(y, y)), mul(z, z))), 1e-12f);
         w = dvd(w, nrm);
         x = dvd(x, nrm);
@@ -374,7 +381,7 @@ static int launch_project_fwd(const ProjFwdParams& p, cudaStream_t stream) {
 using namespace qed;
 
 extern "C" int qed_project_fwd(int C, int N, const float* means, const float* quats, const float* scales,
-                               const float* opacities, const float* colors_in, int K, int sh_degree,
+                               const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
                                int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
                                float eps2d, float near_plane, float far_plane, float radius_clip,
                                int calc_compensations, int tile_size, int n_color, int append_depth,
@@ -409,6 +416,7 @@ extern "C" int qed_project_fwd(int C, int N, const float* means, const float* qu
     p.far_plane = far_plane;
     p.radius_clip = radius_clip;
     p.calc_comp = calc_compensations;
+    p.activations = activations;
     p.tile_size = (float)tile_size;
     p.tile_w = (width + tile_size - 1) / tile_size;
     p.tile_h = (height + tile_size - 1) / tile_size;

@@ -84,7 +84,7 @@ class _ProjectGaussians(torch.autograd.Function):
         opac_out = torch.empty(C, N, device=dev)
         tiles = torch.empty(C, N, dtype=torch.int32, device=dev)
         geom = torch.empty(C, N, GEOM_FLOATS, device=dev)
-        check(lib.qed_project_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors) if n_color else None,
+        check(lib.qed_project_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), 0, ptr(colors) if n_color else None,
                                   K, sh_degree, per_cam, ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane,
                                   far_plane, radius_clip, int(calc_compensations), tile_size, n_color, append_depth,
                                   ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(colors_out),
@@ -113,7 +113,7 @@ class _ProjectGaussians(torch.autograd.Function):
         v_scales = torch.empty_like(scales)
         v_opacities = torch.empty_like(opacities) if opacities is not None else None
         v_colors_in = torch.empty_like(colors) if n_color else None
-        check(lib.qed_project_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(colors) if n_color else None,
+        check(lib.qed_project_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), 0, ptr(colors) if n_color else None,
                                   K, sh_degree, per_cam, ptr(viewmats), ptr(Ks), width, height, eps2d, int(calc_comp),
                                   n_color, append_depth, ptr(radii), ptr(conics), ptr(comps),
                                   ptr(_f32c(v_means2d)), ptr(_f32c(v_depths)), ptr(_f32c(v_conics)), ptr(_f32c(v_colors)),

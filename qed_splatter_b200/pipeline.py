@@ -36,6 +36,9 @@ class StepOutput:
     n_visible: Optional[int] = None
 
 
+ACT_LOG_SCALES, ACT_LOGIT_OPACITIES = 1, 2  # `activations` bits (include/qed_splat.h)
+
+
 class FusedSplatStep:
     """Holds reusable device buffers; `forward()` renders, `step()` renders + loss + full backward."""
 
@@ -80,7 +83,9 @@ class FusedSplatStep:
     @torch.no_grad()
     def forward(self, means, quats, scales, opacities, sh, viewmats, Ks, width: int, height: int, sh_degree: int,
                 render_mode: str = "RGB+ED", rasterize_mode: str = "classic", near_plane: float = 0.01,
-                far_plane: float = 1e10, eps2d: float = 0.3, backgrounds: Optional[Tensor] = None):
+                far_plane: float = 1e10, eps2d: float = 0.3, backgrounds: Optional[Tensor] = None, activations: int = 0):
+        """`activations` (ACT_LOG_SCALES | ACT_LOGIT_OPACITIES): `scales` / `opacities` are the stored parameters; exp /
+        sigmoid (qed_splatter/model.py:269-271) and their chain rule run inside the projection kernels."""
         lib, stream = self.lib, current_stream()
         _lib.require_cuda(means, quats, scales, opacities, sh, viewmats, Ks)
         self._mark("begin")
@@ -105,7 +110,7 @@ class FusedSplatStep:
         opac = self._get("opac", (C, N))
         tiles = self._get("tiles", (C, N), torch.int32)
         geom = self._get("geom", (C, N, 8))
-        check(lib.qed_project_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(sh) if want_rgb else None, K, deg,
+        check(lib.qed_project_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), int(activations), ptr(sh) if want_rgb else None, K, deg,
                                   int(want_rgb and sh_degree is None and sh.dim() == 3), ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane,
                                   far_plane, 0.0, int(comp), tile, n_color, append, ptr(radii), ptr(means2d), ptr(depths),
                                   ptr(conics), ptr(comps), ptr(colors), ptr(opac), ptr(tiles), ptr(geom), stream), "qed_project_fwd")
@@ -170,7 +175,7 @@ class FusedSplatStep:
         check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets), int(exact),
                                  ptr(flat) if M else None, normalize, ptr(render), ptr(alphas), ptr(last_ids), stream), "qed_raster_fwd")
         self._mark("raster_fwd")
-        self._fwd = dict(C=C, N=N, D=D, M=M, exact=exact, K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
+        self._fwd = dict(C=C, N=N, D=D, M=M, exact=exact, activations=int(activations), K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
                          th=th, width=width, height=height, eps2d=eps2d, radii=radii, conics=conics, comps=comps, colors=colors,
                          geom=geom, offsets=offsets, flat=flat, render=render, alphas=alphas, last_ids=last_ids, backgrounds=backgrounds,
                          inputs=(means, quats, scales, opacities, sh, viewmats, Ks))
@@ -217,7 +222,7 @@ class FusedSplatStep:
         for k, (n0, n1) in enumerate(bounds):
             # C == 1 when chunked: flat index == n, so a range is just a pointer offset on every [N,...] / [1,N,...] array
             sl = slice(n0, n1)
-            check(lib.qed_project_bwd(C, n1 - n0, ptr(means[sl]), ptr(quats[sl]), ptr(scales[sl]), ptr(opacities[sl]),
+            check(lib.qed_project_bwd(C, n1 - n0, ptr(means[sl]), ptr(quats[sl]), ptr(scales[sl]), ptr(opacities[sl]), f["activations"],
                                       ptr(sh[sl]) if has_sh else None, f["K"], f["deg"], 0, ptr(viewmats), ptr(Ks), f["width"], f["height"],
                                       f["eps2d"], int(f["comp"]), f["n_color"], f["append"],
                                       ptr(f["radii"][:, sl] if len(bounds) > 1 else f["radii"]),
@@ -237,14 +242,15 @@ class FusedSplatStep:
     def step(self, means, quats, scales, opacities, sh, viewmats, Ks, width: int, height: int, sh_degree: int,
              gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, render_mode: str = "RGB+ED", rgb_weight: float = 0.8,
              depth_lambda: float = 0.2, grad_scale: float = 1.0, rasterize_mode: str = "classic",
-             grad_out: Optional[Dict[str, Tensor]] = None, ssim_lambda: float = 0.0, n_chunks: int = 1, on_chunk=None) -> StepOutput:
+             grad_out: Optional[Dict[str, Tensor]] = None, ssim_lambda: float = 0.0, n_chunks: int = 1, on_chunk=None,
+             activations: int = 0) -> StepOutput:
         """`render_mode` RGB+ED (north_star) or RGB+D (what qed_splatter/model.py:257 passes).
         loss = rgb_weight * L1 + ssim_lambda * (1 - SSIM) + depth_lambda * masked depth-L1 (splatfacto: 0.8 / 0.2 / 0.2)."""
         assert render_mode in ("RGB+D", "RGB+ED")
         lib, stream = self.lib, current_stream()
         self._prezero = self.sort_impl == "two_level"
         render, alphas = self.forward(means, quats, scales, opacities, sh, viewmats, Ks, width, height, sh_degree, render_mode,
-                                      rasterize_mode)
+                                      rasterize_mode, activations=activations)
         self._prezeroed, self._prezero = self._prezero, False
         C = viewmats.shape[0]
         if self._stats is None or self._stats.numel() < C * 8:

@@ -390,9 +390,8 @@ class SplatTrainer:
         total = total_views or C * self.world
         pv = a.views(a.param)
         gv = a.views(a.grad)
-        scales = torch.exp(pv["scales"])
-        opac = torch.sigmoid(pv["opacities"])
-        tmp = {"means": gv["means"], "quats": gv["quats"], "sh": gv["sh"], "scales": torch.empty_like(scales), "opacities": torch.empty_like(opac)}
+        # the stored parameters go straight in: exp / sigmoid (model.py:269-271) and their chain rule run inside the
+        # projection kernels, the gradients land in the arena
         pipelined = self.world > 1 and C == 1 and c.comm_chunks > 1
         sh0 = a.offsets["sh"][0]
         works = []
@@ -404,14 +403,12 @@ class SplatTrainer:
             lo, hi = sh0 + 48 * n0, sh0 + 48 * n1
             works.append((dist.all_reduce(a.grad[lo:hi], group=self.pg, async_op=True), lo, hi))
 
-        out = self._fused.step(pv["means"], pv["quats"], scales, opac, pv["sh"], viewmats, Ks, width, height, self.sh_degree_to_use(),
+        out = self._fused.step(pv["means"], pv["quats"], pv["scales"], pv["opacities"], pv["sh"], viewmats, Ks, width, height, self.sh_degree_to_use(),
                                gt_rgb, gt_depth, background, render_mode=c.render_mode, rgb_weight=1.0 - c.ssim_lambda,
-                               depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, grad_out=tmp,
+                               depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, grad_out=gv,
+                               activations=3,  # ACT_LOG_SCALES | ACT_LOGIT_OPACITIES (pipeline.py / include/qed_splat.h)
                                ssim_lambda=c.ssim_lambda, n_chunks=c.comm_chunks if (pipelined and c.chunk_project_bwd) else 1,
                                on_chunk=on_chunk if (pipelined and c.chunk_project_bwd) else None)
-        # activations' chain rule straight into the arena (model.py:269-271: exp, sigmoid)
-        torch.mul(tmp["scales"], scales, out=gv["scales"])
-        torch.mul(tmp["opacities"], opac * (1.0 - opac), out=gv["opacities"])
         self.accumulate_stats(out.packed_grads, out.radii, width, height, packed=True, n_cameras=total)
         if pipelined:
             import torch.distributed as dist

@@ -201,6 +201,24 @@ def test_exact_tile_lists(cuda, size, scale):
     assert dropped == a["n"] - b["n"]
 
 
+def test_folded_activations_match_torch_chain_rule(cuda):
+    """`activations` = log-scales + logit-opacities inside the projection kernels (model.py:269-271) == torch exp / sigmoid
+    outside + their chain rule: same image bit for bit, same gradients."""
+    s = scene_s0(N=3000, C=2, size=96).to(cuda)
+    bg = torch.tensor([0.2, 0.2, 0.2], device=cuda)
+    log_s, logit_o = torch.log(s.scales), torch.logit(s.opacities.clamp(1e-4, 1 - 1e-4))
+    sc, op = torch.exp(log_s), torch.sigmoid(logit_o)
+    fs = FusedSplatStep(cuda)
+    ref = fs.step(s.means, s.quats, sc, op, s.sh, s.viewmats, s.Ks, s.width, s.height, 3, s.gt_rgb, s.gt_depth, bg)
+    ref_render, ref_g = ref.render.clone(), {k: v.clone() for k, v in ref.grads.items()}
+    out = fs.step(s.means, s.quats, log_s, logit_o, s.sh, s.viewmats, s.Ks, s.width, s.height, 3, s.gt_rgb, s.gt_depth, bg, activations=3)
+    assert torch.equal(out.render, ref_render)
+    want = dict(ref_g, scales=ref_g["scales"] * sc, opacities=ref_g["opacities"] * op * (1 - op))
+    for k in NAMES:
+        scale = float(want[k].abs().mean()) + 1e-12
+        assert_close_frac(out.grads[k], want[k], 1e-4, 1e-5 * scale, 1e-3, f"v_{k}")
+
+
 def test_view_sharding_equals_single_rank(cuda):
     """2 'ranks' x 1 view with grad_scale = 1/2, summed (what the all-reduce does) == 1 rank x 2 views."""
     s = scene_s0(N=3000, C=2, size=96).to(cuda)
