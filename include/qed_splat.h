@@ -252,6 +252,22 @@ int qed_strategy_update(int C, int N, const float* packed_grads, int use_absgrad
                         int width, int height, int n_cameras, float* grad2d, float* count, float* radii_max,
                         qed_stream_t stream);
 
+/* gsplat DefaultStrategy._grow_gs / _prune_gs data movement (ops.duplicate / ops.split / ops.remove + the optimizer-
+ * state surgery) as ONE gather over the flat arenas.  The caller decides, per
+ * Gaussian of the NEW set, where it comes from; this builds the new parameter / exp_avg / exp_avg_sq arenas:
+ *   src[j]        row of the old set that output j copies,
+ *   fresh[j] != 0 its Adam moments start at zero (duplicates and split children), else they are copied,
+ *   child_row[j]  >= 0: output j is a split child whose mean / log-scale come from child_means / child_scales[row]
+ *                 (NULL or -1: copied from src like everything else).
+ * Arena layout (old and new, for their own N): group-major  means 3N | quats 4N | log-scales 3N | logit-opacities N |
+ * SH 48N, every group starting on a 16-byte boundary; old_group_starts / new_group_starts = the 5 group starts in
+ * floats (HOST arrays).  The SH group start must be a multiple of 4 floats.  Padding floats are left untouched. */
+int qed_arena_gather(int64_t n_new, const int32_t* src, const uint8_t* fresh, const int32_t* child_row,
+                     const float* child_means, const float* child_scales, const float* old_param,
+                     const float* old_exp_avg, const float* old_exp_avg_sq, const int64_t* old_group_starts,
+                     float* new_param, float* new_exp_avg, float* new_exp_avg_sq, const int64_t* new_group_starts,
+                     qed_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

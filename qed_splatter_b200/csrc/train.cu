@@ -373,6 +373,76 @@ extern "C" int qed_strategy_update(int C, int N, const float* packed_grads, int 
     return QED_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// densify / prune as one gather: 16 lanes per output Gaussian -- lanes 0..11 move the SH row (12 x float4 = 192 B,
+// coalesced), lanes 12..15 the means / quats / log-scales / logit-opacity -- for the parameter arena and both
+// Adam-moment arenas.  ~3 x 236 B read + written per Gaussian, nothing else.
+// ------------------------------------------------------------------------------------------------
+struct ArenaStarts {
+    int64_t g[5];
+};
+
+__global__ void __launch_bounds__(256) arena_gather_kernel(int64_t n_new, const int32_t* __restrict__ src, const uint8_t* __restrict__ fresh,
+                                                           const int32_t* __restrict__ child_row, const float* __restrict__ child_means,
+                                                           const float* __restrict__ child_scales, const float* __restrict__ op,
+                                                           const float* __restrict__ om, const float* __restrict__ ov, ArenaStarts os,
+                                                           float* __restrict__ np, float* __restrict__ nm, float* __restrict__ nv, ArenaStarts ns) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t j = t >> 4;
+    const int l = (int)(t & 15);
+    if (j >= n_new) return;
+    const int64_t s = src[j];
+    const bool fr = fresh && fresh[j];
+    const int cr = child_row ? child_row[j] : -1;
+    if (l < 12) {
+        const int64_t so = os.g[4] + s * 48 + l * 4, d = ns.g[4] + j * 48 + l * 4;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(np + d) = *reinterpret_cast<const float4*>(op + so);
+        *reinterpret_cast<float4*>(nm + d) = fr ? z : *reinterpret_cast<const float4*>(om + so);
+        *reinterpret_cast<float4*>(nv + d) = fr ? z : *reinterpret_cast<const float4*>(ov + so);
+        return;
+    }
+    const int grp = l - 12;                        // 0 means, 1 quats, 2 log-scales, 3 logit-opacity
+    const int dim = grp == 1 ? 4 : (grp == 3 ? 1 : 3);
+    const int64_t so = os.g[grp] + s * dim, d = ns.g[grp] + j * dim;
+    const float* over = (cr >= 0 && grp == 0) ? child_means + (int64_t)cr * 3 : ((cr >= 0 && grp == 2) ? child_scales + (int64_t)cr * 3 : nullptr);
+    for (int k = 0; k < dim; ++k) {
+        np[d + k] = over ? over[k] : op[so + k];
+        nm[d + k] = fr ? 0.0f : om[so + k];
+        nv[d + k] = fr ? 0.0f : ov[so + k];
+    }
+}
+
+extern "C" int qed_arena_gather(int64_t n_new, const int32_t* src, const uint8_t* fresh, const int32_t* child_row,
+                                const float* child_means, const float* child_scales, const float* old_param,
+                                const float* old_exp_avg, const float* old_exp_avg_sq, const int64_t* old_group_starts,
+                                float* new_param, float* new_exp_avg, float* new_exp_avg_sq, const int64_t* new_group_starts,
+                                qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_new < 0) return QED_ERR_BAD_ARG;
+    if (n_new == 0) return QED_OK;
+    if (!src || !old_param || !old_exp_avg || !old_exp_avg_sq || !old_group_starts || !new_param || !new_exp_avg || !new_exp_avg_sq ||
+        !new_group_starts)
+        return QED_ERR_BAD_ARG;
+    if (child_row && (!child_means || !child_scales)) return QED_ERR_BAD_ARG;
+    if (n_new > 0x7fffffffLL) return QED_ERR_UNSUPPORTED;
+    ArenaStarts os, ns;
+    for (int i = 0; i < 5; ++i) {
+        os.g[i] = old_group_starts[i];
+        ns.g[i] = new_group_starts[i];
+    }
+    auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+    if ((os.g[4] & 3) || (ns.g[4] & 3) || mis(old_param) || mis(old_exp_avg) || mis(old_exp_avg_sq) || mis(new_param) || mis(new_exp_avg) ||
+        mis(new_exp_avg_sq))
+        return QED_ERR_BAD_ARG;  // float4 access to the SH rows
+    const int64_t threads = n_new * 16;
+    arena_gather_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n_new, src, fresh, child_row, child_means, child_scales, old_param,
+                                                                             old_exp_avg, old_exp_avg_sq, os, new_param, new_exp_avg,
+                                                                             new_exp_avg_sq, ns);
+    QED_LAUNCH_CHECK();
+    return QED_OK;
+}
+
 extern "C" int qed_abi_version(void) { return QED_ABI_VERSION; }
 
 extern "C" const char* qed_error_string(int code) {

@@ -219,6 +219,39 @@ def test_folded_activations_match_torch_chain_rule(cuda):
         assert_close_frac(out.grads[k], want[k], 1e-4, 1e-5 * scale, 1e-3, f"v_{k}")
 
 
+@pytest.mark.parametrize("step", [600, 3100, 4100])
+def test_fused_densify_equals_torch_densify(cuda, step):
+    """`qed_arena_gather` (one gather over the three arenas, decisions on index tensors) builds exactly the arenas the
+    torch cat / index formulation of gsplat's duplicate / split / remove builds: same order, same bits, same moments.
+    step 600: grow only; 3100: + prune by scale and screen size; 4100: screen-size rules off."""
+    from qed_splatter_b200.trainer import GaussianArena, StrategyState, TrainConfig, refine_gaussians
+
+    N = 40_000
+    g = torch.Generator().manual_seed(step)
+    mk = lambda *shape: torch.randn(*shape, generator=g)
+    means, quats, sh = mk(N, 3), mk(N, 4), mk(N, 16, 3) * 0.1
+    log_s = torch.rand(N, 3, generator=g) * 5.0 - 6.0          # exp: 0.0025 .. 0.37 (some above the 0.5 cull only after max)
+    log_s[:200] += 3.0                                         # a few huge ones (pruned by scale once that rule is on)
+    logit_o = mk(N) * 3.0                                      # some below sigmoid^-1(0.005)
+    res = {}
+    for impl in ("torch", "fused"):
+        arena = GaussianArena(means.to(cuda), quats.to(cuda), log_s.to(cuda), logit_o.to(cuda), sh.to(cuda))
+        gg = torch.Generator().manual_seed(7)
+        arena.exp_avg.copy_(torch.randn(arena.exp_avg.numel(), generator=gg).to(cuda))
+        arena.exp_avg_sq.copy_(torch.rand(arena.exp_avg_sq.numel(), generator=gg).to(cuda))
+        st = StrategyState.zeros(N, cuda)
+        st.count = torch.randint(0, 5, (N,), generator=gg).float().to(cuda)
+        st.grad2d = (torch.rand(N, generator=gg) * 0.004).to(cuda)   # mean gradient straddles the 0.0005 threshold
+        st.radii = (torch.rand(N, generator=gg) * 0.2).to(cuda)      # some above split (0.05) / cull (0.15) screen sizes
+        info = refine_gaussians(arena, st, TrainConfig(), step, torch.Generator().manual_seed(99), impl=impl)
+        res[impl] = (info, arena)
+    (ia, a), (ib, b) = res["torch"], res["fused"]
+    assert ia == ib and ia["n_dupli"] > 0 and ia["n_split"] > 0 and ia["n_prune"] > 0, (ia, ib)
+    assert a.N == b.N and a.offsets == b.offsets and torch.equal(a.group_ends, b.group_ends)
+    for name in ("param", "exp_avg", "exp_avg_sq", "grad"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+
+
 def test_view_sharding_equals_single_rank(cuda):
     """2 'ranks' x 1 view with grad_scale = 1/2, summed (what the all-reduce does) == 1 rank x 2 views."""
     s = scene_s0(N=3000, C=2, size=96).to(cuda)
