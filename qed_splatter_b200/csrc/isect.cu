@@ -218,7 +218,7 @@ extern "C" int qed_sort_pairs(int64_t n, int64_t* keys_in, int32_t* vals_in, int
 namespace qed {
 
 struct PrepareLayout {
-    size_t scan_ws, cumflag, keys[3], vals[3], hist, cum2, total;
+    size_t scan_ws, keys[3], vals[3], hist, cum2, total;
 };
 
 static PrepareLayout prepare_layout(int64_t CN) {
@@ -230,7 +230,6 @@ static PrepareLayout prepare_layout(int64_t CN) {
         return r;
     };
     L.scan_ws = take(scan_workspace_bytes(CN));
-    L.cumflag = take((size_t)CN * 8);
     for (int i = 0; i < 3; ++i) L.keys[i] = take((size_t)CN * 8);
     for (int i = 0; i < 3; ++i) L.vals[i] = take((size_t)CN * 4);
     L.hist = take(radix_hist_bytes(CN));
@@ -239,20 +238,21 @@ static PrepareLayout prepare_layout(int64_t CN) {
     return L;
 }
 
+// Sink of the visible-flag scan: the compaction IS the final scan phase (entry idx with flag 1 and inclusive count c
+// goes to slot c - 1), so no cumulative-flag array is written and no separate compaction kernel runs.
 template <typename KeyT>
-__global__ void compact_visible_kernel(int64_t CN, int N, const int32_t* __restrict__ tiles, const int64_t* __restrict__ cumflag,
-                                       const float* __restrict__ depths, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= CN) return;
-    if (tiles[idx] <= 0) return;
-    const int64_t j = cumflag[idx] - 1;
-    const uint32_t db = (uint32_t)__float_as_int(depths[idx]);
-    if (sizeof(KeyT) == 8)
-        keys[j] = (KeyT)(((uint64_t)(idx / N) << 32) | db);
-    else
-        keys[j] = (KeyT)db;
-    vals[j] = (int32_t)idx;
-}
+struct CompactVisibleSink {
+    int N;
+    const float* depths;
+    KeyT* keys;
+    int32_t* vals;
+    __device__ __forceinline__ void operator()(int64_t idx, int32_t flag, int64_t inc) const {
+        if (!flag) return;
+        const uint32_t db = (uint32_t)__float_as_int(depths[idx]);
+        keys[inc - 1] = sizeof(KeyT) == 8 ? (KeyT)(((uint64_t)(idx / N) << 32) | db) : (KeyT)db;
+        vals[inc - 1] = (int32_t)idx;
+    }
+};
 
 // Entry-parallel emission in depth order.  Every block owns kEmitTile consecutive OUTPUT entries, so the
 // work is balanced no matter how the tile counts are distributed (the nearest Gaussians are adjacent in
@@ -501,29 +501,28 @@ extern "C" int qed_isect_prepare(int C, int N, const float* depths, const int32_
         const PrepareLayout L = prepare_layout(CN);
         if (workspace_bytes < L.total) return QED_ERR_WORKSPACE;
         char* ws = reinterpret_cast<char*>(workspace);
-        int64_t* cumflag = reinterpret_cast<int64_t*>(ws + L.cumflag);
         int32_t* vals0 = reinterpret_cast<int32_t*>(ws + L.vals[0]);
         int32_t* vals1 = reinterpret_cast<int32_t*>(ws + L.vals[1]);
         int32_t* vals2 = reinterpret_cast<int32_t*>(ws + L.vals[2]);
         int64_t* cum2 = reinterpret_cast<int64_t*>(ws + L.cum2);
-        // 1. ordered compaction of the visible entries (n_visible -> counts_dev[0])
-        int rc = scan_inclusive(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, cumflag, counts_dev, ws + L.scan_ws, stream);
-        if (rc != QED_OK) return rc;
-        const unsigned blocks = (unsigned)((CN + 255) / 256);
-        // 2. stable sort by (camera, depth bits); sorted flat indices land in vals1
+        // 1. ordered compaction of the visible entries (scan of the flags, the compaction being its final phase;
+        //    n_visible -> counts_dev[0]);  2. stable sort by (camera, depth bits): sorted flat indices land in vals1
+        int rc;
         if (C == 1) {
             uint32_t* k0 = reinterpret_cast<uint32_t*>(ws + L.keys[0]);
             uint32_t* k1 = reinterpret_cast<uint32_t*>(ws + L.keys[1]);
             uint32_t* k2 = reinterpret_cast<uint32_t*>(ws + L.keys[2]);
-            compact_visible_kernel<uint32_t><<<blocks, 256, 0, stream>>>(CN, N, tiles_per_gauss, cumflag, depths, k0, vals0);
-            QED_LAUNCH_CHECK();
+            rc = scan_inclusive_to(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, CompactVisibleSink<uint32_t>{N, depths, k0, vals0}, counts_dev,
+                                   ws + L.scan_ws, stream);
+            if (rc != QED_OK) return rc;
             rc = radix_sort_pairs<uint32_t>(CN, counts_dev, k0, vals0, k1, vals1, k2, vals2, ws + L.hist, 32, stream);
         } else {
             uint64_t* k0 = reinterpret_cast<uint64_t*>(ws + L.keys[0]);
             uint64_t* k1 = reinterpret_cast<uint64_t*>(ws + L.keys[1]);
             uint64_t* k2 = reinterpret_cast<uint64_t*>(ws + L.keys[2]);
-            compact_visible_kernel<uint64_t><<<blocks, 256, 0, stream>>>(CN, N, tiles_per_gauss, cumflag, depths, k0, vals0);
-            QED_LAUNCH_CHECK();
+            rc = scan_inclusive_to(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, CompactVisibleSink<uint64_t>{N, depths, k0, vals0}, counts_dev,
+                                   ws + L.scan_ws, stream);
+            if (rc != QED_OK) return rc;
             rc = radix_sort_pairs<uint64_t>(CN, counts_dev, k0, vals0, k1, vals1, k2, vals2, ws + L.hist, 32 + bit_length(C - 1), stream);
         }
         if (rc != QED_OK) return rc;

@@ -85,9 +85,15 @@ __global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int64_t nb, int
     if (threadIdx.x == 0 && total_dev) *total_dev = carry;
 }
 
-template <typename F>
+// output sinks of the final phase: store the inclusive scan, or consume (index, value, inclusive scan) directly
+struct ScanStore {
+    int64_t* out;
+    __device__ __forceinline__ void operator()(int64_t i, int32_t, int64_t inc) const { out[i] = inc; }
+};
+
+template <typename F, typename Sink>
 __global__ void __launch_bounds__(kScanThreads) scan_final_kernel(int64_t n_host, const int64_t* n_dev, F f, const int64_t* __restrict__ block_sums,
-                                                                 int64_t* __restrict__ out) {
+                                                                 Sink sink) {
     __shared__ int64_t sw[kScanThreads / 32 + 1];
     const int64_t n = n_dev ? *n_dev : n_host;
     // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems) of the tile
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_final_kernel(int64_t n_host
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         ex += v[k];
-        if (base + k < n) out[base + k] = ex;
+        if (base + k < n) sink(base + k, v[k], ex);
     }
 }
 
@@ -116,8 +122,9 @@ inline size_t scan_workspace_bytes(int64_t capacity) {
 
 // Inclusive scan of f(0..n) into out (int64); total -> *total_dev.  `capacity` >= n sizes the grid when n
 // is only known on the device (n_dev != nullptr).
-template <typename F>
-inline int scan_inclusive(int64_t capacity, const int64_t* n_dev, F f, int64_t* out, int64_t* total_dev, void* workspace, cudaStream_t stream) {
+// `sink(i, f(i), inclusive_scan(i))` is called for every element in the final phase (ScanStore: write it out).
+template <typename F, typename Sink>
+inline int scan_inclusive_to(int64_t capacity, const int64_t* n_dev, F f, Sink sink, int64_t* total_dev, void* workspace, cudaStream_t stream) {
     int64_t nb = (capacity + kScanTile - 1) / kScanTile;
     if (nb == 0) nb = 1;
     int64_t* sums = reinterpret_cast<int64_t*>(workspace);
@@ -125,9 +132,14 @@ inline int scan_inclusive(int64_t capacity, const int64_t* n_dev, F f, int64_t* 
     QED_LAUNCH_CHECK();
     scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(nb, sums, total_dev);
     QED_LAUNCH_CHECK();
-    scan_final_kernel<F><<<(unsigned)nb, kScanThreads, 0, stream>>>(capacity, n_dev, f, sums, out);
+    scan_final_kernel<F, Sink><<<(unsigned)nb, kScanThreads, 0, stream>>>(capacity, n_dev, f, sums, sink);
     QED_LAUNCH_CHECK();
     return QED_OK;
+}
+
+template <typename F>
+inline int scan_inclusive(int64_t capacity, const int64_t* n_dev, F f, int64_t* out, int64_t* total_dev, void* workspace, cudaStream_t stream) {
+    return scan_inclusive_to(capacity, n_dev, f, ScanStore{out}, total_dev, workspace, stream);
 }
 
 }  // namespace qed
