@@ -304,7 +304,7 @@ def main_ours(args):
 
     # ---- pair counters for the compositing roofline (instrumented launches, outside any timed region) ----
     counters = fs.count_pairs()
-    launches_per_step = fs.launches_per_step + 1 + ((n_chunks - 1) + (n_chunks + 1) if world > 1 else 0)
+    launches_per_step = fs.launches_per_step + ((n_chunks - 1) if world > 1 else 0)  # this library's kernels only (chunked: extra project_bwd launches)
 
     # ---- second half of the metric: train iters/s (full qed-splatter step through trainer.SplatTrainer: render,
     # 0.8 L1 + 0.2 (1-SSIM) + 0.2 depth-L1, backward, gradient all-reduce pipelined with Adam, strategy statistics) ----

@@ -277,19 +277,27 @@ class FusedSplatStep:
 
     @property
     def launches_per_step(self) -> int:
-        """Kernel launches of one step(): project 1; intersections (two_level: 3 scan + 1 compact + 3 per
-        8-bit pass of the Gaussian sort + 3 scan | 1 emit + 3 per pass of the tile sort + compose + ranges;
-        own/cub: 3 scan + emit + sort + ranges); composite fwd 1, loss 3 (+1 memset), grad clear 1,
-        composite bwd 1, project bwd 1."""
+        """Launches of THIS library's kernels in one step() (memsets and torch's own fill kernels not counted):
+        project 1; intersections two_level: flag scan 3 (its last phase compacts) + Gaussian sort + gather scan 3 +
+        emit boundaries 1 + emit 1 + tile sort + compose/ranges 1 (a radix sort is 1 histogram + 1 kernel per 8-bit
+        pass when it fits 444 blocks of 4096 pairs, else 3 kernels per pass; the segmented sort behind the exact emit
+        always takes 3 per pass); own/cub: scan 3 + emit 1 + sort + ranges 1; composite fwd 1, loss 3 (+2 with SSIM),
+        composite bwd 1, project bwd 1.  Cross-checked against the ncu launch list (profiles/r01_launches_bench.csv)."""
         f = self._fwd
         tile_bits = (f["tw"] * f["th"]).bit_length()
+        cam_bits = (f["C"] - 1).bit_length()
+
+        def radix(capacity: int, bits: int, segmented: bool = False) -> int:
+            passes = (bits + 7) // 8
+            one_kernel_passes = (not segmented) and (capacity + 4095) // 4096 <= 444
+            return 1 + passes if one_kernel_passes else 3 * passes
+
         if self.sort_impl == "two_level":
-            gauss_bits = 32 + (f["C"] - 1).bit_length()
-            isect = 3 + 1 + 3 * ((gauss_bits + 7) // 8) + 3 + 1 + 3 * ((tile_bits + (f["C"] - 1).bit_length() + 7) // 8) + 2
+            isect = 3 + radix(f["C"] * f["N"], 32 + cam_bits) + 3 + 1 + 1 + radix(f["M"], tile_bits + cam_bits, bool(f.get("exact"))) + 1
         else:
             end_bit = 32 + tile_bits + f["C"].bit_length()
-            isect = 3 + 1 + (3 * ((end_bit + 7) // 8) if self.sort_impl == "own" else 8) + 1
-        return 1 + isect + 1 + 4 + 1 + 1 + 1
+            isect = 3 + 1 + (radix(f["M"], end_bit) if self.sort_impl == "own" else 8) + 1
+        return 1 + isect + 1 + 3 + 1 + 1
 
     @torch.no_grad()
     def count_pairs(self) -> Dict[str, int]:
