@@ -42,8 +42,8 @@ UNIT = "Mpix/s"
 PARAM_FLOATS = 3 + 4 + 3 + 1 + 48  # means, quats, scales, opacity, SH(16x3) = 59 floats / Gaussian
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
-# workload (profiles/r01_raster_bwd_ncu_summary.txt, profiles/r01_kernel_notes.md); None = not captured
-NCU_DRAM_BYTES = {"raster_bwd": 149.16e6 + 10.39e6, "raster_fwd": 47.55e6 + 15.36e6}
+# workload (profiles/r01_raster_ncu_summary.txt: raster_bwd_ws_kernel / raster_fwd_ws_kernel on the exact tile lists); None = not captured
+NCU_DRAM_BYTES = {"raster_bwd": 140.47e6 + 7.91e6, "raster_fwd": 41.19e6 + 12.53e6}
 
 # SURVEY.md §8(d) per-unit figures (D = 4 channels)
 FLOP_PER_PAIR_FWD = 30.0
