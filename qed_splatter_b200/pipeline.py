@@ -60,6 +60,7 @@ class FusedSplatStep:
         self._buf: Dict[str, Tensor] = {}
         self._prezero = False
         self._prezeroed = False
+        self._counts_ready = torch.cuda.Event()
         self.marks = None  # set to [] to record (name, cuda event) after every stage (bench.py stage timing)
 
     def _mark(self, name: str) -> None:
@@ -125,11 +126,13 @@ class FusedSplatStep:
             check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles), ptr(pws), pws_bytes, ptr(self._counts), ptr(self._counts_host), stream),
                   "qed_isect_prepare")
             self._mark("isect_prepare")
+            # the single host sync of the step (output sizes) waits on an EVENT behind the counts' copy, not on the
+            # stream: work that does not depend on the counts is queued behind the event and keeps the GPU busy while
+            # the host reads the counts and launches the rest (here: clearing the gradient record of the backward)
+            self._counts_ready.record(torch.cuda.current_stream())
             if self._prezero:
-                # work that does not depend on the counts is queued BEFORE the host waits, so the GPU is busy
-                # while the host reads the counts and launches the rest (the gradient record of the backward)
                 self._get("packed", (C * N, 12)).zero_()
-            torch.cuda.current_stream().synchronize()  # the single host sync of the step: output sizes
+            self._counts_ready.synchronize()
             n_vis, M = int(self._counts_host[0]), int(self._counts_host[1])
             self._mark("sync")
             cap = max(M, 1)
