@@ -17,7 +17,7 @@ e2e     = the same work through the public API a qed-splatter maintainer binds (
           `--torch-loss` writes those lines with torch ops as the reference does) + `backward()`, with the step's
           inputs (camera, ground-truth RGB + depth) copied from pinned host memory and the loss read back every
           step.  The Gaussian parameters are model state and stay resident, as in the reference.  For N>1 the
-          parameter gradients are views of one flat bucket (DDP's gradient_as_bucket_view) -> one all-reduce.
+          five parameter gradients go out as one coalesced NCCL group call (as DDP / FSDP issue them).
 train   = full trainer iterations/s (trainer.SplatTrainer: 0.8 L1 + 0.2 (1-SSIM) + 0.2 depth-L1, Adam, strategy
           statistics, pipelined gradient all-reduce) -- the second half of BASELINE.json's metric.
 --impl reference = the CPU arm: the oracle (`oracle/`, a port — the reference's own arithmetic lives in the
@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--comm-chunks", type=int, default=1, help="Gaussian ranges of the projection backward whose SH gradients are all-reduced while the next range computes (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-bucket", action="store_true", help="e2e, N>1: all-reduce one flat bucket of gradient views instead of a coalesced group call")
     ap.add_argument("--torch-loss", action="store_true", help="e2e: write the loss with torch ops as the reference does instead of depth_supervised_loss")
     ap.add_argument("--no-train", action="store_true")
     return ap.parse_args()
@@ -338,10 +339,10 @@ def main_ours(args):
     e2e = None
     if not args.no_e2e:
         params = [t.clone().requires_grad_(True) for t in (means, quats, scales, opac, sh)]
-        # N > 1: the parameter gradients are views of ONE flat bucket (what DDP's gradient_as_bucket_view does), so the
-        # step needs one 236 MB all-reduce instead of five calls of 4..192 MB
+        # N > 1: the five parameter gradients are reduced as ONE coalesced NCCL group call (what DDP / FSDP do), no
+        # flattening copies; `--e2e-bucket` uses a flat bucket of gradient views (gradient_as_bucket_view) instead
         grad_bucket, grad_views = None, None
-        if world > 1:
+        if world > 1 and args.e2e_bucket:
             grad_bucket = torch.zeros(sum(p_.numel() for p_ in params), device=dev)
             grad_views, o_ = [], 0
             for p_ in params:
@@ -391,7 +392,12 @@ def main_ours(args):
                 loss_t = depth_supervised_loss(render, alpha, rgb_gt, d_gt, bg, rgb_weight=0.8, depth_lambda=0.2)[0] / world
             loss_t.backward()
             if world > 1:
-                dist.all_reduce(grad_bucket)
+                if grad_bucket is not None:
+                    dist.all_reduce(grad_bucket)
+                else:
+                    with dist._coalescing_manager(device=dev):
+                        for p_ in params:
+                            dist.all_reduce(p_.grad)
             return float(loss_t.item())  # D2H read of the step's result
 
         for _ in range(W_):
