@@ -15,7 +15,8 @@ value   = fused C-ABI pipeline with everything resident in HBM.
 e2e     = the same work through the public API a qed-splatter maintainer binds: `rasterization()`
           (gsplat surface, torch autograd) + `depth_supervised_loss()` (model.py:295-306, 73-118 as one autograd op;
           `--torch-loss` writes those lines with torch ops as the reference does) + `backward()`, with the step's
-          inputs (camera, ground-truth RGB + depth) copied from pinned host memory and the loss read back every
+          inputs (camera, ground-truth RGB as the uint8 image cache of config.py:37 + float depth) copied from pinned host
+          memory and the loss read back every
           step.  The Gaussian parameters are model state and stay resident, as in the reference.  For N>1 the
           five parameter gradients go out as one coalesced NCCL group call (as DDP / FSDP issue them).
 train   = full trainer iterations/s (trainer.SplatTrainer: 0.8 L1 + 0.2 (1-SSIM) + 0.2 depth-L1, Adam, strategy
@@ -69,6 +70,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-bucket", action="store_true", help="e2e, N>1: all-reduce one flat bucket of gradient views instead of a coalesced group call")
+    ap.add_argument("--gt-float", action="store_true", help="e2e: ground-truth RGB as float32 instead of the uint8 image cache")
     ap.add_argument("--torch-loss", action="store_true", help="e2e: write the loss with torch ops as the reference does instead of depth_supervised_loss")
     ap.add_argument("--no-train", action="store_true")
     return ap.parse_args()
@@ -352,7 +354,10 @@ def main_ours(args):
         # waits on the copy event, so the H2D of the ground truth overlaps projection/sort/compositing
         copy_stream = torch.cuda.Stream()
         vm_d, K_d = torch.empty_like(viewmats), torch.empty_like(Ks)
-        rgb_d, depth_d = torch.empty_like(gt_rgb), torch.empty_like(gt_depth)
+        # ground-truth RGB travels as the reference's data side holds it: the uint8 image cache (config.py:37
+        # cache_images_type="uint8"); depth_supervised_loss converts it in-kernel (--torch-loss: torch .float() / 255)
+        e2e_rgb_h = gt_rgb_h if args.gt_float else (gt_rgb_h * 255.0).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+        rgb_d, depth_d = torch.empty(e2e_rgb_h.shape, dtype=e2e_rgb_h.dtype, device=dev), torch.empty_like(gt_depth)
         cam_ready, gt_ready = torch.cuda.Event(), torch.cuda.Event()
 
         def e2e_step():
@@ -361,7 +366,7 @@ def main_ours(args):
                 vm_d.copy_(vm_h, non_blocking=True)
                 K_d.copy_(K_h, non_blocking=True)
                 cam_ready.record(copy_stream)
-                rgb_d.copy_(gt_rgb_h, non_blocking=True)
+                rgb_d.copy_(e2e_rgb_h, non_blocking=True)
                 depth_d.copy_(gt_depth_h, non_blocking=True)
                 gt_ready.record(copy_stream)
             torch.cuda.current_stream().wait_event(cam_ready)
@@ -379,6 +384,7 @@ def main_ours(args):
             info["means2d"].retain_grad()
             torch.cuda.current_stream().wait_event(gt_ready)
             if args.torch_loss:
+                rgb_gt = rgb_gt.float() / 255.0 if rgb_gt.dtype == torch.uint8 else rgb_gt  # splatfacto get_gt_img
                 # qed_splatter/model.py:295-306 and :87-116 as the reference writes them (a dozen torch element-wise ops)
                 rgb = torch.clamp(render[..., :3] + (1 - alpha) * bg, 0.0, 1.0)
                 depth = render[..., 3:4]
@@ -412,7 +418,7 @@ def main_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item()) / K
-        h2d = vm_h.numel() * 4 + K_h.numel() * 4 + gt_rgb_h.numel() * 4 + gt_depth_h.numel() * 4
+        h2d = vm_h.numel() * 4 + K_h.numel() * 4 + e2e_rgb_h.numel() * e2e_rgb_h.element_size() + gt_depth_h.numel() * 4
         e2e = {"value": world * width * height / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": e2e_ms, "loss": e2e_loss,
                "api": "qed_splatter_b200.rasterization (gsplat surface) + " +

@@ -214,7 +214,9 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  *           and :87-116 (masked depth-L1 * depth_lambda) + the L1 term of splatfacto's RGB loss
  *           (model.py:83-85), i.e. SURVEY.md §8 rows a11-a13.
  *  render[C,H,W,4] (RGB + depth; depth normalised iff normalize_last), alphas[C,H,W],
- *  gt_rgb[C,H,W,3], gt_depth[C,H,W] (<=0 or non-finite = invalid), bg[3].
+ *  gt_rgb[C,H,W,3]: float32 in [0,1], or (gt_rgb_is_u8 != 0) the uint8 image cache of the data side
+ *      (qed_splatter/config.py:37 cache_images_type="uint8"), converted as splatfacto's `image.float() / 255.0` does on CUDA (u8 * (1.0f / 255.0f)) at the point of use;
+ *  gt_depth[C,H,W] (<=0 or non-finite = invalid), bg[3].
  *  loss = rgb_weight * mean|clamp(rgb + (1-a) bg) - gt| + ssim_lambda * (1 - SSIM(clamped rgb, gt))
  *         + depth_lambda * mean_valid|depth - gt_depth|,  per camera (one camera = one reference step: its own
  *         depth fill / n_valid), then the mean over cameras.  splatfacto: rgb_weight = 1 - ssim_lambda = 0.8.
@@ -226,7 +228,7 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  */
 size_t qed_loss_workspace_bytes(int C, int width, int height, float ssim_lambda);
 int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
-                     const float* gt_rgb, const float* gt_depth, const float* bg, float rgb_weight,
+                     const void* gt_rgb, int gt_rgb_is_u8, const float* gt_depth, const float* bg, float rgb_weight,
                      float depth_lambda, float ssim_lambda, float grad_scale, double* stats_dev, float* loss_dev,
                      float* v_render, float* v_alphas, void* workspace, size_t workspace_bytes, qed_stream_t stream);
 

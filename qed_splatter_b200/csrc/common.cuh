@@ -40,6 +40,18 @@ __device__ __forceinline__ float mad3(float a, float b, float c, float d, float 
     return add(add(mul(a, b), mul(c, d)), mul(e, f));
 }
 
+// Ground-truth image as the data side holds it: float32 in [0,1], or the uint8 cache of nerfstudio's
+// FullImageDatamanager (qed_splatter/config.py:37 cache_images_type="uint8"), converted as splatfacto does
+// (`image.float() / 255.0`) at the point of use instead of materialising a float copy per step.
+struct GtImage {
+    const void* p;
+    int u8;
+    __device__ __forceinline__ float at(int64_t i) const {
+        // torch's CUDA `tensor / scalar` is `tensor * (1 / scalar)` in float: the same here, bit for bit
+        return u8 ? __fmul_rn((float)reinterpret_cast<const uint8_t*>(p)[i], 1.0f / 255.0f) : reinterpret_cast<const float*>(p)[i];
+    }
+};
+
 // ---- log2-domain alpha test shared by the compositor (raster.cu) and the exact tile lists (isect.cu) ----
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLog2_255 = 7.99435343685886f;

@@ -39,7 +39,7 @@ static GaussWin make_window() {
 // grid (tiles_x, tiles_y, C*3); 256 threads; every thread produces kBlk adjacent outputs per pass from a register
 // sliding window, so each input is read from shared memory once per kBlk outputs instead of once per output
 __global__ void __launch_bounds__(kSsimThreads) ssim_fwd_kernel(int W, int H, const float* __restrict__ pred /*[C,H,W,3]*/,
-                                                                const float* __restrict__ gt, GaussWin win,
+                                                                const GtImage gt, GaussWin win,
                                                                 float* __restrict__ dmaps /*[C*3][3][OH][OW]*/, double* __restrict__ stats) {
     extern __shared__ float ssim_smem[];
     float(*sx)[kSsimIn + 1] = reinterpret_cast<float(*)[kSsimIn + 1]>(ssim_smem);            // [42][43]
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_fwd_kernel(int W, int H, co
         float a = 0.f, b = 0.f;
         if (y < H && x < W) {
             const int64_t o = (img + (int64_t)y * W + x) * 3 + ch;
-            a = gt[o];
+            a = gt.at(o);
             b = pred[o];
         }
         sx[r][c] = a;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_fwd_kernel(int W, int H, co
 }
 
 // grid (ceil(W/32), ceil(H/32), C*3): dL/dpred for a 32x32 tile of INPUT pixels
-__global__ void __launch_bounds__(kSsimThreads) ssim_bwd_kernel(int W, int H, const float* __restrict__ pred, const float* __restrict__ gt,
+__global__ void __launch_bounds__(kSsimThreads) ssim_bwd_kernel(int W, int H, const float* __restrict__ pred, const GtImage gt,
                                                                 GaussWin win, const float* __restrict__ dmaps, float scale,
                                                                 float* __restrict__ v_pred /*[C,H,W,3]*/) {
     extern __shared__ float ssim_smem[];
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_bwd_kernel(int W, int H, co
             const int y = y0 + yb + o;
             if (y < H && x < W) {
                 const int64_t idx = (((int64_t)cam * H + y) * W + x) * 3 + ch;
-                v_pred[idx] = scale * (acc[0][o] + 2.f * pred[idx] * acc[1][o] + gt[idx] * acc[2][o]);
+                v_pred[idx] = scale * (acc[0][o] + 2.f * pred[idx] * acc[1][o] + gt.at(idx) * acc[2][o]);
             }
         }
     }
@@ -247,7 +247,7 @@ using namespace qed;
 
 // pred/gt [C,H,W,3]; dmaps scratch [C*3*3*(H-10)*(W-10)]; stats[c*8+5] += sum of the SSIM map of camera c;
 // v_pred = scale * d(sum map)/d pred.  Internal to qed_loss_fwd_bwd (train.cu), declared there.
-int qed_ssim_launch(int C, int W, int H, const float* pred, const float* gt, float* dmaps, double* stats, float scale, float* v_pred,
+int qed_ssim_launch(int C, int W, int H, const float* pred, qed::GtImage gt, float* dmaps, double* stats, float scale, float* v_pred,
                     cudaStream_t stream) {
     if (W <= kHalo || H <= kHalo) return QED_ERR_UNSUPPORTED;
     static const GaussWin win = make_window();

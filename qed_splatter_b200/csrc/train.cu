@@ -77,7 +77,7 @@ __device__ __forceinline__ double n_valid_of(const double* s, float maxd) { retu
 //   otherwise  : loss sums + gradients (v_rgb_extra = gradient of the SSIM term w.r.t. the clamped rgb, or NULL)
 template <bool WRITE_PRED>
 __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int C, const float4* __restrict__ render, const float* __restrict__ alphas,
-                                                                const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth,
+                                                                const GtImage gt_rgb, const float* __restrict__ gt_depth,
                                                                 const float* __restrict__ bg, float rgb_weight, float depth_lambda, float grad_scale,
                                                                 double* __restrict__ stats, float4* __restrict__ v_render, float* __restrict__ v_alphas,
                                                                 float* __restrict__ pred_rgb, const float* __restrict__ v_rgb_extra) {
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
             pred_rgb[pix * 3 + 2] = c2;
             continue;
         }
-        const float e0 = c0 - gt_rgb[pix * 3 + 0], e1 = c1 - gt_rgb[pix * 3 + 1], e2 = c2 - gt_rgb[pix * 3 + 2];
+        const float e0 = c0 - gt_rgb.at(pix * 3 + 0), e1 = c1 - gt_rgb.at(pix * 3 + 1), e2 = c2 - gt_rgb.at(pix * 3 + 2);
         const float gd = gt_depth[pix];
         const float d = (a > 0.0f) ? r.w : maxd;
         const bool valid = finitef(d) && finitef(gd) && (gd > 0.0f);
@@ -278,7 +278,7 @@ __global__ void strategy_update_kernel(int C, int N, const float4* __restrict__ 
 
 using namespace qed;
 
-int qed_ssim_launch(int C, int W, int H, const float* pred, const float* gt, float* dmaps, double* stats, float scale, float* v_pred,
+int qed_ssim_launch(int C, int W, int H, const float* pred, qed::GtImage gt, float* dmaps, double* stats, float scale, float* v_pred,
                     cudaStream_t stream);  // ssim.cu
 
 extern "C" size_t qed_loss_workspace_bytes(int C, int width, int height, float ssim_lambda) {
@@ -288,12 +288,13 @@ extern "C" size_t qed_loss_workspace_bytes(int C, int width, int height, float s
 }
 
 extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
-                                const float* gt_rgb, const float* gt_depth, const float* bg, float rgb_weight,
+                                const void* gt_rgb_, int gt_rgb_is_u8, const float* gt_depth, const float* bg, float rgb_weight,
                                 float depth_lambda, float ssim_lambda, float grad_scale, double* stats_dev, float* loss_dev,
                                 float* v_render, float* v_alphas, void* workspace, size_t workspace_bytes, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (C <= 0 || width <= 0 || height <= 0) return QED_ERR_BAD_ARG;
-    if (!render || !alphas || !gt_rgb || !gt_depth || !bg || !stats_dev || !loss_dev || !v_render || !v_alphas) return QED_ERR_BAD_ARG;
+    if (!render || !alphas || !gt_rgb_ || !gt_depth || !bg || !stats_dev || !loss_dev || !v_render || !v_alphas) return QED_ERR_BAD_ARG;
+    const GtImage gt_rgb{gt_rgb_, gt_rgb_is_u8 ? 1 : 0};
     if (C > 21845) return QED_ERR_UNSUPPORTED;
     const bool use_ssim = ssim_lambda > 0.0f;
     if (use_ssim) {

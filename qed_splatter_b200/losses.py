@@ -38,7 +38,9 @@ class _DepthSupervisedLoss(torch.autograd.Function):
         dev = render.device
         r = render.detach().contiguous().float()
         a = alphas.detach().contiguous().float()
-        rgb = gt_rgb.detach().contiguous().float()
+        rgb = gt_rgb.detach().contiguous()  # float32 in [0,1], or the uint8 image cache (converted in-kernel, u8 / 255)
+        if rgb.dtype != torch.uint8:
+            rgb = rgb.float()
         dep = gt_depth.detach().contiguous().float()
         bg = background.detach().contiguous().float()
         stats = torch.zeros(C * 8, dtype=torch.float64, device=dev)
@@ -47,7 +49,7 @@ class _DepthSupervisedLoss(torch.autograd.Function):
         v_alphas = torch.empty_like(a)
         ws_bytes = lib.qed_loss_workspace_bytes(C, W, H, float(ssim_lambda))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-        check(lib.qed_loss_fwd_bwd(C, W, H, ptr(r), ptr(a), ptr(rgb), ptr(dep), ptr(bg), float(rgb_weight), float(depth_lambda),
+        check(lib.qed_loss_fwd_bwd(C, W, H, ptr(r), ptr(a), ptr(rgb), int(rgb.dtype == torch.uint8), ptr(dep), ptr(bg), float(rgb_weight), float(depth_lambda),
                                    float(ssim_lambda), 1.0, ptr(stats), ptr(loss), ptr(v_render), ptr(v_alphas), ptr(ws), ws_bytes,
                                    current_stream()), "qed_loss_fwd_bwd")
         ctx.save_for_backward(v_render, v_alphas)
@@ -66,7 +68,8 @@ def depth_supervised_loss(render: Tensor, alphas: Tensor, gt_rgb: Tensor, gt_dep
                           depth_lambda: float = 0.2, ssim_lambda: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
     """-> (total, rgb_term, depth_term), 0-dim tensors; `total` carries the gradient to `render` and `alphas`.
 
-    render [C,H,W,4] (RGB + depth; expected depth for 'RGB+ED'), alphas [C,H,W,1], gt_rgb [C,H,W,3] in [0,1],
+    render [C,H,W,4] (RGB + depth; expected depth for 'RGB+ED'), alphas [C,H,W,1], gt_rgb [C,H,W,3] float in [0,1] or uint8
+    (nerfstudio's image cache, config.py:37; converted as splatfacto's `image.float() / 255.0` inside the kernels),
     gt_depth [C,H,W] or [C,H,W,1] (<= 0 or non-finite = no supervision), background [3].
     total = rgb_weight * mean|clamp(rgb + (1 - alpha) bg, 0, 1) - gt| + ssim_lambda * (1 - SSIM) + depth_lambda *
     mean_valid|depth_filled - gt_depth|  (qed-splatter: depth_lambda = 0.2; splatfacto: rgb_weight = 0.8, ssim_lambda = 0.2).

@@ -262,7 +262,7 @@ class FusedSplatStep:
         v_alphas = self._get("v_alphas", (C, height, width, 1))
         lws_bytes = lib.qed_loss_workspace_bytes(C, width, height, ssim_lambda)
         lws = self._get("loss_ws", (lws_bytes,), torch.uint8) if lws_bytes else None
-        check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), ptr(gt_depth), ptr(background), rgb_weight,
+        check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), int(gt_rgb.dtype == torch.uint8), ptr(gt_depth), ptr(background), rgb_weight,
                                    depth_lambda, ssim_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas),
                                    ptr(lws), lws_bytes, stream), "qed_loss_fwd_bwd")
         self._mark("loss")

@@ -127,6 +127,36 @@ def test_depth_supervised_loss_is_the_reference_loss(cuda, mode, C, ssim):
         assert_close_frac(lg[k].grad, lo[k].grad, 1e-3, 1e-3 * scale, 5e-3, f"v_{k}")
 
 
+@pytest.mark.parametrize("ssim", [0.0, 0.2])
+def test_uint8_ground_truth_is_converted_in_kernel(cuda, ssim):
+    """The data side caches images as uint8 (config.py:37); splatfacto converts `image.float() / 255.0` every step.
+    Passing the uint8 tensor gives the same loss and bit-identical gradients without materialising the float image."""
+    from qed_splatter_b200 import depth_supervised_loss
+
+    s = scene_s0(N=2000, C=2, size=64).to(cuda)
+    bg = torch.tensor([0.3, 0.1, 0.6], device=cuda)
+    gt_u8 = (s.gt_rgb * 255.0).round().clamp(0, 255).to(torch.uint8)
+    gt_f = gt_u8.float() / 255.0
+    res = []
+    for gt in (gt_f, gt_u8):
+        lg = {k: getattr(s, k).clone().requires_grad_(True) for k in NAMES}
+        render, alpha, _ = rasterization(lg["means"], lg["quats"], lg["scales"], lg["opacities"], lg["sh"], s.viewmats, s.Ks, s.width, s.height,
+                                         sh_degree=3, render_mode="RGB+ED")
+        render.retain_grad()
+        tot = depth_supervised_loss(render, alpha, gt, s.gt_depth, bg, rgb_weight=1.0 - ssim, depth_lambda=0.2, ssim_lambda=ssim)[0]
+        tot.backward()
+        res.append((tot.detach().clone(), render.grad.clone()))
+    # the loss sums are double atomics across blocks (order varies run to run): equal to float rounding; the per-pixel
+    # gradients are bit-identical
+    assert torch.allclose(res[0][0], res[1][0], rtol=1e-6, atol=0) and torch.equal(res[0][1], res[1][1])
+    fs = FusedSplatStep(cuda)
+    a = fs.step(s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, 3, gt_f, s.gt_depth, bg, ssim_lambda=ssim,
+                rgb_weight=1.0 - ssim).loss.clone()
+    b = fs.step(s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, 3, gt_u8, s.gt_depth, bg, ssim_lambda=ssim,
+                rgb_weight=1.0 - ssim).loss.clone()
+    assert torch.allclose(a, b, rtol=1e-6, atol=0)
+
+
 @pytest.mark.timeout(120)
 def test_pair_counters_of_instrumented_kernels(cuda):
     """bench.py's roofline uses the work counters of the instrumented (STATS) compositor kernels: they must run
