@@ -170,3 +170,23 @@ def test_sharded_gradients_equal_single_rank_sum():
     single = sum(per_view) / 4
     sharded = sum((per_view[r * 2] + per_view[r * 2 + 1]) / 2 * (2 / 4) for r in range(2))
     assert torch.allclose(single, sharded, atol=1e-7)
+
+
+def test_arena_layout_matches_build_and_adopt():
+    """`GaussianArena.layout` (used by the fused densify to size the new arenas) is the layout `_build` produces, and
+    `adopt` leaves the arena in the state a rebuild from the same tensors would."""
+    import torch
+
+    from qed_splatter_b200.trainer import GROUPS, GaussianArena
+
+    for N in (1, 7, 10, 33):
+        g = torch.Generator().manual_seed(N)
+        a = GaussianArena(torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g), torch.randn(N, 3, generator=g),
+                          torch.randn(N, generator=g), torch.randn(N, 16, 3, generator=g))
+        off, n = GaussianArena.layout(N)
+        assert off == a.offsets and n == a.param.numel()
+        assert all(off[k][0] % 4 == 0 for k in GROUPS)  # 16-byte aligned groups
+        b = GaussianArena(torch.zeros(1, 3), torch.zeros(1, 4), torch.zeros(1, 3), torch.zeros(1), torch.zeros(1, 16, 3))
+        b.adopt(N, a.param.clone(), a.exp_avg.clone(), a.exp_avg_sq.clone())
+        assert b.N == a.N and b.offsets == a.offsets and torch.equal(b.group_ends, a.group_ends)
+        assert torch.equal(b.param, a.param) and float(b.grad.abs().sum()) == 0.0 and b.grad.numel() == n
