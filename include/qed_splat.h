@@ -37,7 +37,7 @@ typedef void* qed_stream_t; /* cudaStream_t */
 #define QED_ERR_UNSUPPORTED (-2)
 #define QED_ERR_WORKSPACE (-3)
 
-#define QED_ABI_VERSION 1
+#define QED_ABI_VERSION 2
 
 /* Library / ABI version (QED_ABI_VERSION the .so was built with). */
 int qed_abi_version(void);
@@ -217,8 +217,13 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  *  gt_rgb[C,H,W,3]: float32 in [0,1], or (gt_rgb_is_u8 != 0) the uint8 image cache of the data side
  *      (qed_splatter/config.py:37 cache_images_type="uint8"), converted as splatfacto's `image.float() / 255.0` does on CUDA (u8 * (1.0f / 255.0f)) at the point of use;
  *  gt_depth[C,H,W] (<=0 or non-finite = invalid), bg[3].
- *  loss = rgb_weight * mean|clamp(rgb + (1-a) bg) - gt| + ssim_lambda * (1 - SSIM(clamped rgb, gt))
- *         + depth_lambda * mean_valid|depth - gt_depth|,  per camera (one camera = one reference step: its own
+ *  mask[C,H,W] or NULL: the batch's `mask` (qed_splatter/model.py:93-97), float32 or (mask_is_u8 != 0) uint8 / bool.
+ *      As in the reference, rendered and ground-truth depth are both multiplied by it BEFORE the validity test
+ *      (model.py:96-97), and -- splatfacto's parent loss, model.py:83-85 -- so are the predicted and ground-truth
+ *      RGB images before L1 and SSIM (means still run over all H*W pixels).  The depth fill value stays the
+ *      maximum of the unmasked rendered depth (model.py:304-306 run before the loss).
+ *  loss = rgb_weight * mean|m clamp(rgb + (1-a) bg) - m gt| + ssim_lambda * (1 - SSIM(m clamped rgb, m gt))
+ *         + depth_lambda * mean_valid|m depth - m gt_depth|,  per camera (one camera = one reference step: its own
  *         depth fill / n_valid), then the mean over cameras.  splatfacto: rgb_weight = 1 - ssim_lambda = 0.8.
  *  SSIM = pytorch_msssim.SSIM(data_range=1, channel=3): 11x11 Gaussian window (sigma 1.5), valid convolution,
  *         mean over channels and pixels; ssim_lambda == 0 skips it (then workspace may be NULL).
@@ -228,7 +233,8 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  */
 size_t qed_loss_workspace_bytes(int C, int width, int height, float ssim_lambda);
 int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
-                     const void* gt_rgb, int gt_rgb_is_u8, const float* gt_depth, const float* bg, float rgb_weight,
+                     const void* gt_rgb, int gt_rgb_is_u8, const float* gt_depth, const void* mask, int mask_is_u8,
+                     const float* bg, float rgb_weight,
                      float depth_lambda, float ssim_lambda, float grad_scale, double* stats_dev, float* loss_dev,
                      float* v_render, float* v_alphas, void* workspace, size_t workspace_bytes, qed_stream_t stream);
 

@@ -15,6 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("QED_SPLAT_LIB", _PKG / "libqedsplat.so"))
 
 P = c_void_p  # every device pointer / stream
+ABI_VERSION = 2  # QED_ABI_VERSION of include/qed_splat.h this binding was written against
 
 # name -> (restype, argtypes); must match include/qed_splat.h exactly (tests/test_abi.py checks the names)
 SIGNATURES = {
@@ -45,7 +46,7 @@ SIGNATURES = {
                                c_int, P, P, P, P, P, P, P]),
     "qed_unpack_grads": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
     "qed_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_float]),
-    "qed_loss_fwd_bwd": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P, P, c_float, c_float, c_float, c_float, P, P, P, P, P, c_size_t, P]),
+    "qed_loss_fwd_bwd": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P, c_float, c_float, c_float, c_float, P, P, P, P, P, c_size_t, P]),
     "qed_adam_arena": (c_int, [c_int64, P, P, P, P, c_int, P, P, P, P, P, c_double, c_double, c_double, c_int, P]),
     "qed_strategy_update": (c_int, [c_int, c_int, P, c_int, P, c_int, c_int, c_int, P, P, P, P]),
     "qed_arena_gather": (c_int, [c_int64, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
@@ -84,8 +85,8 @@ def load() -> ctypes.CDLL:
             raise QedLibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.qed_abi_version() != 1:
-        raise QedLibraryError(f"ABI version mismatch: library {lib.qed_abi_version()} != binding 1")
+    if lib.qed_abi_version() != ABI_VERSION:
+        raise QedLibraryError(f"ABI version mismatch: library {lib.qed_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
 
@@ -116,8 +117,29 @@ def current_stream() -> c_void_p:
 
 
 def require_cuda(*tensors) -> None:
+    """Every tensor handed to the C-ABI must live on ONE CUDA device, and that device must be the current one: the
+    kernels are launched on `torch.cuda.current_stream()` of the current device (gsplat guards with the tensors'
+    device; here a mismatch raises instead of launching on the wrong device).  None entries are skipped."""
+    import torch
+
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 "qed_splatter_b200 runs on CUDA (sm_100a) only: got a CPU tensor.  "
                 "There is no CPU fallback; the CPU oracle lives in oracle/ and is test infrastructure.")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"qed_splatter_b200: tensors on different devices ({dev} and {t.device})")
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise RuntimeError(
+            f"qed_splatter_b200: tensors live on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            f"call torch.cuda.set_device({dev.index}) (or wrap the call in `with torch.cuda.device({dev.index})`)")
+
+
+def require_dtype(t, dtypes, what: str) -> None:
+    if t is not None and t.dtype not in dtypes:
+        raise TypeError(f"{what}: expected {' or '.join(str(d) for d in dtypes)}, got {t.dtype}")

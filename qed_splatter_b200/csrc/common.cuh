@@ -52,6 +52,17 @@ struct GtImage {
     }
 };
 
+// Optional per-pixel loss mask of the batch (`batch["mask"]`, qed_splatter/model.py:93-97; splatfacto multiplies the
+// RGB images by it too): float32 or uint8 / bool [C,H,W]; NULL = all ones.
+struct PixelMask {
+    const void* p;
+    int u8;
+    __device__ __forceinline__ float at(int64_t pix) const {
+        if (!p) return 1.0f;
+        return u8 ? (float)reinterpret_cast<const uint8_t*>(p)[pix] : reinterpret_cast<const float*>(p)[pix];
+    }
+};
+
 // ---- log2-domain alpha test shared by the compositor (raster.cu) and the exact tile lists (isect.cu) ----
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLog2_255 = 7.99435343685886f;

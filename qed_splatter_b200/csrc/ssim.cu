@@ -39,7 +39,7 @@ static GaussWin make_window() {
 // grid (tiles_x, tiles_y, C*3); 256 threads; every thread produces kBlk adjacent outputs per pass from a register
 // sliding window, so each input is read from shared memory once per kBlk outputs instead of once per output
 __global__ void __launch_bounds__(kSsimThreads) ssim_fwd_kernel(int W, int H, const float* __restrict__ pred /*[C,H,W,3]*/,
-                                                                const GtImage gt, GaussWin win,
+                                                                const GtImage gt, const PixelMask mask, GaussWin win,
                                                                 float* __restrict__ dmaps /*[C*3][3][OH][OW]*/, double* __restrict__ stats) {
     extern __shared__ float ssim_smem[];
     float(*sx)[kSsimIn + 1] = reinterpret_cast<float(*)[kSsimIn + 1]>(ssim_smem);            // [42][43]
@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_fwd_kernel(int W, int H, co
         const int y = oy0 + r, x = ox0 + c;
         float a = 0.f, b = 0.f;
         if (y < H && x < W) {
-            const int64_t o = (img + (int64_t)y * W + x) * 3 + ch;
-            a = gt.at(o);
+            const int64_t pix = img + (int64_t)y * W + x, o = pix * 3 + ch;
+            a = gt.at(o) * mask.at(pix);  // pred already carries the mask (loss_grad_kernel<WRITE_PRED>)
             b = pred[o];
         }
         sx[r][c] = a;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_fwd_kernel(int W, int H, co
 }
 
 // grid (ceil(W/32), ceil(H/32), C*3): dL/dpred for a 32x32 tile of INPUT pixels
-__global__ void __launch_bounds__(kSsimThreads) ssim_bwd_kernel(int W, int H, const float* __restrict__ pred, const GtImage gt,
+__global__ void __launch_bounds__(kSsimThreads) ssim_bwd_kernel(int W, int H, const float* __restrict__ pred, const GtImage gt, const PixelMask mask,
                                                                 GaussWin win, const float* __restrict__ dmaps, float scale,
                                                                 float* __restrict__ v_pred /*[C,H,W,3]*/) {
     extern __shared__ float ssim_smem[];
@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_bwd_kernel(int W, int H, co
         for (int o = 0; o < kBlk; ++o) {
             const int y = y0 + yb + o;
             if (y < H && x < W) {
-                const int64_t idx = (((int64_t)cam * H + y) * W + x) * 3 + ch;
-                v_pred[idx] = scale * (acc[0][o] + 2.f * pred[idx] * acc[1][o] + gt.at(idx) * acc[2][o]);
+                const int64_t pix = ((int64_t)cam * H + y) * W + x, idx = pix * 3 + ch;
+                v_pred[idx] = scale * (acc[0][o] + 2.f * pred[idx] * acc[1][o] + gt.at(idx) * mask.at(pix) * acc[2][o]);
             }
         }
     }
@@ -245,20 +245,20 @@ constexpr size_t kSsimBwdSmem = (size_t)(3 * kSsimIn * (kSsimIn + 1) + 3 * kSsim
 
 using namespace qed;
 
-// pred/gt [C,H,W,3]; dmaps scratch [C*3*3*(H-10)*(W-10)]; stats[c*8+5] += sum of the SSIM map of camera c;
+// pred (already multiplied by the mask) / gt [C,H,W,3], mask [C,H,W] or NULL; dmaps scratch [C*3*3*(H-10)*(W-10)]; stats[c*8+5] += sum of the SSIM map of camera c;
 // v_pred = scale * d(sum map)/d pred.  Internal to qed_loss_fwd_bwd (train.cu), declared there.
-int qed_ssim_launch(int C, int W, int H, const float* pred, qed::GtImage gt, float* dmaps, double* stats, float scale, float* v_pred,
-                    cudaStream_t stream) {
+int qed_ssim_launch(int C, int W, int H, const float* pred, qed::GtImage gt, qed::PixelMask mask, float* dmaps, double* stats, float scale,
+                    float* v_pred, cudaStream_t stream) {
     if (W <= kHalo || H <= kHalo) return QED_ERR_UNSUPPORTED;
     static const GaussWin win = make_window();
     const int OW = W - kHalo, OH = H - kHalo;
     QED_CUDA_TRY(cudaFuncSetAttribute(ssim_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimFwdSmem));
     QED_CUDA_TRY(cudaFuncSetAttribute(ssim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimBwdSmem));
     dim3 g1((OW + kSsimTile - 1) / kSsimTile, (OH + kSsimTile - 1) / kSsimTile, C * 3);
-    ssim_fwd_kernel<<<g1, kSsimThreads, kSsimFwdSmem, stream>>>(W, H, pred, gt, win, dmaps, stats);
+    ssim_fwd_kernel<<<g1, kSsimThreads, kSsimFwdSmem, stream>>>(W, H, pred, gt, mask, win, dmaps, stats);
     QED_LAUNCH_CHECK();
     dim3 g2((W + kSsimTile - 1) / kSsimTile, (H + kSsimTile - 1) / kSsimTile, C * 3);
-    ssim_bwd_kernel<<<g2, kSsimThreads, kSsimBwdSmem, stream>>>(W, H, pred, gt, win, dmaps, scale, v_pred);
+    ssim_bwd_kernel<<<g2, kSsimThreads, kSsimBwdSmem, stream>>>(W, H, pred, gt, mask, win, dmaps, scale, v_pred);
     QED_LAUNCH_CHECK();
     return QED_OK;
 }

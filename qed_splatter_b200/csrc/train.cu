@@ -22,14 +22,14 @@ __device__ __forceinline__ bool finitef(float x) { return fabsf(x) <= 3.40282346
 // float bits is the float order and atomicMax on the bits works.  stats[2] = valid pixels with alpha > 0,
 // stats[6] = pixels with alpha == 0 whose ground truth is usable (valid iff the fill value is finite).
 __global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, const float4* __restrict__ render, const float* __restrict__ alphas,
-                                                                 const float* __restrict__ gt_depth, double* __restrict__ stats) {
+                                                                 const float* __restrict__ gt_depth, const PixelMask mask, double* __restrict__ stats) {
     __shared__ float s_max[kLossThreads / 32];
     __shared__ int s_na[kLossThreads / 32], s_nb[kLossThreads / 32];
     const int cam = blockIdx.y;
     float maxd = 0.0f;
     int na = 0, nb = 0;
     const int64_t base = (int64_t)blockIdx.x * (kLossThreads * kLossUnroll) + threadIdx.x;
-    float d[kLossUnroll], a[kLossUnroll], gd[kLossUnroll];
+    float d[kLossUnroll], a[kLossUnroll], gd[kLossUnroll], mk[kLossUnroll];
 #pragma unroll
     for (int u = 0; u < kLossUnroll; ++u) {  // all loads first: kLossUnroll independent requests in flight per thread
         const int64_t i = base + (int64_t)u * kLossThreads;
@@ -38,12 +38,14 @@ __global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, co
         d[u] = in ? render[pix].w : 0.0f;
         a[u] = in ? alphas[pix] : 1.0f;
         gd[u] = in ? gt_depth[pix] : 0.0f;
+        mk[u] = in ? mask.at(pix) : 0.0f;
     }
 #pragma unroll
     for (int u = 0; u < kLossUnroll; ++u) {
-        maxd = fmaxf(maxd, d[u]);
-        const bool gt_ok = finitef(gd[u]) && gd[u] > 0.0f;
-        if (a[u] > 0.0f) na += (gt_ok && finitef(d[u])) ? 1 : 0;
+        maxd = fmaxf(maxd, d[u]);  // the fill value is the maximum of the UNMASKED rendered depth (model.py:304-306 run before the loss)
+        const float gm = gd[u] * mk[u];  // model.py:96-97: both sides are multiplied by the mask before the validity test
+        const bool gt_ok = finitef(gm) && gm > 0.0f;
+        if (a[u] > 0.0f) na += (gt_ok && finitef(d[u] * mk[u])) ? 1 : 0;
         else nb += gt_ok ? 1 : 0;
     }
 #pragma unroll
@@ -77,7 +79,7 @@ __device__ __forceinline__ double n_valid_of(const double* s, float maxd) { retu
 //   otherwise  : loss sums + gradients (v_rgb_extra = gradient of the SSIM term w.r.t. the clamped rgb, or NULL)
 template <bool WRITE_PRED>
 __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int C, const float4* __restrict__ render, const float* __restrict__ alphas,
-                                                                const GtImage gt_rgb, const float* __restrict__ gt_depth,
+                                                                const GtImage gt_rgb, const float* __restrict__ gt_depth, const PixelMask mask,
                                                                 const float* __restrict__ bg, float rgb_weight, float depth_lambda, float grad_scale,
                                                                 double* __restrict__ stats, float4* __restrict__ v_render, float* __restrict__ v_alphas,
                                                                 float* __restrict__ pred_rgb, const float* __restrict__ v_rgb_extra) {
@@ -99,29 +101,32 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
         const float om = 1.0f - a;
         const float pre0 = r.x + om * b0, pre1 = r.y + om * b1, pre2 = r.z + om * b2;
         const float c0 = fminf(fmaxf(pre0, 0.0f), 1.0f), c1 = fminf(fmaxf(pre1, 0.0f), 1.0f), c2 = fminf(fmaxf(pre2, 0.0f), 1.0f);
-        if (WRITE_PRED) {
-            pred_rgb[pix * 3 + 0] = c0;
-            pred_rgb[pix * 3 + 1] = c1;
-            pred_rgb[pix * 3 + 2] = c2;
+        const float mk = mask.at(pix);  // 1 without a mask: every product below is then exact
+        if (WRITE_PRED) {  // splatfacto multiplies prediction and ground truth by the mask before L1 and SSIM
+            pred_rgb[pix * 3 + 0] = c0 * mk;
+            pred_rgb[pix * 3 + 1] = c1 * mk;
+            pred_rgb[pix * 3 + 2] = c2 * mk;
             continue;
         }
-        const float e0 = c0 - gt_rgb.at(pix * 3 + 0), e1 = c1 - gt_rgb.at(pix * 3 + 1), e2 = c2 - gt_rgb.at(pix * 3 + 2);
-        const float gd = gt_depth[pix];
-        const float d = (a > 0.0f) ? r.w : maxd;
+        const float e0 = __fmul_rn(c0, mk) - __fmul_rn(gt_rgb.at(pix * 3 + 0), mk), e1 = __fmul_rn(c1, mk) - __fmul_rn(gt_rgb.at(pix * 3 + 1), mk),
+                    e2 = __fmul_rn(c2, mk) - __fmul_rn(gt_rgb.at(pix * 3 + 2), mk);
+        const float gd = __fmul_rn(gt_depth[pix], mk);                 // model.py:96-97
+        const float d = __fmul_rn((a > 0.0f) ? r.w : maxd, mk);
         const bool valid = finitef(d) && finitef(gd) && (gd > 0.0f);
         s_rgb += (double)(fabsf(e0) + fabsf(e1) + fabsf(e2));
         if (valid) s_d += (double)fabsf(d - gd);
         float x0 = 0.f, x1 = 0.f, x2 = 0.f;  // gradient of the SSIM term w.r.t. the clamped rgb
-        if (v_rgb_extra) {
-            x0 = v_rgb_extra[pix * 3 + 0];
-            x1 = v_rgb_extra[pix * 3 + 1];
-            x2 = v_rgb_extra[pix * 3 + 2];
+        if (v_rgb_extra) {  // gradient w.r.t. the masked prediction -> chain rule through the mask product
+            x0 = v_rgb_extra[pix * 3 + 0] * mk;
+            x1 = v_rgb_extra[pix * 3 + 1] * mk;
+            x2 = v_rgb_extra[pix * 3 + 2] * mk;
         }
+        const float gm_rgb = g_rgb * mk, gm_d = g_d * mk;
         float4 v;
-        v.x = (pre0 >= 0.0f && pre0 <= 1.0f) ? g_rgb * signf(e0) + x0 : 0.0f;
-        v.y = (pre1 >= 0.0f && pre1 <= 1.0f) ? g_rgb * signf(e1) + x1 : 0.0f;
-        v.z = (pre2 >= 0.0f && pre2 <= 1.0f) ? g_rgb * signf(e2) + x2 : 0.0f;
-        v.w = (valid && a > 0.0f) ? g_d * signf(d - gd) : 0.0f;
+        v.x = (pre0 >= 0.0f && pre0 <= 1.0f) ? gm_rgb * signf(e0) + x0 : 0.0f;
+        v.y = (pre1 >= 0.0f && pre1 <= 1.0f) ? gm_rgb * signf(e1) + x1 : 0.0f;
+        v.z = (pre2 >= 0.0f && pre2 <= 1.0f) ? gm_rgb * signf(e2) + x2 : 0.0f;
+        v.w = (valid && a > 0.0f) ? gm_d * signf(d - gd) : 0.0f;
         v_render[pix] = v;
         v_alphas[pix] = -(v.x * b0 + v.y * b1 + v.z * b2);
     }
@@ -278,8 +283,8 @@ __global__ void strategy_update_kernel(int C, int N, const float4* __restrict__ 
 
 using namespace qed;
 
-int qed_ssim_launch(int C, int W, int H, const float* pred, qed::GtImage gt, float* dmaps, double* stats, float scale, float* v_pred,
-                    cudaStream_t stream);  // ssim.cu
+int qed_ssim_launch(int C, int W, int H, const float* pred, qed::GtImage gt, qed::PixelMask mask, float* dmaps, double* stats, float scale,
+                    float* v_pred, cudaStream_t stream);  // ssim.cu
 
 extern "C" size_t qed_loss_workspace_bytes(int C, int width, int height, float ssim_lambda) {
     if (!(ssim_lambda > 0.0f) || C <= 0) return 0;
@@ -288,13 +293,15 @@ extern "C" size_t qed_loss_workspace_bytes(int C, int width, int height, float s
 }
 
 extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
-                                const void* gt_rgb_, int gt_rgb_is_u8, const float* gt_depth, const float* bg, float rgb_weight,
+                                const void* gt_rgb_, int gt_rgb_is_u8, const float* gt_depth, const void* mask_, int mask_is_u8,
+                                const float* bg, float rgb_weight,
                                 float depth_lambda, float ssim_lambda, float grad_scale, double* stats_dev, float* loss_dev,
                                 float* v_render, float* v_alphas, void* workspace, size_t workspace_bytes, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (C <= 0 || width <= 0 || height <= 0) return QED_ERR_BAD_ARG;
     if (!render || !alphas || !gt_rgb_ || !gt_depth || !bg || !stats_dev || !loss_dev || !v_render || !v_alphas) return QED_ERR_BAD_ARG;
     const GtImage gt_rgb{gt_rgb_, gt_rgb_is_u8 ? 1 : 0};
+    const PixelMask mask{mask_, mask_is_u8 ? 1 : 0};
     if (C > 21845) return QED_ERR_UNSUPPORTED;
     const bool use_ssim = ssim_lambda > 0.0f;
     if (use_ssim) {
@@ -310,19 +317,19 @@ extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* rende
     QED_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, (size_t)C * 8 * sizeof(double), stream));
     const int bx = (int)((HW + kLossThreads * kLossUnroll - 1) / (kLossThreads * kLossUnroll));
     dim3 grid(bx, C);
-    loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, stats_dev);
+    loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, mask, stats_dev);
     QED_LAUNCH_CHECK();
     const double ssim_count = (double)(width - 10) * (double)(height - 10) * 3.0;
     if (use_ssim) {
-        loss_grad_kernel<true><<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg,
+        loss_grad_kernel<true><<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, mask, bg,
                                                                   rgb_weight, depth_lambda, grad_scale, stats_dev, nullptr, nullptr, pred_rgb, nullptr);
         QED_LAUNCH_CHECK();
         // loss term = ssim_lambda * (1 - mean(map)) per camera, mean over cameras
         const float scale = -ssim_lambda * grad_scale / ((float)C * (float)ssim_count);
-        int rc = qed_ssim_launch(C, width, height, pred_rgb, gt_rgb, dmaps, stats_dev, scale, v_ssim, stream);
+        int rc = qed_ssim_launch(C, width, height, pred_rgb, gt_rgb, mask, dmaps, stats_dev, scale, v_ssim, stream);
         if (rc != QED_OK) return rc;
     }
-    loss_grad_kernel<false><<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, bg,
+    loss_grad_kernel<false><<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, mask, bg,
                                                                rgb_weight, depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render),
                                                                v_alphas, nullptr, v_ssim);
     QED_LAUNCH_CHECK();

@@ -107,6 +107,13 @@ def rasterization(
             "qed_splatter/model.py:267-288 and are out of scope for this path")
     if tile_size != 16:
         raise NotImplementedError("tile_size is 16 on this path (qed_splatter/model.py:243)")
+    if torch.is_grad_enabled() and (viewmats.requires_grad or Ks.requires_grad):
+        # gsplat returns v_viewmats; this path does not (qed_project_bwd has no pose gradient).  With splatfacto's
+        # camera_optimizer mode "off" (the default, and what qed_splatter/config.py keeps) the viewmat built at
+        # model.py:212,246 carries no gradient; any other mode would silently train with zero pose gradients.
+        raise NotImplementedError(
+            "gradients with respect to viewmats / Ks (camera optimisation) are not implemented on this path: "
+            "use camera_optimizer mode 'off' or pass viewmats.detach()")
     N = means.shape[0]
     C = viewmats.shape[0]
     assert means.shape == (N, 3), means.shape
@@ -140,8 +147,14 @@ def rasterization(
     def gsplat_lists(m=means2d.detach(), r=radii, d=depths.detach(), t=tiles_per_gauss):
         return ops.isect_tiles(m, r, d, tile_size, tile_width, tile_height, tiles_per_gauss=t, return_offsets=True)[1:]
 
-    if backgrounds is not None and want_rgb and want_depth:
-        backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device, dtype=backgrounds.dtype)], dim=-1)
+    if backgrounds is not None:
+        if want_rgb and want_depth:  # gsplat: the depth channel gets no background
+            backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device, dtype=backgrounds.dtype)], dim=-1)
+        elif not want_rgb:  # "D" / "ED": gsplat replaces the colour background by zeros(C, 1)
+            backgrounds = torch.zeros(C, 1, device=backgrounds.device, dtype=backgrounds.dtype)
+        n_channels = (3 if want_rgb else 0) + int(want_depth)
+        if backgrounds.shape != (C, n_channels):
+            raise ValueError(f"backgrounds must be [C, 3] = [{C}, 3], got {tuple(backgrounds.shape)}")
 
     render_colors, render_alphas = ops.rasterize_to_pixels(
         means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,

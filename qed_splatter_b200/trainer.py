@@ -498,8 +498,9 @@ class SplatTrainer:
     # -- the full step --------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, viewmats: Tensor, Ks: Tensor, width: int, height: int, gt_rgb: Tensor, gt_depth: Tensor,
-             background: Tensor, total_views: Optional[int] = None):
-        """Local views [C_local,...].  Returns (loss[3] device tensor of the local views, refine info|None)."""
+             background: Tensor, total_views: Optional[int] = None, mask: Optional[Tensor] = None):
+        """Local views [C_local,...]; `mask` = the batch's optional loss mask (model.py:93-97).
+        Returns (loss[3] device tensor of the local views -- a fresh copy, safe to keep for logging --, refine info|None)."""
         if self._fused is None:
             raise RuntimeError("rendering needs the CUDA library (backend='cuda'); there is no CPU fallback")
         c, a = self.cfg, self.arena
@@ -524,7 +525,7 @@ class SplatTrainer:
                                gt_rgb, gt_depth, background, render_mode=c.render_mode, rgb_weight=1.0 - c.ssim_lambda,
                                depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, grad_out=gv,
                                activations=3,  # ACT_LOG_SCALES | ACT_LOGIT_OPACITIES (pipeline.py / include/qed_splat.h)
-                               ssim_lambda=c.ssim_lambda, n_chunks=c.comm_chunks if (pipelined and c.chunk_project_bwd) else 1,
+                               mask=mask, ssim_lambda=c.ssim_lambda, n_chunks=c.comm_chunks if (pipelined and c.chunk_project_bwd) else 1,
                                on_chunk=on_chunk if (pipelined and c.chunk_project_bwd) else None)
         self.accumulate_stats(out.packed_grads, out.radii, width, height, packed=True, n_cameras=total)
         if pipelined:
@@ -543,6 +544,7 @@ class SplatTrainer:
         else:
             self._all_reduce(a.grad)
             self.optimizer_step()
+        loss = out.loss.clone()  # out.loss is a buffer the next step overwrites in place
         info = self.maybe_refine(self.step_count)
         self.step_count += 1
-        return out.loss, info
+        return loss, info

@@ -1,5 +1,15 @@
 """Shared helpers for the parity tests."""
+import json
+import os
+
 import torch
+
+# hard caps on the size of an outlier, relative to the largest magnitude of the reference tensor: a threshold flip
+# (alpha < 1/255, T <= 1e-4, SURVEY.md section 7 hard part a) moves a pixel by at most ~4e-3 of full scale, and a
+# per-Gaussian gradient by the contribution of the few pixels that flipped
+MAX_OUTLIER_FWD = 5e-3
+MAX_OUTLIER_GRAD = 5e-2
+_LOG = os.environ.get("QED_PARITY_LOG")  # optional: append one JSON line per comparison (tolerance calibration)
 
 
 def mismatch_fraction(a: torch.Tensor, b: torch.Tensor, rtol: float, atol: float) -> float:
@@ -10,12 +20,26 @@ def mismatch_fraction(a: torch.Tensor, b: torch.Tensor, rtol: float, atol: float
     return float(bad.double().mean()) if bad.numel() else 0.0
 
 
-def assert_close_frac(a, b, rtol, atol, max_frac, what=""):
-    """allclose with a bounded mismatch fraction: threshold tests (alpha < 1/255, T <= 1e-4) flip on 1-ulp
-    differences between exp and ex2.approx and move a pixel by up to ~4e-3 (SURVEY.md §7 hard part a)."""
+def assert_close_frac(a, b, rtol, atol, max_frac, what="", max_outlier=None):
+    """allclose with a bounded mismatch fraction AND a bounded outlier size.
+
+    Threshold tests (alpha < 1/255, T <= 1e-4) flip on 1-ulp differences between exp and ex2.approx, so a small
+    fraction of elements may sit outside rtol/atol (SURVEY.md section 7 hard part a) -- but never by more than
+    `max_outlier` x the largest magnitude of the reference tensor (default: MAX_OUTLIER_FWD when rtol <= 1e-4,
+    the forward tolerance of north_star, else MAX_OUTLIER_GRAD)."""
+    if max_outlier is None:
+        max_outlier = MAX_OUTLIER_FWD if rtol <= 1e-4 else MAX_OUTLIER_GRAD
     frac = mismatch_fraction(a, b, rtol, atol)
-    err = float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max()) if a.numel() else 0.0
+    ad, bd = a.detach().double().cpu(), b.detach().double().cpu()
+    err = float((ad - bd).abs().max()) if a.numel() else 0.0
+    scale = max(float(bd.abs().max()), 1e-30) if b.numel() else 1.0
+    if _LOG:
+        with open(_LOG, "a") as f:
+            f.write(json.dumps({"what": what, "frac": frac, "max_abs_err": err, "scale": scale, "rel_outlier": err / scale, "rtol": rtol,
+                                "atol": atol, "max_frac": max_frac, "max_outlier": max_outlier, "numel": a.numel()}) + "\n")
     assert frac <= max_frac, f"{what}: {frac:.3e} of elements outside rtol={rtol} atol={atol} (max abs err {err:.3e})"
+    assert err <= max_outlier * scale + atol, (f"{what}: largest error {err:.3e} exceeds the outlier cap {max_outlier:g} x max|ref| = "
+                                               f"{max_outlier * scale:.3e}")
     return frac, err
 
 
