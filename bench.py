@@ -12,17 +12,19 @@ gradient arena and of the densification statistics (weak scaling).
 
 metric  = fwd+bwd RGB+depth Mpix/s (whole job: N*H*W*K / time, device-timed, max over ranks).
 value   = fused C-ABI pipeline with everything resident in HBM.
-e2e     = the same work through the public API a qed-splatter maintainer binds: `rasterization()`
-          (gsplat surface, torch autograd) + `depth_supervised_loss()` (model.py:295-306, 73-118 as one autograd op;
-          `--torch-loss` writes those lines with torch ops as the reference does) + `backward()`, with the step's
-          inputs (camera, ground-truth RGB as the uint8 image cache of config.py:37 + float depth) copied from pinned host
-          memory and the loss read back every
-          step.  The Gaussian parameters are model state and stay resident, as in the reference.  For N>1 the
-          five parameter gradients go out as one coalesced NCCL group call (as DDP / FSDP issue them).
+e2e     = the same work through the reference-facing call: `rasterization()` (gsplat surface, torch autograd) followed by
+          THE REFERENCE'S OWN LINES for the loss, written with torch ops exactly as qed_splatter/model.py:295-306 and
+          :87-116 write them (+ the L1 line of splatfacto's parent loss), then `backward()`; the step's inputs (camera,
+          ground-truth RGB as the uint8 image cache of config.py:37 + float depth) are copied from pinned host memory
+          and the loss is read back every step.  The Gaussian parameters are model state and stay resident, as in
+          the reference.  For N>1 the five parameter gradients go out as one coalesced NCCL group call (as DDP / FSDP
+          issue them).
+e2e_fused_loss = the same with the package's drop-in for those lines, `depth_supervised_loss()` (one autograd op).
 train   = full trainer iterations/s (trainer.SplatTrainer: 0.8 L1 + 0.2 (1-SSIM) + 0.2 depth-L1, Adam, strategy
           statistics, pipelined gradient all-reduce) -- the second half of BASELINE.json's metric.
 --impl reference = the CPU arm: the oracle (`oracle/`, a port — the reference's own arithmetic lives in the
-          un-vendored gsplat and cannot be run here) on the host cores on a bounded 1/16 sample.
+          un-vendored gsplat and cannot be run here) on the host cores on a bounded sample of THE SAME workload (see
+          cpu_sample_step); `cpu_baseline` in the GPU arm's line is the same sample, same code.
 """
 from __future__ import annotations
 
@@ -42,9 +44,19 @@ METRIC = "fwd+bwd RGB+depth Mpix/s"
 UNIT = "Mpix/s"
 PARAM_FLOATS = 3 + 4 + 3 + 1 + 48  # means, quats, scales, opacity, SH(16x3) = 59 floats / Gaussian
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
-# workload (profiles/r01_raster_ncu_summary.txt: raster_bwd_ws_kernel / raster_fwd_ws_kernel on the exact tile lists); None = not captured
-NCU_DRAM_BYTES = {"raster_bwd": 140.47e6 + 7.91e6, "raster_fwd": 41.19e6 + 12.53e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per step and stage, from the committed `ncu --set full` capture of one
+# step of this workload: profiles/r02_dram_bytes.json, written by benchmarks/ncu_dram_bytes.py from the .ncu-rep
+# (profiles/README.md has the command).  Absent file / stage -> traffic null.
+DRAM_BYTES_JSON = os.path.join(ROOT, "profiles", "r02_dram_bytes.json")
+
+
+def load_ncu_traffic():
+    try:
+        d = json.load(open(DRAM_BYTES_JSON))
+        return {k: float(v["dram_bytes"]) for k, v in d.get("stages", {}).items()}, d.get("workload")
+    except Exception:
+        return {}, None
+
 
 # SURVEY.md §8(d) per-unit figures (D = 4 channels)
 FLOP_PER_PAIR_FWD = 30.0
@@ -71,8 +83,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-bucket", action="store_true", help="e2e, N>1: all-reduce one flat bucket of gradient views instead of a coalesced group call")
     ap.add_argument("--gt-float", action="store_true", help="e2e: ground-truth RGB as float32 instead of the uint8 image cache")
-    ap.add_argument("--torch-loss", action="store_true", help="e2e: write the loss with torch ops as the reference does instead of depth_supervised_loss")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--repeats", type=int, default=5, help="extra timed windows of K steps after the measured one (spread: median / p10 / p90)")
+    ap.add_argument("--no-multi-gpu-check", action="store_true", help="N>1: skip the N-rank == 1-rank gradient / replica-identity check")
     return ap.parse_args()
 
 
@@ -80,20 +93,54 @@ def parse_args():
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / power / throttle reasons sampled DURING the timed regions.  NVML from a thread (every 5 ms, so even a
+    30 ms window holds several samples); `nvidia-smi -lms` as the fallback when pynvml is not importable."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.005
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.proc = None
+        self.thread = None
         self.lines = []
+        self.samples = []  # (sm_mhz, power_w, reasons bitmask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.how = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(self.PERIOD_S)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
 
@@ -101,77 +148,154 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    @staticmethod
+    def _pct(v, q):
+        return v[min(len(v) - 1, max(0, int(round(q * (len(v) - 1)))))] if v else None
+
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], None, set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+        sm, power, reasons = [], [], set()
+        if self.how == "nvml":
+            self._stop.set()
+            self.thread.join(timeout=1)
+            # NVML bits: 0x8 hw_slowdown, 0x20 sw_thermal, 0x40 hw_thermal, 0x4 sw_power_cap
+            for f, pw, r in self.samples:
+                sm.append(f)
+                power.append(pw)
+                for bit, name in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")):
+                    if r & bit:
+                        reasons.add(name)
+            mx = self.sm_max
+        elif self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
             try:
-                sm.append(float(f[1]))
-                mx = float(f[2])
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            mx = None
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                    power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+        return {"sm_mhz": self._pct(sm, 0.5), "sm_mhz_p10": self._pct(sm, 0.1), "sm_mhz_p90": self._pct(sm, 0.9), "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None, "sampler": self.how}
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm (oracle) on a bounded sample of the workload
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_step(sample, torch, oracle):
-    names = ("means", "quats", "scales", "opacities", "sh")
-    leaves = {k: getattr(sample, k).clone().requires_grad_(True) for k in names}
-    r, a, _ = oracle.rasterization(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["sh"],
-                                   sample.viewmats, sample.Ks, sample.width, sample.height, sh_degree=3, render_mode="RGB+ED")
-    rgb, d = oracle.composite_and_fill(r, a, torch.tensor([0.1, 0.2, 0.3]))
-    loss = oracle.rgb_l1_loss(rgb, sample.gt_rgb) + oracle.depth_l1_loss(d, sample.gt_depth, 0.2)
-    loss.backward()
-    return float(loss)
+CPU_TILE_STRIDE = 8  # every 8th tile column x every 8th tile row = 1/64 of the tiles, spread over the whole image
 
 
-def make_cpu_sample(args, n_steps_total: int = 3):
-    """A bounded sample of the workload for the CPU arm: 1/k of the Gaussians and 1/k of the pixels at the same field
-    of view, with k chosen so that `n_steps_total` oracle steps finish in a few minutes (~5 s per step at k = 16 on
-    16 cores)."""
-    from qed_splatter_b200.scenes import scene_s1
+def workload_name(args) -> str:
+    return (f"S1 (BASELINE.json configs[1]): {args.gaussians} Gaussians (SH degree 3), one {args.width}x{args.height} view per GPU, "
+            f"{args.mode} forward + RGB-L1/depth-L1 loss + backward to means/quats/scales/opacities/SH")
 
-    k = 16 if n_steps_total <= 8 else (64 if n_steps_total <= 40 else 256)
-    r = int(round(k ** 0.5))
-    n = max(args.gaussians // k, 1000)
-    w, h = args.width // r, args.height // r
-    return scene_s1(N=n, width=w, height=h, f=1200.0 * w / 1920.0), f"1/{k} sample: {n} Gaussians, one {w}x{h} view, RGB+ED fwd+loss+bwd, float32"
+
+def bench_config(args, world: int) -> dict:
+    """The `config` object: names the workload; identical in the GPU arm and in `--impl reference`."""
+    return {
+        "workload": workload_name(args),
+        "parallelism": f"view-sharded x{world}, replicated Gaussians, gradient arena ({PARAM_FLOATS * 4} B/Gaussian) summed over the ranks every step "
+                       "(densification accumulators are all-reduced when a refine step consumes them, not per step)",
+        "cache": "inputs larger than L2 (236 MB parameters + ~0.3 GB intermediates per step vs 126 MB L2); no explicit flush",
+        "sort": args.sort,
+    }
+
+
+class CpuSample:
+    """The CPU arm's bounded sample of the SAME workload (full Gaussian count, full resolution, same camera):
+    projection + SH and the tile intersection (incl. the 64-bit key sort) run on everything, forward and backward;
+    compositing + loss forward / backward run on a systematic 1/64 sample of the 16x16 tiles (every 8th tile row and
+    column, spread over the whole image, so the sample sees the image's mean splat density).  One step's time for the
+    whole image is then   t = t_project+SH(fwd+bwd) + t_intersect + (t_composite(fwd+bwd) + t_loss) / sampled_fraction,
+    every term measured in that step; Mpix/s = W * H / t."""
+
+    def __init__(self, args):
+        import torch
+
+        from qed_splatter_b200.scenes import scene_s1
+
+        self.W, self.H = args.width, args.height
+        self.mode = args.mode
+        self.s = scene_s1(N=args.gaussians, width=self.W, height=self.H)
+        self.tw, self.th = (self.W + 15) // 16, (self.H + 15) // 16
+        keep = torch.zeros(self.th, self.tw, dtype=torch.bool)
+        keep[CPU_TILE_STRIDE // 2 - 1::CPU_TILE_STRIDE, CPU_TILE_STRIDE // 2 - 1::CPU_TILE_STRIDE] = True
+        self.keep = keep.flatten()
+        self.picks = torch.nonzero(self.keep).flatten().tolist()
+        self.pix = keep.repeat_interleave(16, 0).repeat_interleave(16, 1)[:self.H, :self.W][None, :, :, None].float()
+        self.frac = float(self.pix.sum()) / (self.W * self.H)
+        self.desc = (f"same workload ({args.gaussians} Gaussians, {self.W}x{self.H}, {args.mode}, float32): projection+SH and tile "
+                     f"intersection/sort fwd+bwd over everything; compositing+loss fwd+bwd on a systematic sample of {len(self.picks)} of "
+                     f"{self.tw * self.th} tiles ({self.frac:.4f} of the pixels), that part scaled by 1/{self.frac:.4f}")
+
+    def step(self):
+        import torch
+
+        import oracle
+
+        s, W, H, tw, th = self.s, self.W, self.H, self.tw, self.th
+        leaves = {k: getattr(s, k).clone().requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "sh")}
+        t = [time.perf_counter()]
+        radii, means2d, depths, conics, _ = oracle.fully_fused_projection(leaves["means"], leaves["quats"], leaves["scales"], s.viewmats, s.Ks, W, H)
+        dirs = leaves["means"][None] - oracle.torch_impl.camera_positions(s.viewmats)[:, None, :]
+        cols = torch.clamp_min(oracle.spherical_harmonics(3, dirs, leaves["sh"][None], masks=radii > 0) + 0.5, 0.0)
+        cols = torch.cat([cols, depths[..., None]], -1)
+        opac = leaves["opacities"][None]
+        t.append(time.perf_counter())  # 1: project + SH forward
+        _, ids, flat = oracle.isect_tiles(means2d, radii, depths, 16, tw, th)
+        offs = oracle.isect_offset_encode(ids, 1, tw, th)
+        t.append(time.perf_counter())  # 2: intersection
+        b = torch.cat([offs.flatten().long(), torch.tensor([flat.numel()])])
+        lens = torch.where(self.keep, b[1:] - b[:-1], torch.zeros(1, dtype=torch.long))
+        off_sub = (torch.cumsum(lens, 0) - lens).reshape(1, th, tw).to(torch.int32)
+        flat_sub = torch.cat([flat[b[i]:b[i + 1]] for i in self.picks]) if self.picks else flat[:0]
+        render, alpha, _ = oracle.rasterize_to_pixels(means2d, conics, cols, opac, W, H, 16, off_sub, flat_sub)
+        if self.mode == "RGB+ED":
+            render = torch.cat([render[..., :3], render[..., 3:] / alpha.clamp(min=1e-10)], -1)
+        rgb, d = oracle.composite_and_fill(render, alpha, torch.tensor([0.1, 0.2, 0.3]))
+        loss = 0.8 * ((rgb - s.gt_rgb).abs() * self.pix).sum() / (self.pix.sum() * 3) + oracle.depth_l1_loss(d, s.gt_depth, 0.2, mask=self.pix)
+        t.append(time.perf_counter())  # 3: composite + loss forward (sampled tiles)
+        g = torch.autograd.grad(loss, [means2d, conics, cols, leaves["opacities"]], allow_unused=True)
+        t.append(time.perf_counter())  # 4: composite + loss backward (sampled tiles)
+        torch.autograd.backward([means2d, conics, cols], [g[0], g[1], g[2]])
+        t.append(time.perf_counter())  # 5: project + SH backward
+        d_ = [b_ - a_ for a_, b_ in zip(t[:-1], t[1:])]
+        whole = d_[0] + d_[1] + d_[4] + (d_[2] + d_[3]) / self.frac
+        return whole, sum(d_), float(loss)
 
 
 def run_cpu_baseline(args, steps: int, warmup: int):
     import torch
 
-    import oracle
-
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample, desc = make_cpu_sample(args, steps + warmup)
+    sample = CpuSample(args)
     for _ in range(warmup):
-        cpu_sample_step(sample, torch, oracle)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_sample_step(sample, torch, oracle)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    mpix = sample.width * sample.height / dt / 1e6
-    return {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "ms_per_step": dt * 1e3}
+        sample.step()
+    whole, spent = [], 0.0
+    for _ in range(max(steps, 1)):
+        w, t, _ = sample.step()
+        whole.append(w)
+        spent += t
+    whole.sort()
+    dt = sum(whole) / len(whole)
+    mpix = args.width * args.height / dt / 1e6
+    return {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample.desc, "ms_per_step": dt * 1e3,
+            "cpu_seconds_spent": spent, "steps": len(whole)}
 
 
 def main_reference(args):
@@ -183,13 +307,71 @@ def main_reference(args):
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"S1: {args.gaussians} Gaussians, one {args.width}x{args.height} view per GPU, RGB+ED fwd+loss+bwd",
-                   "note": "CPU oracle port (gsplat reference rasterizer restated in torch) on host cores, bounded sample"},
+        "config": bench_config(args, max(args.gpus, 1)),
+        "note": "CPU arm: the oracle port (gsplat's reference rasterizer restated in torch) on the host cores; ms_per_step is the time of one "
+                "whole-image step derived from the bounded sample described in cpu_baseline.sample",
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# N > 1: the view-sharded step equals the single-rank step (SURVEY.md section 8e "Check"); never inside a timed region
+# ------------------------------------------------------------------------------------------------
+def run_multi_gpu_check(torch, dist, dev, rank, world):
+    """1. N ranks x 1 view, gradients summed over the ranks  ==  1 rank x N views (the whole batch in one process).
+    2. 3 trainer steps (render, loss, backward, gradient reduction, Adam): every replica holds bit-identical parameters,
+       and they equal (to float tolerance: the reduction order differs) a single-process trainer fed all N views."""
+    from qed_splatter_b200.pipeline import FusedSplatStep
+    from qed_splatter_b200.scenes import scene_s0
+    from qed_splatter_b200.trainer import SplatTrainer, TrainConfig
+
+    s = scene_s0(N=20000, C=world, size=160).to(dev)
+    bg = torch.tensor([0.2, 0.3, 0.4], device=dev)
+    sl = slice(rank, rank + 1)
+    mine = dict(viewmats=s.viewmats[sl].contiguous(), Ks=s.Ks[sl].contiguous(), gt_rgb=s.gt_rgb[sl].contiguous(), gt_depth=s.gt_depth[sl].contiguous())
+    fs = FusedSplatStep(dev)
+    whole = fs.step(s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, 3, s.gt_rgb, s.gt_depth, bg)
+    ref = {k: v.clone() for k, v in whole.grads.items()}
+    part = fs.step(s.means, s.quats, s.scales, s.opacities, s.sh, mine["viewmats"], mine["Ks"], s.width, s.height, 3, mine["gt_rgb"],
+                   mine["gt_depth"], bg, grad_scale=1.0 / world)
+    res = {"scene": f"S0-style: 20000 Gaussians, {world} views 160x160, one view per rank", "gradients": {}}
+    ok = True
+    for k, v in part.grads.items():
+        g = v.clone()
+        dist.all_reduce(g)
+        d = (g - ref[k]).abs()
+        scale = float(ref[k].abs().mean()) + 1e-20
+        frac = float((d > 1e-4 * ref[k].abs() + 1e-5 * scale).float().mean())
+        res["gradients"][k] = {"max_abs_diff_over_mean_abs": float(d.max()) / scale, "frac_outside_rtol1e-4": frac}
+        ok = ok and frac < 1e-3 and float(d.max()) / scale < 1e-2
+    identical, vs_single = True, None
+    log_s, logit_o = torch.log(s.scales), torch.logit(s.opacities)
+    tr = SplatTrainer(s.means.clone(), s.quats.clone(), log_s.clone(), logit_o.clone(), s.sh.clone(), cfg=TrainConfig(), rank=rank, world_size=world, backend="cuda")
+    tr.step_count = 3000
+    for _ in range(3):
+        tr.step(mine["viewmats"], mine["Ks"], s.width, s.height, mine["gt_rgb"], mine["gt_depth"], bg, total_views=world)
+    gathered = [torch.empty_like(tr.arena.param) for _ in range(world)]
+    dist.all_gather(gathered, tr.arena.param)
+    for r in range(1, world):
+        identical = identical and torch.equal(gathered[0], gathered[r])
+    single = SplatTrainer(s.means.clone(), s.quats.clone(), log_s.clone(), logit_o.clone(), s.sh.clone(), cfg=TrainConfig(), rank=0, world_size=1, backend="cuda")
+    single.step_count = 3000
+    for _ in range(3):
+        single.step(s.viewmats, s.Ks, s.width, s.height, s.gt_rgb, s.gt_depth, bg, total_views=world)
+    d = (single.arena.param - tr.arena.param).abs()
+    upd = (single.arena.param - torch.cat([t.reshape(-1) for t in (s.means, s.quats, log_s, logit_o, s.sh)])[:single.arena.param.numel()]).abs() \
+        if single.arena.param.numel() == sum(t.numel() for t in (s.means, s.quats, log_s, logit_o, s.sh)) else None
+    vs_single = {"max_abs_param_diff": float(d.max()), "frac_above_1e-5": float((d > 1e-5).float().mean()),
+                 "mean_abs_update": float(upd.mean()) if upd is not None else None}
+    ok = ok and identical and vs_single["frac_above_1e-5"] < 1e-2
+    res.update({"replicas_bit_identical_after_3_steps": bool(identical), "vs_single_process_trainer": vs_single, "ok": bool(ok), "world": world})
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["ok_all_ranks"] = bool(flag.item() > 0)
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -269,27 +451,43 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_window(fn, steps):
+        """`steps` calls of fn bracketed by barrier + synchronize on both sides, device-timed, max over ranks -> ms."""
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t_ = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    def pct(v, q):
+        v = sorted(v)
+        return v[min(len(v) - 1, max(0, int(round(q * (len(v) - 1)))))]
+
+    def spread(windows_ms, steps):
+        per = [w / steps for w in windows_ms]
+        return {"windows": len(per), "steps_per_window": steps, "ms_per_step_median": pct(per, 0.5), "ms_per_step_p10": pct(per, 0.1),
+                "ms_per_step_p90": pct(per, 0.9), "ms_per_step_min": min(per), "ms_per_step_max": max(per)}
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(W_):
         out = step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        out = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    # THE measurement (contract): exactly K steps, one window
+    ms_total = timed_window(step, K)
     ms_per_step = ms_total / K
     value = world * width * height / (ms_per_step * 1e-3) / 1e6
+    # R more windows of K steps: run-to-run spread (median / p10 / p90), and enough wall time for >= 10 clock samples
+    windows = [ms_total] + [timed_window(step, K) for _ in range(args.repeats)]
+    clocks = sampler.stop() if rank == 0 else None
+    repeats = spread(windows, K)
 
     # ---- stage timing (same inputs, CUDA events between the stages on the launching stream) ----
     stage_ms = {}
@@ -303,6 +501,7 @@ def main_ours(args):
     fs.marks = None
     n_visible = int((out.radii > 0).sum())
     M = out.n_isects
+    n_exact = fs.n_isects_exact()
     loss = [float(x) for x in out.loss.tolist()]
 
     # ---- pair counters for the compositing roofline (instrumented launches, outside any timed region) ----
@@ -321,24 +520,16 @@ def main_ours(args):
         tr.step_count = 3000  # SH degree 3, no opacity reset inside the timed window
         for _ in range(W_):
             tr.step(viewmats, Ks, width, height, gt_rgb, gt_depth, bg, total_views=world)
-        barrier()
-        e0.record()
-        for _ in range(K):
-            tr.step(viewmats, Ks, width, height, gt_rgb, gt_depth, bg, total_views=world)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        tms = float(t.item()) / K
-        train = {"train_iters_per_s": 1e3 / tms, "ms_per_step": tms, "views_per_s": world * 1e3 / tms,
+        tw_ = [timed_window(lambda: tr.step(viewmats, Ks, width, height, gt_rgb, gt_depth, bg, total_views=world), K) for _ in range(1 + min(args.repeats, 2))]
+        tms = tw_[0] / K
+        train = {"train_iters_per_s": 1e3 / tms, "repeats": spread(tw_, K), "ms_per_step": tms, "views_per_s": world * 1e3 / tms,
                  "loss": "0.8 L1 + 0.2 (1-SSIM) + 0.2 depth-L1", "optimizer": "fused Adam over the 59-float/Gaussian arena",
                  "comm_chunks": tcfg.comm_chunks if world > 1 else 1}
         del tr
         torch.cuda.empty_cache()
 
     # ---- e2e through the public API with host buffers ----
-    e2e = None
+    e2e = e2e_fused_loss = None
     if not args.no_e2e:
         params = [t.clone().requires_grad_(True) for t in (means, quats, scales, opac, sh)]
         # N > 1: the five parameter gradients are reduced as ONE coalesced NCCL group call (what DDP / FSDP do), no
@@ -360,7 +551,7 @@ def main_ours(args):
         rgb_d, depth_d = torch.empty(e2e_rgb_h.shape, dtype=e2e_rgb_h.dtype, device=dev), torch.empty_like(gt_depth)
         cam_ready, gt_ready = torch.cuda.Event(), torch.cuda.Event()
 
-        def e2e_step():
+        def e2e_step(reference_lines: bool):
             copy_stream.wait_stream(torch.cuda.current_stream())  # previous step is done with the buffers
             with torch.cuda.stream(copy_stream):
                 vm_d.copy_(vm_h, non_blocking=True)
@@ -383,16 +574,23 @@ def main_ours(args):
                                                 sh_degree=3, sparse_grad=False, absgrad=True, rasterize_mode="classic")
             info["means2d"].retain_grad()
             torch.cuda.current_stream().wait_event(gt_ready)
-            if args.torch_loss:
+            if reference_lines:
                 rgb_gt = rgb_gt.float() / 255.0 if rgb_gt.dtype == torch.uint8 else rgb_gt  # splatfacto get_gt_img
-                # qed_splatter/model.py:295-306 and :87-116 as the reference writes them (a dozen torch element-wise ops)
-                rgb = torch.clamp(render[..., :3] + (1 - alpha) * bg, 0.0, 1.0)
-                depth = render[..., 3:4]
-                depth = torch.where(alpha > 0, depth, depth.detach().max())
-                valid = torch.isfinite(depth) & torch.isfinite(d_gt) & (d_gt > 0)
-                l_rgb = 0.8 * (rgb_gt - rgb).abs().mean()
-                l_d = 0.2 * ((depth - d_gt).abs() * valid).sum() / valid.sum().clamp(min=1)
-                loss_t = (l_rgb + l_d) / world
+                # qed_splatter/model.py:295-297, 304-306 as written
+                rgb = render[:, ..., :3] + (1 - alpha) * bg
+                rgb = torch.clamp(rgb, 0.0, 1.0)
+                depth_im = render[:, ..., 3:4]
+                depth_im = torch.where(alpha > 0, depth_im, depth_im.detach().max())
+                # qed_splatter/model.py:101-116 as written (boolean-index gathers and the numel() test included)
+                valid_mask = torch.isfinite(depth_im) & torch.isfinite(d_gt) & (d_gt > 0.0)
+                valid_depth_out = depth_im[valid_mask]
+                valid_depth_batch = d_gt[valid_mask]
+                if valid_depth_out.numel() > 0:
+                    l_d = torch.abs(valid_depth_out - valid_depth_batch).mean()
+                else:
+                    l_d = torch.tensor(0.0, device=depth_im.device)
+                l_rgb = 0.8 * torch.abs(rgb_gt - rgb).mean()  # the L1 line of splatfacto's parent loss (model.py:83-85)
+                loss_t = (l_rgb + 0.2 * l_d) / world
             else:
                 # the same lines through the package's drop-in for them (losses.depth_supervised_loss)
                 loss_t = depth_supervised_loss(render, alpha, rgb_gt, d_gt, bg, rgb_weight=0.8, depth_lambda=0.2)[0] / world
@@ -406,24 +604,33 @@ def main_ours(args):
                             dist.all_reduce(p_.grad)
             return float(loss_t.item())  # D2H read of the step's result
 
-        for _ in range(W_):
-            e2e_step()
-        barrier()
-        e0.record()
-        for _ in range(K):
-            e2e_loss = e2e_step()
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item()) / K
         h2d = vm_h.numel() * 4 + K_h.numel() * 4 + e2e_rgb_h.numel() * e2e_rgb_h.element_size() + gt_depth_h.numel() * 4
-        e2e = {"value": world * width * height / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": e2e_ms, "loss": e2e_loss,
-               "api": "qed_splatter_b200.rasterization (gsplat surface) + " +
-                      ("torch autograd loss as qed_splatter/model.py writes it" if args.torch_loss else
-                       "qed_splatter_b200.depth_supervised_loss (model.py:295-306, 73-118 as one autograd op)") + " + backward()"}
+        last = {}
+
+        def run_e2e(reference_lines: bool):
+            def one():
+                last["loss"] = e2e_step(reference_lines)
+
+            for _ in range(W_):
+                one()
+            wins = [timed_window(one, K) for _ in range(1 + min(args.repeats, 2))]
+            ms_ = wins[0] / K
+            return {"value": world * width * height / (ms_ * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_, "loss": last["loss"], "repeats": spread(wins, K),
+                    "api": "qed_splatter_b200.rasterization (gsplat surface) + " +
+                           ("the reference's own loss lines in torch (qed_splatter/model.py:295-306, 101-116 + splatfacto's L1 line)"
+                            if reference_lines else "qed_splatter_b200.depth_supervised_loss (model.py:295-306, 73-118 as one autograd op)") +
+                           " + backward(); inputs from pinned host memory, loss read back, every step"}
+
+        e2e = run_e2e(True)               # headline: the model's own lines on top of the drop-in call
+        e2e_fused_loss = run_e2e(False)   # with the package's fused drop-in for those lines
+        del params
+        torch.cuda.empty_cache()
+
+    # ---- N > 1: N ranks x 1 view == 1 rank x N views, replicas identical (outside every timed region) ----
+    multi_gpu_check = None
+    if world > 1 and not args.no_multi_gpu_check:
+        multi_gpu_check = run_multi_gpu_check(torch, dist, dev, rank, world)
 
     if rank == 0:
         peaks = {}
@@ -434,6 +641,9 @@ def main_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        traffic, traffic_workload = load_ncu_traffic()
+        if traffic_workload is not None and traffic_workload != workload_name(args):
+            traffic = {}  # the capture belongs to another workload
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s at the SM clock seen during the timed region
 
         def fp32_roof(name, pairs, evaluated, flop_per_pair):
@@ -444,7 +654,7 @@ def main_ours(args):
                 return None
             ach = pairs * flop_per_pair / (t_ms * 1e-3) / 1e12
             return {"kernel": name, "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-                    "traffic": NCU_DRAM_BYTES.get(name), "ms": t_ms, "pairs_composited": pairs, "pairs_evaluated": evaluated,
+                    "traffic": traffic.get(name), "ms": t_ms, "pairs_composited": pairs, "pairs_evaluated": evaluated,
                     "flop_per_pair": flop_per_pair,
                     "peak_source": f"derived: 148 SM x 128 lanes x 2 FLOP x {sm_mhz:.0f} MHz (median SM clock sampled during the timed region)"}
 
@@ -453,8 +663,10 @@ def main_ours(args):
             if not t_ms:
                 return None
             ach = bytes_ / (t_ms * 1e-3) / 1e9
+            tr_ = traffic.get(name)
             return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": NCU_DRAM_BYTES.get(name), "ms": t_ms, "algorithmic_bytes": bytes_, "peak_source": hbm_src}
+                    "traffic": tr_, "traffic_over_algorithmic": (tr_ / bytes_) if tr_ else None, "ms": t_ms, "algorithmic_bytes": bytes_,
+                    "peak_source": hbm_src}
 
         tile_bits = (((width + 15) // 16) * ((height + 15) // 16)).bit_length()
         tile_passes = (tile_bits + 7) // 8
@@ -481,18 +693,17 @@ def main_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": f"S1 (BASELINE.json configs[1]): {N} Gaussians (SH degree 3), one {width}x{height} view per GPU, "
-                            f"{args.mode} forward + RGB-L1/depth-L1 loss + backward to means/quats/scales/opacities/SH",
-                "parallelism": f"view-sharded x{world}, replicated Gaussians, NCCL all-reduce of the {PARAM_FLOATS * 4} B/Gaussian gradient arena every step "
-                               "(densification accumulators are all-reduced when a refine step consumes them, not per step)",
-                "cache": "inputs larger than L2: 236 MB parameters + %.0f MB intermediates per step vs 126 MB L2; no explicit flush" % ((N * 150 + M * 24) / 1e6),
-                "sort": args.sort, "n_visible": n_visible, "n_isects": M, "loss": loss,
-                "mean_gaussians_composited_per_pixel": counters.get("fwd_pairs_contributing", 0) / float(width * height),
-            },
+            "config": bench_config(args, world),
+            "workload_stats": {"n_visible": n_visible, "n_isects": M, "n_isects_exact": n_exact, "loss": loss,
+                               "mean_gaussians_composited_per_pixel": counters.get("fwd_pairs_contributing", 0) / float(width * height),
+                               "intermediates_mb_per_step": (N * 150 + M * 24) / 1e6},
+            "repeats": repeats,
             "clocks": clocks,
             "e2e": e2e,
+            "e2e_fused_loss": e2e_fused_loss,
             "train": train,
+            "multi_gpu_check": multi_gpu_check,
+            "traffic_source": "profiles/r02_dram_bytes.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per step and stage)" if traffic else None,
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
             "roofline": dominant,
@@ -501,8 +712,8 @@ def main_ours(args):
             "pair_counters": counters,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = run_cpu_baseline(args, steps=2, warmup=1)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cb = run_cpu_baseline(args, steps=2, warmup=1)  # the same sample and code as `--impl reference`
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_seconds_spent")}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))

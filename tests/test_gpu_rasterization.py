@@ -108,3 +108,34 @@ def test_rejects_unsupported(cuda):
         rasterization(**a, width=32, height=32, render_mode="nope", sh_degree=3)
     with pytest.raises(RuntimeError):
         rasterization(**{k: v.cpu() for k, v in a.items()}, width=32, height=32, sh_degree=3)
+
+
+def test_advisor_guards(cuda):
+    """Round-1 advisor findings: pose gradients raise instead of silently being zero; 'D' / 'ED' renders ignore a colour
+    background (gsplat: zeros(C, 1)); host / wrong-dtype tensors raise before a raw pointer reaches a kernel."""
+    from qed_splatter_b200 import depth_supervised_loss
+    from qed_splatter_b200.pipeline import FusedSplatStep
+
+    s = scene_s0(N=400, C=2, size=48)
+    a = scene_args(s, cuda)
+    with pytest.raises(NotImplementedError):
+        rasterization(**{**a, "viewmats": a["viewmats"].clone().requires_grad_(True)}, width=48, height=48, sh_degree=3)
+    bg = torch.tensor([[0.9, 0.1, 0.5], [0.2, 0.3, 0.4]], device=cuda)
+    d_bg, _, _ = rasterization(**a, width=48, height=48, sh_degree=3, render_mode="D", backgrounds=bg)
+    d_no, _, _ = rasterization(**a, width=48, height=48, sh_degree=3, render_mode="D")
+    assert torch.equal(d_bg, d_no)
+    with pytest.raises(ValueError):
+        rasterization(**a, width=48, height=48, sh_degree=3, render_mode="RGB", backgrounds=bg[:1])
+    render, alpha, _ = rasterization(**a, width=48, height=48, sh_degree=3, render_mode="RGB+D")
+    gt_rgb, gt_depth = s.gt_rgb.to(cuda), s.gt_depth.to(cuda)
+    with pytest.raises(RuntimeError):
+        depth_supervised_loss(render, alpha, s.gt_rgb, gt_depth, bg[0])  # CPU image cache
+    with pytest.raises(TypeError):
+        depth_supervised_loss(render, alpha, gt_rgb, gt_depth.double(), bg[0])
+    with pytest.raises(TypeError):
+        depth_supervised_loss(render, alpha, gt_rgb.half(), gt_depth, bg[0])
+    fs = FusedSplatStep(cuda)
+    with pytest.raises(RuntimeError):
+        fs.step(a["means"], a["quats"], a["scales"], a["opacities"], a["colors"], a["viewmats"], a["Ks"], 48, 48, 3, gt_rgb, s.gt_depth, bg[0])
+    with pytest.raises(TypeError):
+        fs.step(a["means"], a["quats"], a["scales"], a["opacities"], a["colors"], a["viewmats"], a["Ks"], 48, 48, 3, gt_rgb, gt_depth, bg[0].double())
