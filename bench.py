@@ -79,6 +79,9 @@ def parse_args():
     ap.add_argument("--mode", default="RGB+ED", choices=["RGB+ED", "RGB+D"])
     ap.add_argument("--sort", default="two_level", choices=["two_level", "own", "cub"])
     ap.add_argument("--comm-chunks", type=int, default=1, help="Gaussian ranges of the projection backward whose SH gradients are all-reduced while the next range computes (N>1)")
+    ap.add_argument("--comm", default="exchange", choices=["exchange", "nccl"],
+                    help="N>1, how the gradient arena is summed over the ranks: this library's NVLink path (view-colour exchange + one "
+                         "all-reduce kernel, comm.ViewShardedGradients) or torch.distributed / NCCL all-reduce (the library baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-bucket", action="store_true", help="e2e, N>1: all-reduce one flat bucket of gradient views instead of a coalesced group call")
@@ -347,6 +350,26 @@ def run_multi_gpu_check(torch, dist, dev, rank, world):
         frac = float((d > 1e-4 * ref[k].abs() + 1e-5 * scale).float().mean())
         res["gradients"][k] = {"max_abs_diff_over_mean_abs": float(d.max()) / scale, "frac_outside_rtol1e-4": frac}
         ok = ok and frac < 1e-3 and float(d.max()) / scale < 1e-2
+    # the same through this library's NVLink path (view-colour exchange + all-reduce kernel)
+    from qed_splatter_b200.comm import ViewShardedGradients
+
+    xg = ViewShardedGradients(s.N, 1, dev)
+    res["comm_path"] = xg.arena.path
+    for rep in range(2):  # twice: both exchange buffers, stale records of the previous step present
+        fs.step(s.means, s.quats, s.scales, s.opacities, s.sh, mine["viewmats"], mine["Ks"], s.width, s.height, 3, mine["gt_rgb"],
+                mine["gt_depth"], bg, grad_scale=1.0 / world, exchange=xg)
+    res["gradients_exchange"] = {}
+    for k, g in xg.views().items():
+        d = (g - ref[k]).abs()
+        scale = float(ref[k].abs().mean()) + 1e-20
+        frac = float((d > 1e-4 * ref[k].abs() + 1e-5 * scale).float().mean())
+        res["gradients_exchange"][k] = {"max_abs_diff_over_mean_abs": float(d.max()) / scale, "frac_outside_rtol1e-4": frac}
+        ok = ok and frac < 1e-3 and float(d.max()) / scale < 1e-2
+    chk = torch.stack([xg.grad.double().sum(), xg.grad.view(torch.int32).sum().double()])
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    res["exchange_arena_bit_identical_on_all_ranks"] = all(torch.equal(allc[0], c_) for c_ in allc)
+    ok = ok and res["exchange_arena_bit_identical_on_all_ranks"]
     identical, vs_single = True, None
     log_s, logit_o = torch.log(s.scales), torch.logit(s.opacities)
     tr = SplatTrainer(s.means.clone(), s.quats.clone(), log_s.clone(), logit_o.clone(), s.sh.clone(), cfg=TrainConfig(), rank=rank, world_size=world, backend="cuda")
@@ -367,6 +390,7 @@ def run_multi_gpu_check(torch, dist, dev, rank, world):
     vs_single = {"max_abs_param_diff": float(d.max()), "frac_above_1e-5": float((d > 1e-5).float().mean()),
                  "mean_abs_update": float(upd.mean()) if upd is not None else None}
     ok = ok and identical and vs_single["frac_above_1e-5"] < 1e-2
+    res["trainer_comm"] = tr.comm
     res.update({"replicas_bit_identical_after_3_steps": bool(identical), "vs_single_process_trainer": vs_single, "ok": bool(ok), "world": world})
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -431,7 +455,23 @@ def main_ours(args):
         # backward of the next range is still running (NCCL runs on its own stream)
         pending.append(dist.all_reduce(arena[sh_begin + 48 * n0: sh_begin + 48 * n1], async_op=True))
 
+    xg = None
+    if world > 1 and args.comm == "exchange":
+        from qed_splatter_b200.comm import ViewShardedGradients
+
+        xg = ViewShardedGradients(N, 1, dev)
+        del arena
+        arena, views = xg.grad, xg.views()
+
     def step():
+        if xg is not None:
+            # the step ends (in stream order) with the gradient arena summed over all ranks on every rank: per-view colour
+            # gradients exchanged by the projection backward, one all-reduce kernel, local rebuild of the SH gradient
+            out = fs.step(means, quats, scales, opac, sh, viewmats, Ks, width, height, 3, gt_rgb, gt_depth, bg, render_mode=args.mode,
+                          grad_scale=1.0 / world, exchange=xg)
+            _lib.check(lib.qed_strategy_update(1, N, _lib.ptr(out.packed_grads), 1, _lib.ptr(out.radii), width, height, world, _lib.ptr(stats[0]),
+                                               _lib.ptr(stats[1]), _lib.ptr(stats[2]), _lib.current_stream()), "qed_strategy_update")
+            return out
         out = fs.step(means, quats, scales, opac, sh, viewmats, Ks, width, height, 3, gt_rgb, gt_depth, bg, render_mode=args.mode,
                       grad_scale=1.0 / world, grad_out=views, n_chunks=n_chunks, on_chunk=on_chunk if world > 1 else None)
         _lib.check(lib.qed_strategy_update(1, N, _lib.ptr(out.packed_grads), 1, _lib.ptr(out.radii), width, height, world, _lib.ptr(stats[0]),
@@ -506,7 +546,14 @@ def main_ours(args):
 
     # ---- pair counters for the compositing roofline (instrumented launches, outside any timed region) ----
     counters = fs.count_pairs()
-    launches_per_step = fs.launches_per_step + ((n_chunks - 1) if world > 1 else 0)  # this library's kernels only (chunked: extra project_bwd launches)
+    launches_per_step = fs.launches_per_step + ((n_chunks - 1) if (world > 1 and xg is None) else 0)  # this library's kernels only (chunked: extra project_bwd launches)
+    if xg is not None:
+        launches_per_step += 2  # + the all-reduce kernel and the SH-gradient rebuild
+    comm_info = None
+    if world > 1:
+        comm_info = {"impl": "exchange" if xg is not None else "nccl", "path": xg.arena.path if xg is not None else "torch.distributed all_reduce",
+                     "bytes_all_reduced_per_rank": (xg.offsets["sh"][0] * 4) if xg is not None else PARAM_FLOATS * N * 4,
+                     "bytes_exchanged_per_rank": (n_visible * 16) if xg is not None else 0}
 
     # ---- second half of the metric: train iters/s (full qed-splatter step through trainer.SplatTrainer: render,
     # 0.8 L1 + 0.2 (1-SSIM) + 0.2 depth-L1, backward, gradient all-reduce pipelined with Adam, strategy statistics) ----
@@ -703,6 +750,7 @@ def main_ours(args):
             "e2e_fused_loss": e2e_fused_loss,
             "train": train,
             "multi_gpu_check": multi_gpu_check,
+            "comm": comm_info,
             "traffic_source": "profiles/r02_dram_bytes.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, per step and stage)" if traffic else None,
             "gpu_launches": launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,

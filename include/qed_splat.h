@@ -276,6 +276,52 @@ int qed_arena_gather(int64_t n_new, const int32_t* src, const uint8_t* fresh, co
                      float* new_param, float* new_exp_avg, float* new_exp_avg_sq, const int64_t* new_group_starts,
                      qed_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * multi-GPU: sum of the gradient arena over the ranks of the view-sharded step (the reference has
+ * no collective -- it renders one camera per step on one GPU, qed_splatter/model.py:211)
+ *
+ * The arena must live in SYMMETRIC memory: the same allocation on every rank, mapped into every peer process
+ * (`peer_bases[r]` = address of rank r's arena in THIS process) and, when the box has NVSwitch multicast, into one
+ * multicast address range (`multicast_base`, NULL = use the peer path).  `peer_flags[r]` = address of rank r's flag
+ * block (qed_comm_flag_words() uint32, zero-initialised once, symmetric as well).  peer_bases / peer_flags are HOST
+ * arrays of `world` device pointers.
+ *
+ * qed_comm_allreduce_f32: elements [begin, end) (multiples of 4) of every rank's arena are replaced by their sum over
+ *   the ranks, in ONE kernel on `stream`: rank r sums the r-th part of the range -- inside the switch
+ *   (multimem.ld_reduce) or from peer loads -- and broadcasts it (multimem.st / peer stores); epoch flags (release /
+ *   acquire, system scope) order it against the other ranks' kernels, so no host synchronisation and no NCCL call is
+ *   involved.  Every rank must call it with the same (begin, end, epoch) in the same order; `epoch` must grow by 2
+ *   from call to call (it uses epoch and epoch + 1), starting at 1.  All replicas receive identical bits.
+ *
+ * View-colour exchange (what makes the per-step traffic small).  81 % of the arena is the SH coefficient gradient
+ * [N,16,3], and d colour / d coeff[k,ch] = basis_k(direction): v_sh[n] = sum over views of basis(dir(n,view)) (x)
+ * v_colour(n,view) -- rank-1 per view.  So instead of all-reducing 192 B per Gaussian:
+ *   qed_project_bwd_exchange = qed_project_bwd (fused path: packed_grads in, v_means / v_quats / v_scales / v_opacities
+ *     out, SH colours) that does NOT build the coefficient gradient; it stores the gated colour gradient
+ *     {v_r, v_g, v_b, tag} of every VISIBLE (view, Gaussian) into slot (first_slot + c) * N + n of the exchange buffer of
+ *     EVERY rank (one multimem.st through the switch, or peer stores), and its views' camera positions {x, y, z, tag}
+ *     behind the slots (element total_slots * N + slot).  Exchange buffer = (total_slots * N + total_slots) float4,
+ *     symmetric, zero-initialised once; `tag` must differ from step to step (records of Gaussians not visible this
+ *     step stay stale and are recognised by their tag).  Callers alternate between two exchange buffers from step to
+ *     step, so that a rank one step ahead never overwrites records a slower rank is still reading.
+ *   qed_comm_allreduce_f32 over the 11 floats per Gaussian that are left (means, quats, scales, opacity), then
+ *   qed_sh_grad_from_view_colors: every rank rebuilds v_sh[N,K,3] from ITS copy of the exchange buffer -- all views, in
+ *     slot order, same bits everywhere -- after the all-reduce (whose entry barrier also orders the exchange).
+ * Per GPU and step 16 B x visible (view, Gaussian) pairs + 44 B x N x (1 + 1/G) cross NVLink instead of 236 B x N x (1 + 1/G).
+ */
+int qed_project_bwd_exchange(int C, int N, const float* means, const float* quats, const float* scales,
+                             const float* opacities, int activations, const float* sh_coeffs, int K, int sh_degree,
+                             const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                             int calc_compensations, int append_depth, const int32_t* radii, const float* conics,
+                             const float* compensations, const float* packed_grads, float* v_means, float* v_quats,
+                             float* v_scales, float* v_opacities, float* exchange_multicast, float* const* exchange_peers,
+                             int world, int first_slot, int total_slots, float tag, qed_stream_t stream);
+int qed_sh_grad_from_view_colors(int total_slots, int N, int K, int sh_degree, const float* means, const float* exchange_local,
+                                 float tag, float* v_sh, qed_stream_t stream);
+int qed_comm_flag_words(void);
+int qed_comm_allreduce_f32(float* multicast_base, float* const* peer_bases, uint32_t* const* peer_flags, int rank, int world,
+                           int64_t begin, int64_t end, uint32_t epoch, int blocks, qed_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

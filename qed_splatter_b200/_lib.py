@@ -49,6 +49,11 @@ SIGNATURES = {
     "qed_loss_fwd_bwd": (c_int, [c_int, c_int, c_int, P, P, P, c_int, P, P, c_int, P, c_float, c_float, c_float, c_float, P, P, P, P, P, c_size_t, P]),
     "qed_adam_arena": (c_int, [c_int64, P, P, P, P, c_int, P, P, P, P, P, c_double, c_double, c_double, c_int, P]),
     "qed_strategy_update": (c_int, [c_int, c_int, P, c_int, P, c_int, c_int, c_int, P, P, P, P]),
+    "qed_project_bwd_exchange": (c_int, [c_int, c_int, P, P, P, P, c_int, P, c_int, c_int, P, P, c_int, c_int, c_float, c_int, c_int, P, P, P, P,
+                                         P, P, P, P, P, P, c_int, c_int, c_int, c_float, P]),
+    "qed_sh_grad_from_view_colors": (c_int, [c_int, c_int, c_int, c_int, P, P, c_float, P, P]),
+    "qed_comm_flag_words": (c_int, []),
+    "qed_comm_allreduce_f32": (c_int, [P, P, P, c_int, c_int, c_int64, c_int64, ctypes.c_uint32, c_int, P]),
     "qed_arena_gather": (c_int, [c_int64, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
 }
 # test hooks, not part of the reference-facing surface

@@ -35,7 +35,22 @@ struct ProjBwdParams {
     const float *conics, *comps;
     const float *v_means2d, *v_depths, *v_conics, *v_colors, *v_opac_cn, *packed;
     float *v_means, *v_quats, *v_scales, *v_opacities, *v_colors_in;
+    // view-colour exchange (multi-GPU, see qed_project_bwd_exchange): instead of the 192-B SH coefficient gradient, the
+    // gated colour gradient of every VISIBLE (view, Gaussian) is stored as {v_r, v_g, v_b, tag} into slot
+    // (xch_slot0 + c) * N + n of the exchange buffer of every rank
+    float4* xch_mc;                // NVSwitch multicast address of the exchange buffer, or NULL
+    float4* xch_peer[16];          // else: its unicast address on every rank
+    int xch_world, xch_slot0, xch_total_slots;
+    float xch_tag;
 };
+
+__device__ __forceinline__ void xch_store(const ProjBwdParams& p, int64_t i, float4 v) {
+    if (p.xch_mc) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.xch_mc + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    } else {
+        for (int r = 0; r < p.xch_world; ++r) p.xch_peer[r][i] = v;
+    }
+}
 
 __device__ void load_camera_b(const float* __restrict__ V, const float* __restrict__ Kc, int width, int height, CamB& cam) {
     float a[3][3], t[3];
@@ -130,7 +145,9 @@ __device__ __forceinline__ void sh_bases_vjp(float x, float y, float z, const fl
 }
 
 // DEG=-1: colours pass through.  VEC: coefficient rows 16-byte aligned and K*3 % 4 == 0.
-template <int DEG, bool VEC>
+// XCH (multi-GPU view-colour exchange, VEC only): no coefficient gradient is built or written (half the shared memory, 192 B
+// per Gaussian less HBM traffic); the gated colour gradient goes to every rank's exchange buffer instead.
+template <int DEG, bool VEC, bool XCH = false>
 __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const ProjBwdParams p) {
     extern __shared__ float4 smem4[];
     CamB* cams = reinterpret_cast<CamB*>(smem4);
@@ -213,8 +230,10 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
             }
             cp_async_commit();
         }
+        if (!XCH) {
 #pragma unroll
-        for (int j = 0; j < Sh::kVec; ++j) my_vcoef[j] = make_float4(0, 0, 0, 0);
+            for (int j = 0; j < Sh::kVec; ++j) my_vcoef[j] = make_float4(0, 0, 0, 0);
+        }
         if (VEC) {
             cp_async_wait<0>();
             __syncwarp();
@@ -401,7 +420,21 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
                     float vpre[3];
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) vpre[ch] = (pre[ch] + 0.5f >= 0.0f) ? g_col[ch] : 0.0f;
-                    if (VEC) {
+                    if (VEC && XCH) {
+                        // the coefficient gradient b (x) vpre is rebuilt on every rank from the exchanged colour gradients
+                        // (qed_sh_grad_from_view_colors); only the direction term needs the coefficients here
+#pragma unroll
+                        for (int j = 0; j < Sh::kVec; ++j) {
+                            float4 cf = my_coef[j];
+                            float cfa[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int f = 4 * j + i;
+                                if (f < Sh::kFloats) vb[f / 3] += cfa[i] * vpre[f % 3];
+                            }
+                        }
+                        xch_store(p, (int64_t)(p.xch_slot0 + c) * p.N + n, make_float4(vpre[0], vpre[1], vpre[2], p.xch_tag));
+                    } else if (VEC) {
 #pragma unroll
                         for (int j = 0; j < Sh::kVec; ++j) {
                             float4 cf = my_coef[j];
@@ -481,8 +514,14 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         if (p.v_opacities) p.v_opacities[n] = vopac;
     }
 
+    // ---- camera positions of this rank's views, for the ranks that rebuild the coefficient gradient ----
+    if (XCH && blockIdx.x == 0 && threadIdx.x < p.C) {
+        const CamB& cam = cams[threadIdx.x];
+        xch_store(p, (int64_t)p.xch_total_slots * p.N + p.xch_slot0 + threadIdx.x, make_float4(cam.campos[0], cam.campos[1], cam.campos[2], p.xch_tag));
+    }
+
     // ---- stream the coefficient gradient out (all K rows; unused ones are zero) ----
-    if (use_sh && VEC) {
+    if (use_sh && VEC && !XCH) {
         __syncwarp();
         const int64_t row0 = (int64_t)blockIdx.x * kProjBwdThreads + warp * 32;
         const int row_vec = row_floats / 4;
@@ -497,15 +536,91 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
     }
 }
 
-template <int DEG, bool VEC>
+template <int DEG, bool VEC, bool XCH = false>
 static int launch_project_bwd(const ProjBwdParams& p, cudaStream_t stream) {
     using Sh = ShShapeB<(DEG < 0 ? 0 : DEG)>;
     size_t smem = (size_t)p.C * kCamFloatsB * 4;
-    if (DEG >= 0 && p.n_color > 0) smem += (size_t)2 * kProjBwdThreads * Sh::kStrideVec * 16;
-    auto kern = project_bwd_kernel<DEG, VEC>;
+    if (DEG >= 0 && p.n_color > 0) smem += (size_t)(XCH ? 1 : 2) * kProjBwdThreads * Sh::kStrideVec * 16;
+    auto kern = project_bwd_kernel<DEG, VEC, XCH>;
     if (smem > 48 * 1024) QED_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (p.N + kProjBwdThreads - 1) / kProjBwdThreads;
     kern<<<blocks, kProjBwdThreads, smem, stream>>>(p);
+    QED_LAUNCH_CHECK();
+    return QED_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SH coefficient gradient rebuilt from exchanged per-view colour gradients (multi-GPU, see qed_project_bwd_exchange).
+// d colour / d coeff[k, ch] = basis_k(direction) for every view, so   v_sh[n] = sum_views  basis(dir(n, view)) (x) v_colour(n, view):
+// rank-1 per view.  Every rank evaluates the sum over ALL views of the batch, in view order, from the same bits --
+// replicas stay bit-identical -- and 16 B per visible (view, Gaussian) cross NVLink instead of a 192-B row per Gaussian
+// through an all-reduce.  One thread per Gaussian, 48 accumulators in registers, rows streamed out through shared
+// memory with coalesced 16-byte stores (the pattern of project_bwd_kernel).
+// ------------------------------------------------------------------------------------------------
+constexpr int kShGradThreads = 128;
+
+template <int DEG>
+__global__ void __launch_bounds__(kShGradThreads) sh_grad_from_view_colors_kernel(int V, int N, int K, const float* __restrict__ means,
+                                                                                 const float4* __restrict__ xch, float tag,
+                                                                                 float* __restrict__ v_sh) {
+    using Sh = ShShapeB<DEG>;
+    extern __shared__ float4 smem4[];
+    float4* rows = smem4;  // [kShGradThreads][kStrideVec]
+    const int n = blockIdx.x * kShGradThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4* campos = xch + (int64_t)V * N;
+    float acc[Sh::kBases][3];
+#pragma unroll
+    for (int k = 0; k < Sh::kBases; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.0f;
+    if (n < N) {
+        const float m0 = means[n * 3 + 0], m1 = means[n * 3 + 1], m2 = means[n * 3 + 2];
+        for (int v0 = 0; v0 < V; v0 += 4) {  // four views' records in flight per thread
+            float4 vc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) vc[u] = (v0 + u < V) ? xch[(int64_t)(v0 + u) * N + n] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v0 + u >= V || vc[u].w != tag) continue;  // not visible in that view this step (stale record)
+                const float4 cp = campos[v0 + u];
+                const float dx = m0 - cp.x, dy = m1 - cp.y, dz = m2 - cp.z;
+                const float dn = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+                float b[16];
+                sh_bases_b<DEG>(dx / dn, dy / dn, dz / dn, b);
+#pragma unroll
+                for (int k = 0; k < Sh::kBases; ++k) {
+                    acc[k][0] = fmaf(b[k], vc[u].x, acc[k][0]);
+                    acc[k][1] = fmaf(b[k], vc[u].y, acc[k][1]);
+                    acc[k][2] = fmaf(b[k], vc[u].z, acc[k][2]);
+                }
+            }
+        }
+    }
+    float* my = reinterpret_cast<float*>(rows + (warp * 32 + lane) * Sh::kStrideVec);
+#pragma unroll
+    for (int k = 0; k < Sh::kBases; ++k) {
+        my[k * 3 + 0] = acc[k][0];
+        my[k * 3 + 1] = acc[k][1];
+        my[k * 3 + 2] = acc[k][2];
+    }
+#pragma unroll
+    for (int f = Sh::kFloats; f < Sh::kVec * 4; ++f) my[f] = 0.0f;
+    __syncwarp();
+    const int64_t row0 = (int64_t)blockIdx.x * kShGradThreads + warp * 32;
+    const int row_vec = K * 3 / 4;
+    float4* dst = reinterpret_cast<float4*>(v_sh) + row0 * row_vec;
+    const float4* wbuf = rows + warp * 32 * Sh::kStrideVec;
+    const int nrows = (N - row0) < 32 ? (int)(N - row0) : 32;
+    for (int q = lane; q < nrows * row_vec; q += 32) {
+        const int r = q / row_vec, j = q - r * row_vec;
+        dst[q] = (j < Sh::kVec) ? wbuf[r * Sh::kStrideVec + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <int DEG>
+static int launch_sh_grad(int V, int N, int K, const float* means, const float4* xch, float tag, float* v_sh, cudaStream_t stream) {
+    using Sh = ShShapeB<DEG>;
+    const size_t smem = (size_t)kShGradThreads * Sh::kStrideVec * 16;
+    sh_grad_from_view_colors_kernel<DEG><<<(N + kShGradThreads - 1) / kShGradThreads, kShGradThreads, smem, stream>>>(V, N, K, means, xch, tag, v_sh);
     QED_LAUNCH_CHECK();
     return QED_OK;
 }
@@ -514,16 +629,15 @@ static int launch_project_bwd(const ProjBwdParams& p, cudaStream_t stream) {
 
 using namespace qed;
 
-extern "C" int qed_project_bwd(int C, int N, const float* means, const float* quats, const float* scales,
-                               const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
-                               int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
-                               float eps2d, int calc_compensations, int n_color, int append_depth,
-                               const int32_t* radii, const float* conics, const float* compensations,
-                               const float* v_means2d, const float* v_depths, const float* v_conics,
-                               const float* v_colors, const float* v_opacities_cn, const float* packed_grads,
-                               float* v_means, float* v_quats, float* v_scales, float* v_opacities,
-                               float* v_colors_in, qed_stream_t stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+static int project_bwd_impl(int C, int N, const float* means, const float* quats, const float* scales,
+                            const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
+                            int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
+                            float eps2d, int calc_compensations, int n_color, int append_depth,
+                            const int32_t* radii, const float* conics, const float* compensations,
+                            const float* v_means2d, const float* v_depths, const float* v_conics,
+                            const float* v_colors, const float* v_opacities_cn, const float* packed_grads,
+                            float* v_means, float* v_quats, float* v_scales, float* v_opacities,
+                            float* v_colors_in, const ProjBwdParams* xch, cudaStream_t stream) {
     if (C < 0 || N < 0) return QED_ERR_BAD_ARG;
     if (!(n_color == 0 || n_color == 3) || !(append_depth == 0 || append_depth == 1)) return QED_ERR_BAD_ARG;
     if (C == 0 || N == 0) return QED_OK;
@@ -531,11 +645,12 @@ extern "C" int qed_project_bwd(int C, int N, const float* means, const float* qu
     if (!means || !quats || !scales || !viewmats || !Ks || !radii || !conics || !v_means || !v_quats || !v_scales)
         return QED_ERR_BAD_ARG;
     if (calc_compensations && (!compensations || !opacities)) return QED_ERR_BAD_ARG;
-    if (n_color > 0 && (!colors_in || !v_colors_in)) return QED_ERR_BAD_ARG;
+    if (n_color > 0 && (!colors_in || (!v_colors_in && !xch))) return QED_ERR_BAD_ARG;
     if (n_color == 0) sh_degree = -1;
     if (sh_degree > 3) return QED_ERR_UNSUPPORTED;
 
-    ProjBwdParams p;
+    ProjBwdParams p{};
+    if (xch) p = *xch;
     p.C = C;
     p.N = N;
     p.K = K;
@@ -571,7 +686,16 @@ extern "C" int qed_project_bwd(int C, int N, const float* means, const float* qu
     p.v_colors_in = v_colors_in;
 
     const bool vec_ok = sh_degree >= 0 && ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors_in) & 15) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(v_colors_in) & 15) == 0);
+                        (xch || (reinterpret_cast<uintptr_t>(v_colors_in) & 15) == 0);
+    if (xch) {
+        if (!vec_ok || n_color != 3) return QED_ERR_UNSUPPORTED;  // the exchange carries SH colour gradients
+        switch (sh_degree) {
+            case 0: return launch_project_bwd<0, true, true>(p, stream);
+            case 1: return launch_project_bwd<1, true, true>(p, stream);
+            case 2: return launch_project_bwd<2, true, true>(p, stream);
+            default: return launch_project_bwd<3, true, true>(p, stream);
+        }
+    }
     if (n_color > 0 && (sh_degree < 0 || !vec_ok)) {
         // fallback paths accumulate straight into v_colors_in: clear it first
         size_t bytes = sh_degree < 0 ? (size_t)(colors_per_camera ? (size_t)C * N : (size_t)N) * 3 * 4 : (size_t)N * K * 3 * 4;
@@ -583,5 +707,61 @@ extern "C" int qed_project_bwd(int C, int N, const float* means, const float* qu
         case 2: return vec_ok ? launch_project_bwd<2, true>(p, stream) : launch_project_bwd<2, false>(p, stream);
         case 3: return vec_ok ? launch_project_bwd<3, true>(p, stream) : launch_project_bwd<3, false>(p, stream);
         default: return launch_project_bwd<-1, false>(p, stream);
+    }
+}
+
+extern "C" int qed_project_bwd(int C, int N, const float* means, const float* quats, const float* scales,
+                               const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
+                               int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
+                               float eps2d, int calc_compensations, int n_color, int append_depth,
+                               const int32_t* radii, const float* conics, const float* compensations,
+                               const float* v_means2d, const float* v_depths, const float* v_conics,
+                               const float* v_colors, const float* v_opacities_cn, const float* packed_grads,
+                               float* v_means, float* v_quats, float* v_scales, float* v_opacities,
+                               float* v_colors_in, qed_stream_t stream_) {
+    return project_bwd_impl(C, N, means, quats, scales, opacities, activations, colors_in, K, sh_degree, colors_per_camera, viewmats, Ks, width,
+                            height, eps2d, calc_compensations, n_color, append_depth, radii, conics, compensations, v_means2d, v_depths, v_conics,
+                            v_colors, v_opacities_cn, packed_grads, v_means, v_quats, v_scales, v_opacities, v_colors_in, nullptr,
+                            (cudaStream_t)stream_);
+}
+
+extern "C" int qed_project_bwd_exchange(int C, int N, const float* means, const float* quats, const float* scales,
+                                        const float* opacities, int activations, const float* sh_coeffs, int K, int sh_degree,
+                                        const float* viewmats, const float* Ks, int width, int height, float eps2d,
+                                        int calc_compensations, int append_depth, const int32_t* radii, const float* conics,
+                                        const float* compensations, const float* packed_grads, float* v_means, float* v_quats,
+                                        float* v_scales, float* v_opacities, float* exchange_multicast, float* const* exchange_peers,
+                                        int world, int first_slot, int total_slots, float tag, qed_stream_t stream_) {
+    if (world < 1 || world > 16 || first_slot < 0 || C < 0 || first_slot + C > total_slots) return QED_ERR_BAD_ARG;
+    if (!exchange_multicast && !exchange_peers) return QED_ERR_BAD_ARG;
+    if (!packed_grads || sh_degree < 0) return QED_ERR_BAD_ARG;
+    ProjBwdParams x{};
+    x.xch_mc = reinterpret_cast<float4*>(exchange_multicast);
+    for (int r = 0; r < world; ++r) {
+        x.xch_peer[r] = exchange_peers ? reinterpret_cast<float4*>(exchange_peers[r]) : nullptr;
+        if (!x.xch_mc && !x.xch_peer[r]) return QED_ERR_BAD_ARG;
+    }
+    x.xch_world = world;
+    x.xch_slot0 = first_slot;
+    x.xch_total_slots = total_slots;
+    x.xch_tag = tag;
+    return project_bwd_impl(C, N, means, quats, scales, opacities, activations, sh_coeffs, K, sh_degree, 0, viewmats, Ks, width, height, eps2d,
+                            calc_compensations, 3, append_depth, radii, conics, compensations, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            packed_grads, v_means, v_quats, v_scales, v_opacities, nullptr, &x, (cudaStream_t)stream_);
+}
+
+extern "C" int qed_sh_grad_from_view_colors(int total_slots, int N, int K, int sh_degree, const float* means, const float* exchange_local,
+                                            float tag, float* v_sh, qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (total_slots < 0 || N < 0 || K <= 0 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > K) return QED_ERR_BAD_ARG;
+    if (N == 0) return QED_OK;
+    if (!means || !exchange_local || !v_sh) return QED_ERR_BAD_ARG;
+    if ((K * 3) % 4 || (reinterpret_cast<uintptr_t>(v_sh) & 15) || (reinterpret_cast<uintptr_t>(exchange_local) & 15)) return QED_ERR_BAD_ARG;
+    const float4* x = reinterpret_cast<const float4*>(exchange_local);
+    switch (sh_degree) {
+        case 0: return launch_sh_grad<0>(total_slots, N, K, means, x, tag, v_sh, stream);
+        case 1: return launch_sh_grad<1>(total_slots, N, K, means, x, tag, v_sh, stream);
+        case 2: return launch_sh_grad<2>(total_slots, N, K, means, x, tag, v_sh, stream);
+        default: return launch_sh_grad<3>(total_slots, N, K, means, x, tag, v_sh, stream);
     }
 }

@@ -187,13 +187,18 @@ class FusedSplatStep:
     # -- backward from explicit output gradients ------------------------------------------------
     @torch.no_grad()
     def backward(self, v_render: Tensor, v_alphas: Optional[Tensor], grad_out: Optional[Dict[str, Tensor]] = None,
-                 n_chunks: int = 1, on_chunk=None):
+                 n_chunks: int = 1, on_chunk=None, exchange=None):
         """`grad_out`: optional preallocated {means,quats,scales,opacities,sh} (e.g. views into a flat
         all-reduce arena) that the projection backward writes straight into.
 
         `n_chunks` > 1 (single-camera calls only) launches the projection backward over `n_chunks` Gaussian
         ranges and calls `on_chunk(k, n0, n1)` after each launch, so a caller can start the all-reduce of a
-        finished range while the next one is still being computed (view-sharded training)."""
+        finished range while the next one is still being computed (view-sharded training).
+
+        `exchange` (comm.ViewShardedGradients, world_size > 1): the gradients are SUMMED OVER ALL RANKS' views before this
+        returns (in stream order): the projection backward stores its per-view colour gradients into every rank's exchange
+        buffer, one all-reduce kernel sums the 11 non-SH floats per Gaussian and every rank rebuilds the SH coefficient
+        gradient locally.  Returns views into the exchange's arena."""
         lib, stream, f = self.lib, current_stream(), self._fwd
         C, N, D, M = f["C"], f["N"], f["D"], f["M"]
         means, quats, scales, opacities, sh, viewmats, Ks = f["inputs"]
@@ -207,6 +212,15 @@ class FusedSplatStep:
                                      f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"], ptr(f["render"]),
                                      ptr(f["alphas"]), ptr(f["last_ids"]), ptr(v_render), ptr(v_alphas), ptr(packed), stream), "qed_raster_bwd")
         self._mark("raster_bwd")
+        if exchange is not None:
+            if not f["n_color"] or f["deg"] < 0:
+                raise ValueError("the view-colour exchange needs SH colours (render_mode RGB / RGB+D / RGB+ED with sh_degree)")
+            exchange.project_bwd(lib, C, means, quats, scales, opacities, f["activations"], sh, f["K"], f["deg"], viewmats, Ks, f["width"], f["height"],
+                                 f["eps2d"], f["comp"], f["append"], f["radii"], f["conics"], f["comps"], packed, stream)
+            self._mark("project_bwd")
+            exchange.finish(lib, means, f["K"], f["deg"], stream)
+            self._mark("grad_exchange")
+            return exchange.views(), packed
         if grad_out is not None:
             v_means, v_quats, v_scales, v_opac = grad_out["means"], grad_out["quats"], grad_out["scales"], grad_out["opacities"]
             v_sh = grad_out["sh"] if f["n_color"] else None
@@ -246,7 +260,7 @@ class FusedSplatStep:
              gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, render_mode: str = "RGB+ED", rgb_weight: float = 0.8,
              depth_lambda: float = 0.2, grad_scale: float = 1.0, rasterize_mode: str = "classic",
              grad_out: Optional[Dict[str, Tensor]] = None, ssim_lambda: float = 0.0, n_chunks: int = 1, on_chunk=None,
-             activations: int = 0, mask: Optional[Tensor] = None) -> StepOutput:
+             activations: int = 0, mask: Optional[Tensor] = None, exchange=None) -> StepOutput:
         """`render_mode` RGB+ED (north_star) or RGB+D (what qed_splatter/model.py:257 passes).
         loss = rgb_weight * L1 + ssim_lambda * (1 - SSIM) + depth_lambda * masked depth-L1 (splatfacto: 0.8 / 0.2 / 0.2).
         `mask` [C,H,W(,1)] float32 / uint8 / bool = `batch["mask"]` (model.py:93-97), see losses.depth_supervised_loss.
@@ -284,7 +298,7 @@ class FusedSplatStep:
                                    depth_lambda, ssim_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas),
                                    ptr(lws), lws_bytes, stream), "qed_loss_fwd_bwd")
         self._mark("loss")
-        grads, packed = self.backward(v_render, v_alphas, grad_out, n_chunks=n_chunks, on_chunk=on_chunk)
+        grads, packed = self.backward(v_render, v_alphas, grad_out, n_chunks=n_chunks, on_chunk=on_chunk, exchange=exchange)
         self._last_v = (v_render, v_alphas)
         return StepOutput(loss=self._loss, grads=grads, packed_grads=packed, radii=self._fwd["radii"], render=render, alphas=alphas,
                           n_isects=self._fwd["M"])

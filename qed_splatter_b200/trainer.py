@@ -73,8 +73,15 @@ class TrainConfig:
     use_absgrad: bool = True
     scene_scale: float = 1.0
     seed: int = 42
-    comm_chunks: int = 4  # world_size > 1: Gaussian ranges whose SH gradients are all-reduced / Adam-stepped in a pipeline
-    chunk_project_bwd: bool = True  # also split the projection backward so the first reductions start earlier
+    # world_size > 1, how the gradients are summed over the ranks:
+    #   "exchange": this library's NVLink path (comm.ViewShardedGradients: per-view colour gradients stored into every rank's
+    #               exchange buffer by the projection backward, one all-reduce kernel over the 11 non-SH floats per Gaussian,
+    #               SH coefficient gradient rebuilt locally) -- no NCCL on the data path;  CUDA backend + NCCL group only
+    #   "nccl"    : torch.distributed all-reduce of the arena, pipelined over `comm_chunks` Gaussian ranges (also gloo / CPU)
+    #   "auto"    : "exchange" when available, else "nccl"
+    comm: str = "auto"
+    comm_chunks: int = 4  # "nccl": Gaussian ranges whose SH gradients are all-reduced / Adam-stepped in a pipeline
+    chunk_project_bwd: bool = True  # "nccl": also split the projection backward so the first reductions start earlier
 
     def lr_means_at(self, step: int) -> float:
         """nerfstudio ExponentialDecayScheduler (no warmup): log-linear from lr to lr_final over max_steps."""
@@ -395,6 +402,34 @@ class SplatTrainer:
 
             self._fused = FusedSplatStep(self.device)
         self._lr_dev = None
+        self._xg = None  # comm.ViewShardedGradients for the current (N, views per rank), built lazily
+        self.comm = self._pick_comm()
+
+    def _pick_comm(self) -> str:
+        c = self.cfg.comm
+        if self.world <= 1:
+            return "none"
+        ok = self.backend == "cuda" and self.device.type == "cuda"
+        if ok:
+            import torch.distributed as dist
+
+            ok = dist.is_initialized() and dist.get_backend(self.pg) == "nccl"
+        if c == "exchange" and not ok:
+            raise RuntimeError("comm='exchange' needs the CUDA backend and an NCCL process group (symmetric memory)")
+        return "exchange" if (c in ("auto", "exchange") and ok) else "nccl"
+
+    def _exchange_for(self, views_per_rank: int):
+        """The symmetric gradient arena + exchange buffers for the current Gaussian count (rebuilt, collectively, when a
+        refine step changed N: every rank refines at the same step)."""
+        from .comm import ViewShardedGradients
+
+        x = self._xg
+        if x is None or x.N != self.arena.N or x.views_per_rank != views_per_rank:
+            self._xg = x = ViewShardedGradients(self.arena.N, views_per_rank, self.device, self.pg)
+        if self.arena.grad.data_ptr() != x.grad.data_ptr():
+            assert x.grad.numel() == self.arena.grad.numel()
+            self.arena.grad = x.grad  # Adam reads the summed gradients straight from the symmetric arena
+        return x
 
     # -- collectives --------------------------------------------------------------------------
     def _all_reduce(self, t: Tensor, op: str = "sum") -> None:
@@ -510,6 +545,18 @@ class SplatTrainer:
         gv = a.views(a.grad)
         # the stored parameters go straight in: exp / sigmoid (model.py:269-271) and their chain rule run inside the
         # projection kernels, the gradients land in the arena
+        if self.comm == "exchange":
+            xg = self._exchange_for(C)
+            out = self._fused.step(pv["means"], pv["quats"], pv["scales"], pv["opacities"], pv["sh"], viewmats, Ks, width, height,
+                                   self.sh_degree_to_use(), gt_rgb, gt_depth, background, render_mode=c.render_mode, rgb_weight=1.0 - c.ssim_lambda,
+                                   depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, activations=3,
+                                   mask=mask, ssim_lambda=c.ssim_lambda, exchange=xg)
+            self.accumulate_stats(out.packed_grads, out.radii, width, height, packed=True, n_cameras=total)
+            self.optimizer_step()
+            loss = out.loss.clone()
+            info = self.maybe_refine(self.step_count)
+            self.step_count += 1
+            return loss, info
         pipelined = self.world > 1 and C == 1 and c.comm_chunks > 1
         sh0 = a.offsets["sh"][0]
         works = []
