@@ -60,7 +60,8 @@ def main():
 
     for force_peer in (False, True):
         arena = SymmetricArena(n, dev, force_peer_path=force_peer)
-        key = arena.path
+        arena.reduce_in_switch = bool(arena.multicast_ptr)  # this benchmark times both paths at every world size
+        key = "nvls-multimem" if arena.reduce_in_switch else "peer-load-store"
         if force_peer is False and not arena.multicast_ptr:
             res["nvls"] = "no multicast support on this box"
             continue

@@ -319,6 +319,9 @@ int qed_project_bwd_exchange(int C, int N, const float* means, const float* quat
 int qed_sh_grad_from_view_colors(int total_slots, int N, int K, int sh_degree, const float* means, const float* exchange_local,
                                  float tag, float* v_sh, qed_stream_t stream);
 int qed_comm_flag_words(void);
+/* All ranks' work enqueued before this call on their streams is complete and visible to every rank afterwards (one tiny
+ * kernel, epoch flags as above; uses `epoch` only -- the caller's epoch counter grows by 1). */
+int qed_comm_barrier(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch, qed_stream_t stream);
 int qed_comm_allreduce_f32(float* multicast_base, float* const* peer_bases, uint32_t* const* peer_flags, int rank, int world,
                            int64_t begin, int64_t end, uint32_t epoch, int blocks, qed_stream_t stream);
 

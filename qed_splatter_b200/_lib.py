@@ -53,6 +53,7 @@ SIGNATURES = {
                                          P, P, P, P, P, P, c_int, c_int, c_int, c_float, P]),
     "qed_sh_grad_from_view_colors": (c_int, [c_int, c_int, c_int, c_int, P, P, c_float, P, P]),
     "qed_comm_flag_words": (c_int, []),
+    "qed_comm_barrier": (c_int, [P, c_int, c_int, ctypes.c_uint32, P]),
     "qed_comm_allreduce_f32": (c_int, [P, P, P, c_int, c_int, c_int64, c_int64, ctypes.c_uint32, c_int, P]),
     "qed_arena_gather": (c_int, [c_int64, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
 }

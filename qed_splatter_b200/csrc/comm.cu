@@ -14,8 +14,9 @@
 //     Either way one rank computes each sum and everyone receives those bits: replicas stay bit-identical.
 //   cross-GPU ordering: epoch flags in symmetric memory (release / acquire at system scope), no host involvement, no reset:
 //     every call uses two fresh epochs (entry: all ranks' gradients are written; exit: all slices are broadcast).
-//   `row_ranges` variant: only [begin, end) element ranges are reduced -- the chunked / pipelined reductions of the
-//     trainer (SH rows of a finished Gaussian range while the projection backward of the next range runs).
+//   Any [begin, end) element range can be reduced: the step only all-reduces the 11 non-SH floats per Gaussian; the SH
+//   coefficient gradient (81 % of the arena) is rebuilt on every rank from exchanged per-view colour gradients
+//   (project_bwd.cu: qed_project_bwd_exchange / qed_sh_grad_from_view_colors).
 #include "common.cuh"
 
 namespace qed {
@@ -108,11 +109,28 @@ __global__ void __launch_bounds__(kCommThreads) comm_allreduce_kernel(float* __r
     barrier_all_ranks(peers, rank, world, epoch + 1);  // every slice has been broadcast
 }
 
+// every rank's earlier work on its stream (e.g. the exchange stores of the projection backward) is complete and visible
+__global__ void comm_barrier_kernel(CommPeers peers, int rank, int world, uint32_t epoch) { barrier_all_ranks(peers, rank, world, epoch); }
+
 }  // namespace qed
 
 using namespace qed;
 
 extern "C" int qed_comm_flag_words(void) { return kCommMaxBlocks * kCommMaxWorld; }
+
+extern "C" int qed_comm_barrier(uint32_t* const* peer_flags, int rank, int world, uint32_t epoch, qed_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (world < 1 || world > kCommMaxWorld || rank < 0 || rank >= world || !peer_flags) return QED_ERR_BAD_ARG;
+    if (world == 1) return QED_OK;
+    CommPeers peers{};
+    for (int r = 0; r < world; ++r) {
+        peers.flags[r] = peer_flags[r];
+        if (!peers.flags[r]) return QED_ERR_BAD_ARG;
+    }
+    comm_barrier_kernel<<<1, 32, 0, stream>>>(peers, rank, world, epoch);
+    QED_LAUNCH_CHECK();
+    return QED_OK;
+}
 
 extern "C" int qed_comm_allreduce_f32(float* multicast_base, float* const* peer_bases, uint32_t* const* peer_flags, int rank, int world,
                                       int64_t begin, int64_t end, uint32_t epoch, int blocks, qed_stream_t stream_) {
@@ -121,7 +139,7 @@ extern "C" int qed_comm_allreduce_f32(float* multicast_base, float* const* peer_
     if ((begin & 3) || (end & 3)) return QED_ERR_BAD_ARG;  // float4 units: the arena groups are 16-byte aligned
     if (!peer_flags || (!multicast_base && !peer_bases)) return QED_ERR_BAD_ARG;
     if (world == 1 || begin == end) return QED_OK;
-    if (blocks <= 0) blocks = 64;
+    if (blocks <= 0) blocks = 32;  // NVLS saturates with few SMs (8 B200: 16 blocks 0.54 ms, 256 blocks 0.59 ms for 236 MB)
     if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
     CommPeers peers{};
     for (int r = 0; r < world; ++r) {
