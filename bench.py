@@ -760,8 +760,8 @@ def main_ours(args):
             "pair_counters": counters,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = run_cpu_baseline(args, steps=2, warmup=1)  # the same sample and code as `--impl reference`
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_seconds_spent")}
+            cb = run_cpu_baseline(args, steps=8, warmup=1)  # ~15 s of CPU work; the same sample and code as `--impl reference`
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_seconds_spent", "steps")}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))

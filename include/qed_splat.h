@@ -158,7 +158,15 @@ int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* k
  *   dropped if it cannot touch a pixel centre of the tile (about half of them; no pixel changes).  The number of
  *   survivors stays on the device: it is written to n_exact_dev[1] (int64), flatten_ids / isect_ids are filled for
  *   that many entries (buffers sized for n_isects), and isect_offsets must have C*tile_height*tile_width + 1
- *   elements, the last one receiving the end of the last range (pass offsets_has_end = 1 to qed_raster_fwd). */
+ *   elements, the last one receiving the end of the last range (pass offsets_has_end = 1 to qed_raster_fwd).
+ *
+ * counts_dev != NULL (= the counts_dev of qed_isect_prepare): NO host synchronisation is needed between prepare and fill.
+ *   n_visible / n_isects are then CAPACITIES (n_visible = C*N is always enough; n_isects = what the caller sized
+ *   flatten_ids / isect_ids / the workspace for); the real counts are read on the device.  isect_offsets must have
+ *   C*tile_height*tile_width + 1 elements (its last element receives the end of the last range, pass offsets_has_end = 1
+ *   to qed_raster_fwd) also for gsplat's lists.  If the real entry count exceeds the capacity an EMPTY list is built
+ *   (every consumer stays memory-safe) -- the caller reads counts_host_pinned once the work is queued, sees the
+ *   overflow, grows its buffers and repeats the fill (pipeline.FusedSplatStep does; the device never idles on that read). */
 size_t qed_isect_prepare_workspace_bytes(int64_t CN);
 int qed_isect_prepare(int C, int N, const float* depths, const int32_t* tiles_per_gauss, void* workspace,
                       size_t workspace_bytes, int64_t* counts_dev, int64_t* counts_host_pinned, qed_stream_t stream);
@@ -166,8 +174,8 @@ size_t qed_isect_fill_workspace_bytes(int64_t n_isects);
 int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects, const float* means2d, const int32_t* radii,
                    const float* depths, const float* geom, int image_width, int image_height, int tile_size, int tile_width,
                    int tile_height, const void* prepare_workspace, void* workspace, size_t workspace_bytes,
-                   int64_t* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets, int64_t* n_exact_dev,
-                   qed_stream_t stream);
+                   const int64_t* counts_dev, int64_t* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets,
+                   int64_t* n_exact_dev, qed_stream_t stream);
 
 /* isect_offsets[C*tile_height*tile_width] i32: first sorted index of each (camera,tile); empty tiles get
  * the start of the next non-empty one; tiles after the last entry get n_isects. */

@@ -38,7 +38,7 @@ SIGNATURES = {
     "qed_isect_prepare_workspace_bytes": (c_size_t, [c_int64]),
     "qed_isect_prepare": (c_int, [c_int, c_int, P, P, P, c_size_t, P, P, P]),
     "qed_isect_fill_workspace_bytes": (c_size_t, [c_int64]),
-    "qed_isect_fill": (c_int, [c_int, c_int, c_int64, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P, P, P, P, P]),
+    "qed_isect_fill": (c_int, [c_int, c_int, c_int64, c_int64, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_size_t, P, P, P, P, P, P]),
     "qed_tile_ranges": (c_int, [c_int64, P, c_int, c_int, c_int, P, P]),
     "qed_raster_fwd": (c_int, [c_int, c_int, c_int64, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P,
                                c_int, P, P, P, P]),

@@ -263,8 +263,24 @@ constexpr int kEmitThreads = 256;
 constexpr int kEmitTile = 1024;
 
 // first_j[b] = index (in depth order) of the Gaussian that owns output entry b * kEmitTile
-__global__ void emit_boundaries_kernel(int64_t n_vis, const int64_t* __restrict__ cum2, int32_t* __restrict__ first_j) {
+// counts_dev != NULL (sizes only known on the device: no host sync before this launch): n_vis / n_isects are the
+// CAPACITIES the buffers were sized for; the real counts are read here and published, clamped, in `clamped[2]` for the
+// kernels that follow.  If the real entry count exceeds the capacity, an EMPTY list is built (clamped[1] = 0: every
+// later kernel is then trivially memory-safe) and the caller, who reads the counts after the fact, redoes the step with
+// larger buffers.
+__global__ void emit_boundaries_kernel(int64_t n_vis, int64_t n_isects, const int64_t* __restrict__ counts_dev, int64_t* __restrict__ clamped,
+                                       const int64_t* __restrict__ cum2, int32_t* __restrict__ first_j) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (counts_dev) {
+        const int64_t real_vis = counts_dev[0], real_isects = counts_dev[1];
+        n_vis = real_vis < n_vis ? real_vis : n_vis;
+        n_isects = real_isects <= n_isects ? real_isects : 0;
+        if (n_isects == 0) n_vis = 0;
+        if (j == 0) {
+            clamped[0] = n_vis;
+            clamped[1] = n_isects;
+        }
+    }
     if (j >= n_vis) return;
     const int64_t start = j > 0 ? cum2[j - 1] : 0, end = cum2[j];
     for (int64_t b = (start + kEmitTile - 1) / kEmitTile; b * kEmitTile < end; ++b) first_j[b] = (int32_t)j;
@@ -286,7 +302,8 @@ struct ExactEmit {
 };
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis, int64_t n_isects, int N, const int32_t* __restrict__ sorted_vals,
+__global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis, int64_t n_isects, const int64_t* __restrict__ clamped, int N,
+                                                                  const int32_t* __restrict__ sorted_vals,
                                                                   const int64_t* __restrict__ cum2, const int32_t* __restrict__ first_j,
                                                                   const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
                                                                   float tile_size, int tile_w, int tile_h, int tile_n_bits,
@@ -302,6 +319,14 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
     __shared__ int s_wsum[kEmitThreads / 32];
     const uint32_t vb = blockIdx.x;
     const int64_t e0 = (int64_t)vb * kEmitTile;
+    if (clamped) {  // device-side counts: the grid covers the capacity, blocks behind the real count have nothing to do
+        n_vis = clamped[0];
+        n_isects = clamped[1];
+        if (e0 >= n_isects) {
+            if (EXACT && threadIdx.x == 0) ex.seg_counts[vb] = 0;
+            return;
+        }
+    }
     const int64_t e1 = min(e0 + kEmitTile, n_isects);
     const int64_t j0 = first_j[vb];
     int64_t j1;  // Gaussian that owns entry e1 - 1
@@ -553,16 +578,18 @@ extern "C" int qed_isect_prepare(int C, int N, const float* depths, const int32_
 extern "C" size_t qed_isect_fill_workspace_bytes(int64_t n_isects) {
     if (n_isects <= 0) return 256;
     const size_t nb = (size_t)((n_isects + kEmitTile - 1) / kEmitTile + 1);
-    return 5 * align_up((size_t)n_isects * 4, 256) + radix_hist_bytes(n_isects) + align_up(nb * 4, 256) + align_up(nb * 8 + 8, 256);
+    return 5 * align_up((size_t)n_isects * 4, 256) + radix_hist_bytes(n_isects) + align_up(nb * 4, 256) + align_up(nb * 8 + 8, 256) + 256;
 }
 
 extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects, const float* means2d, const int32_t* radii,
                               const float* depths, const float* geom, int image_width, int image_height, int tile_size, int tile_width,
                               int tile_height, const void* prepare_workspace, void* workspace, size_t workspace_bytes,
-                              int64_t* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets, int64_t* n_exact_dev,
-                              qed_stream_t stream_) {
+                              const int64_t* counts_dev, int64_t* isect_ids, int32_t* flatten_ids, int32_t* isect_offsets,
+                              int64_t* n_exact_dev, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (C < 0 || N < 0 || n_visible < 0 || n_isects < 0 || tile_size <= 0) return QED_ERR_BAD_ARG;
+    // counts_dev: no host sync happened; n_visible / n_isects are capacities and the offsets always carry their end
+    if (counts_dev && !isect_offsets) return QED_ERR_BAD_ARG;
     const int64_t CN = (int64_t)C * N;
     const int n_tiles = tile_width * tile_height;
     // exact tile lists are requested by passing n_exact_dev (geom may legitimately be NULL for an empty scene):
@@ -573,7 +600,7 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     if (!exact && geom) return QED_ERR_BAD_ARG;  // geom without n_exact_dev: the caller would not learn the count
     if (n_isects == 0 || CN == 0) {
         if (isect_offsets && (int64_t)C * n_tiles > 0)
-            QED_CUDA_TRY(cudaMemsetAsync(isect_offsets, 0, ((size_t)C * n_tiles + (exact ? 1 : 0)) * 4, stream));
+            QED_CUDA_TRY(cudaMemsetAsync(isect_offsets, 0, ((size_t)C * n_tiles + ((exact || counts_dev) ? 1 : 0)) * 4, stream));
         if (exact) QED_CUDA_TRY(cudaMemsetAsync(n_exact_dev, 0, 8, stream));
         return QED_OK;
     }
@@ -598,7 +625,11 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     const size_t nb = (size_t)((n_isects + kEmitTile - 1) / kEmitTile);
     int32_t* first_j = reinterpret_cast<int32_t*>(ws + 5 * seg + radix_hist_bytes(n_isects));
     int32_t* seg_counts = reinterpret_cast<int32_t*>(ws + 5 * seg + radix_hist_bytes(n_isects) + align_up((nb + 1) * 4, 256));
-    emit_boundaries_kernel<<<(unsigned)((n_visible + 255) / 256), 256, 0, stream>>>(n_visible, cum2, first_j);
+    int64_t* clamped = counts_dev ? reinterpret_cast<int64_t*>(ws + 5 * seg + radix_hist_bytes(n_isects) + align_up((nb + 1) * 4, 256) +
+                                                               align_up((nb + 1) * 8 + 8, 256))
+                                  : nullptr;
+    if (n_visible == 0) return QED_ERR_BAD_ARG;  // n_isects > 0 needs at least one visible entry (capacity when counts_dev)
+    emit_boundaries_kernel<<<(unsigned)((n_visible + 255) / 256), 256, 0, stream>>>(n_visible, n_isects, counts_dev, clamped, cum2, first_j);
     QED_LAUNCH_CHECK();
     ExactEmit ex{};
     if (exact) {
@@ -608,16 +639,16 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
         ex.n_out = reinterpret_cast<unsigned long long*>(n_exact_dev);
         ex.width = image_width;
         ex.height = image_height;
-        emit_sorted_kernel<true><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, N, sorted_vals, cum2, first_j,
+        emit_sorted_kernel<true><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, clamped, N, sorted_vals, cum2, first_j,
                                                                            reinterpret_cast<const float2*>(means2d), radii, (float)tile_size,
                                                                            tile_width, tile_height, tile_n_bits, k0, v0, ex);
     } else {
-        emit_sorted_kernel<false><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, N, sorted_vals, cum2, first_j,
+        emit_sorted_kernel<false><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, clamped, N, sorted_vals, cum2, first_j,
                                                                             reinterpret_cast<const float2*>(means2d), radii, (float)tile_size,
                                                                             tile_width, tile_height, tile_n_bits, k0, v0, ex);
     }
     QED_LAUNCH_CHECK();
-    const int64_t* n_dev = exact ? n_exact_dev : nullptr;
+    const int64_t* n_dev = exact ? n_exact_dev : (clamped ? clamped + 1 : nullptr);
     SegCounts sc;
     if (exact) {
         sc.counts = seg_counts;

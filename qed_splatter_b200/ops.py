@@ -195,7 +195,7 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
         fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
         # geom = NULL: gsplat's lists bit for bit (the exact tile lists are the fused pipeline's business)
         check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), None, 0, 0, tile_size, tile_width,
-                                 tile_height, ptr(pws), ptr(fws), fws_bytes, ptr(isect_ids) if n_isects else None,
+                                 tile_height, ptr(pws), ptr(fws), fws_bytes, None, ptr(isect_ids) if n_isects else None,
                                  ptr(flatten_ids) if n_isects else None, ptr(offsets), None, stream), "qed_isect_fill")
         if return_offsets:
             return tiles_per_gauss, isect_ids, flatten_ids, offsets
@@ -267,7 +267,7 @@ def isect_tiles_exact(means2d: Tensor, radii: Tensor, depths: Tensor, geom: Tens
     fws_bytes = lib.qed_isect_fill_workspace_bytes(n_isects)
     fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
     check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), ptr(geom), width, height, tile_size,
-                             tile_width, tile_height, ptr(pws), ptr(fws), fws_bytes, None, ptr(flatten_ids) if n_isects else None,
+                             tile_width, tile_height, ptr(pws), ptr(fws), fws_bytes, None, None, ptr(flatten_ids) if n_isects else None,
                              ptr(offsets), ptr(counts[2:]), stream), "qed_isect_fill")
     return flatten_ids, offsets, counts[2:]
 

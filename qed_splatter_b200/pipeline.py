@@ -42,7 +42,8 @@ ACT_LOG_SCALES, ACT_LOGIT_OPACITIES = 1, 2  # `activations` bits (include/qed_sp
 class FusedSplatStep:
     """Holds reusable device buffers; `forward()` renders, `step()` renders + loss + full backward."""
 
-    def __init__(self, device, sort_impl: str = "two_level", want_isect_ids: bool = False, exact_tile_lists: bool = True):
+    def __init__(self, device, sort_impl: str = "two_level", want_isect_ids: bool = False, exact_tile_lists: bool = True,
+                 defer_sync: bool = True):
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.sort_impl = sort_impl
@@ -51,6 +52,14 @@ class FusedSplatStep:
         # centre of the tile are dropped before the tile sort (about half of gsplat's bounding-box lists); pixels are
         # unchanged.  The public `rasterization()` keeps gsplat's lists bit for bit (`info` contract).
         self.exact_tile_lists = exact_tile_lists
+        # The sizes of the intersection lists are only known on the device.  defer_sync (two_level only): from the second
+        # call on, the lists are built into buffers sized from the largest count seen so far (+25 %) and the counts are
+        # read by the host AFTER the rest of the forward (and, in step(), the loss and the compositor's backward) has been
+        # queued -- the device never idles on that read.  A count above the capacity builds an empty list on the device
+        # (memory-safe); the host sees it, grows the buffers and repeats the pass (rare: first steps, new viewpoints).
+        self.defer_sync = defer_sync and sort_impl == "two_level"
+        self._cap_isects = 0
+        self.overflow_repeats = 0
         self._n_exact = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._total = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._counts = torch.zeros(2, dtype=torch.int64, device=self.device)
@@ -84,9 +93,13 @@ class FusedSplatStep:
     @torch.no_grad()
     def forward(self, means, quats, scales, opacities, sh, viewmats, Ks, width: int, height: int, sh_degree: int,
                 render_mode: str = "RGB+ED", rasterize_mode: str = "classic", near_plane: float = 0.01,
-                far_plane: float = 1e10, eps2d: float = 0.3, backgrounds: Optional[Tensor] = None, activations: int = 0):
+                far_plane: float = 1e10, eps2d: float = 0.3, backgrounds: Optional[Tensor] = None, activations: int = 0,
+                _resolve: bool = True, _force_sync: bool = False):
         """`activations` (ACT_LOG_SCALES | ACT_LOGIT_OPACITIES): `scales` / `opacities` are the stored parameters; exp /
         sigmoid (qed_splatter/model.py:269-271) and their chain rule run inside the projection kernels."""
+        self._call = dict(args=(means, quats, scales, opacities, sh, viewmats, Ks, width, height, sh_degree),
+                          kw=dict(render_mode=render_mode, rasterize_mode=rasterize_mode, near_plane=near_plane, far_plane=far_plane, eps2d=eps2d,
+                                  backgrounds=backgrounds, activations=activations))
         lib, stream = self.lib, current_stream()
         _lib.require_cuda(means, quats, scales, opacities, sh, viewmats, Ks)
         self._mark("begin")
@@ -132,19 +145,26 @@ class FusedSplatStep:
             self._counts_ready.record(torch.cuda.current_stream())
             if self._prezero:
                 self._get("packed", (C * N, 12)).zero_()
-            self._counts_ready.synchronize()
-            n_vis, M = int(self._counts_host[0]), int(self._counts_host[1])
-            self._mark("sync")
+            deferred = self.defer_sync and not _force_sync and self._cap_isects > 0 and CN > 0
+            if deferred:
+                n_vis, M = CN, self._cap_isects  # capacities; the real counts stay on the device until _resolve_counts()
+            else:
+                self._counts_ready.synchronize()
+                n_vis, M = int(self._counts_host[0]), int(self._counts_host[1])
+                self._cap_isects = max(self._cap_isects, M + M // 4 + 4096)
+                self._mark("sync")
             cap = max(M, 1)
             ids = self._get("ids", (cap,), torch.int64)[:M]
             flat = self._get("flat", (cap,), torch.int32)[:M]
             fws_bytes = lib.qed_isect_fill_workspace_bytes(M)
             fws = self._get("fill_ws", (fws_bytes,), torch.uint8)
             check(lib.qed_isect_fill(C, N, n_vis, M, ptr(means2d), ptr(radii), ptr(depths), ptr(geom) if exact else None, width, height,
-                                     tile, tw, th, ptr(pws), ptr(fws), fws_bytes, ptr(ids) if (M and self.want_isect_ids) else None,
-                                     ptr(flat) if M else None, ptr(offsets), ptr(self._n_exact) if exact else None, stream), "qed_isect_fill")
+                                     tile, tw, th, ptr(pws), ptr(fws), fws_bytes, ptr(self._counts) if deferred else None,
+                                     ptr(ids) if (M and self.want_isect_ids) else None, ptr(flat) if M else None, ptr(offsets),
+                                     ptr(self._n_exact) if exact else None, stream), "qed_isect_fill")
             self._mark("isect_fill")
         else:
+            deferred = False
             cum = self._get("cum", (CN,), torch.int64)
             ws_bytes = lib.qed_isect_scan_workspace_bytes(CN)
             ws = self._get("scan_ws", (ws_bytes,), torch.uint8)
@@ -175,19 +195,40 @@ class FusedSplatStep:
         render = self._get("render", (C, height, width, D))
         alphas = self._get("alphas", (C, height, width, 1))
         last_ids = self._get("last_ids", (C, height, width), torch.int32)
-        check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets), int(exact),
+        check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets), int(exact or deferred),
                                  ptr(flat) if M else None, normalize, ptr(render), ptr(alphas), ptr(last_ids), stream), "qed_raster_fwd")
         self._mark("raster_fwd")
-        self._fwd = dict(C=C, N=N, D=D, M=M, exact=exact, activations=int(activations), K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
+        self._fwd = dict(C=C, N=N, D=D, M=M, exact=exact, deferred=deferred, has_end=int(exact or deferred), n_visible=None if deferred else n_vis, activations=int(activations), K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
                          th=th, width=width, height=height, eps2d=eps2d, radii=radii, conics=conics, comps=comps, colors=colors,
                          geom=geom, offsets=offsets, flat=flat, render=render, alphas=alphas, last_ids=last_ids, backgrounds=backgrounds,
                          inputs=(means, quats, scales, opacities, sh, viewmats, Ks))
+        if _resolve and not self._resolve_counts():
+            # the lists did not fit the buffers: repeat with the sizes read from the device (buffers grow, never shrink)
+            self.overflow_repeats += 1
+            return self.forward(*self._call["args"], **self._call["kw"], _force_sync=True)
         return render, alphas
+
+    def _resolve_counts(self) -> bool:
+        """Deferred mode: read the counts of the last forward (the copy was queued right behind the intersection build, the
+        device is busy with what was queued after it).  False = the real entry count exceeded the capacity (the device built
+        an empty list): the caller repeats the pass."""
+        f = self._fwd
+        if not f.get("deferred"):
+            return True
+        self._counts_ready.synchronize()
+        n_vis, M = int(self._counts_host[0]), int(self._counts_host[1])
+        ok = M <= f["M"]
+        self._cap_isects = max(self._cap_isects, M + M // 4 + 4096)
+        if ok:
+            # M stays the capacity the flat buffers were sliced with (an upper bound for the compositors, whose ranges end at
+            # the device-side count); the real count is kept for reporting
+            f["deferred"], f["n_visible"], f["n_isects_real"] = False, n_vis, M
+        return ok
 
     # -- backward from explicit output gradients ------------------------------------------------
     @torch.no_grad()
     def backward(self, v_render: Tensor, v_alphas: Optional[Tensor], grad_out: Optional[Dict[str, Tensor]] = None,
-                 n_chunks: int = 1, on_chunk=None, exchange=None):
+                 n_chunks: int = 1, on_chunk=None, exchange=None, _redo=None):
         """`grad_out`: optional preallocated {means,quats,scales,opacities,sh} (e.g. views into a flat
         all-reduce arena) that the projection backward writes straight into.
 
@@ -199,19 +240,34 @@ class FusedSplatStep:
         returns (in stream order): the projection backward stores its per-view colour gradients into every rank's exchange
         buffer, one all-reduce kernel sums the 11 non-SH floats per Gaussian and every rank rebuilds the SH coefficient
         gradient locally.  Returns views into the exchange's arena."""
-        lib, stream, f = self.lib, current_stream(), self._fwd
+        lib, stream = self.lib, current_stream()
+
+        def composite_backward(v_r, v_a):
+            f = self._fwd
+            C, N, D, M = f["C"], f["N"], f["D"], f["M"]
+            packed = self._get("packed", (C * N, 12))
+            if not self._prezeroed:
+                packed.zero_()
+            self._prezeroed = False
+            self._mark("zero_grads")
+            if M:
+                check(lib.qed_raster_bwd(C, N, M, D, ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]), f["width"], f["height"], 16,
+                                         f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"], ptr(f["render"]),
+                                         ptr(f["alphas"]), ptr(f["last_ids"]), ptr(v_r), ptr(v_a), ptr(packed), stream), "qed_raster_bwd")
+            self._mark("raster_bwd")
+            return packed
+
+        packed = composite_backward(v_render, v_alphas)
+        if not self._resolve_counts():
+            # deferred sizes (step() only): the intersection lists did not fit; everything queued so far ran on an empty
+            # list.  Repeat forward + loss with the sizes now known, then the compositor's backward.
+            if _redo is None:
+                raise RuntimeError("intersection capacity exceeded and no way to repeat the forward pass")
+            v_render, v_alphas = _redo()
+            packed = composite_backward(v_render, v_alphas)
+        f = self._fwd
         C, N, D, M = f["C"], f["N"], f["D"], f["M"]
         means, quats, scales, opacities, sh, viewmats, Ks = f["inputs"]
-        packed = self._get("packed", (C * N, 12))
-        if not self._prezeroed:
-            packed.zero_()
-        self._prezeroed = False
-        self._mark("zero_grads")
-        if M:
-            check(lib.qed_raster_bwd(C, N, M, D, ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]), f["width"], f["height"], 16,
-                                     f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"], ptr(f["render"]),
-                                     ptr(f["alphas"]), ptr(f["last_ids"]), ptr(v_render), ptr(v_alphas), ptr(packed), stream), "qed_raster_bwd")
-        self._mark("raster_bwd")
         if exchange is not None:
             if not f["n_color"] or f["deg"] < 0:
                 raise ValueError("the view-colour exchange needs SH colours (render_mode RGB / RGB+D / RGB+ED with sh_degree)")
@@ -282,33 +338,43 @@ class FusedSplatStep:
             mask = mask.contiguous()
             if mask.dtype == torch.bool:
                 mask = mask.view(torch.uint8)
-        self._prezero = self.sort_impl == "two_level"
-        render, alphas = self.forward(means, quats, scales, opacities, sh, viewmats, Ks, width, height, sh_degree, render_mode,
-                                      rasterize_mode, activations=activations)
-        self._prezeroed, self._prezero = self._prezero, False
         C = viewmats.shape[0]
         if self._stats is None or self._stats.numel() < C * 8:
             self._stats = torch.zeros(C * 8, dtype=torch.float64, device=self.device)
-        v_render = self._get("v_render", (C, height, width, 4))
-        v_alphas = self._get("v_alphas", (C, height, width, 1))
-        lws_bytes = lib.qed_loss_workspace_bytes(C, width, height, ssim_lambda)
-        lws = self._get("loss_ws", (lws_bytes,), torch.uint8) if lws_bytes else None
-        check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), int(gt_rgb.dtype == torch.uint8), ptr(gt_depth), ptr(mask),
-                                   int(mask is not None and mask.dtype == torch.uint8), ptr(background), rgb_weight,
-                                   depth_lambda, ssim_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas),
-                                   ptr(lws), lws_bytes, stream), "qed_loss_fwd_bwd")
-        self._mark("loss")
-        grads, packed = self.backward(v_render, v_alphas, grad_out, n_chunks=n_chunks, on_chunk=on_chunk, exchange=exchange)
+
+        def forward_and_loss(force_sync: bool):
+            self._prezero = self.sort_impl == "two_level"
+            render, alphas = self.forward(means, quats, scales, opacities, sh, viewmats, Ks, width, height, sh_degree, render_mode,
+                                          rasterize_mode, activations=activations, _resolve=False, _force_sync=force_sync)
+            self._prezeroed, self._prezero = self._prezero, False
+            v_render = self._get("v_render", (C, height, width, 4))
+            v_alphas = self._get("v_alphas", (C, height, width, 1))
+            lws_bytes = lib.qed_loss_workspace_bytes(C, width, height, ssim_lambda)
+            lws = self._get("loss_ws", (lws_bytes,), torch.uint8) if lws_bytes else None
+            check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), int(gt_rgb.dtype == torch.uint8), ptr(gt_depth), ptr(mask),
+                                       int(mask is not None and mask.dtype == torch.uint8), ptr(background), rgb_weight,
+                                       depth_lambda, ssim_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas),
+                                       ptr(lws), lws_bytes, stream), "qed_loss_fwd_bwd")
+            self._mark("loss")
+            return render, alphas, v_render, v_alphas
+
+        def redo():
+            self.overflow_repeats += 1
+            return forward_and_loss(True)[2:]
+
+        render, alphas, v_render, v_alphas = forward_and_loss(False)
+        grads, packed = self.backward(v_render, v_alphas, grad_out, n_chunks=n_chunks, on_chunk=on_chunk, exchange=exchange, _redo=redo)
         self._last_v = (v_render, v_alphas)
-        return StepOutput(loss=self._loss, grads=grads, packed_grads=packed, radii=self._fwd["radii"], render=render, alphas=alphas,
-                          n_isects=self._fwd["M"])
+        f = self._fwd
+        return StepOutput(loss=self._loss, grads=grads, packed_grads=packed, radii=f["radii"], render=f["render"], alphas=f["alphas"],
+                          n_isects=f.get("n_isects_real", f["M"]), n_visible=f.get("n_visible"))
 
     # -- instrumentation (never inside a timed region) --------------------------------------------
     def n_isects_exact(self) -> int:
         """Entries of the exact tile lists of the last forward (device -> host read: not for timed regions);
         equals StepOutput.n_isects (gsplat's bounding-box count) when exact_tile_lists is off."""
         f = self._fwd
-        return int(self._n_exact.item()) if (f.get("exact") and f["M"]) else int(f["M"])
+        return int(self._n_exact.item()) if (f.get("exact") and f["M"]) else int(f.get("n_isects_real", f["M"]))
 
     @property
     def launches_per_step(self) -> int:
@@ -349,7 +415,7 @@ class FusedSplatStep:
             try:
                 if which == "fwd":
                     check(lib.qed_raster_fwd(f["C"], f["N"], f["M"], f["D"], ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]),
-                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), int(f["exact"]), ptr(f["flat"]),
+                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), int(f["has_end"]), ptr(f["flat"]),
                                              f["normalize"], ptr(f["render"]), ptr(f["alphas"]), ptr(f["last_ids"]), stream), "qed_raster_fwd(stats)")
                 else:
                     v_render, v_alphas = self._last_v

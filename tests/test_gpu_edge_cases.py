@@ -116,7 +116,7 @@ def test_culling_is_exact_on_thin_tilted_splats(cuda):
         assert_close_frac(outs["cull"][i], ref, 1e-4, 1e-5 * float(ref.abs().mean() + 1e-30), 1e-3, name)
     for k in outs["cull"][2]:
         ref = outs["nocull"][2][k]
-        assert_close_frac(outs["cull"][2][k], ref, 5e-2, 1e-3 * float(ref.abs().mean() + 1e-30), 2e-2, f"v_{k}")
+        assert_close_frac(outs["cull"][2][k], ref, 5e-2, 1e-3 * float(ref.abs().mean() + 1e-30), 2e-2, f"v_{k}", max_outlier=5e-2)
     outs[True] = outs["cull"]
     # and against the oracle
     ro, ao, _ = oracle.rasterization(**a, width=W, height=H, render_mode="RGB+ED", sh_degree=None)

@@ -351,3 +351,39 @@ def test_trainer_steps_reduce_loss_and_refine(cuda):
     fired = [i for i, x in enumerate(infos) if x is not None]
     assert fired == [3, 6] and infos[3]["n"] == tr.arena.N or infos[6]["n"] == tr.arena.N
     assert infos[3]["n_dupli"] + infos[3]["n_split"] > 0
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_deferred_size_read_equals_synchronous_path_and_survives_overflow(cuda, exact):
+    """FusedSplatStep(defer_sync=True): the intersection counts are read by the host only after the rest of the pass has
+    been queued (buffers sized from earlier calls).  Same images as the synchronous path; a call whose lists exceed
+    the capacity is repeated with larger buffers and still gives the right answer."""
+    small = scene_s0(N=3000, C=1, size=96).to(cuda)
+    big = scene_s0(N=3000, C=1, size=96, seed=42)
+    big.scales = big.scales * 4.0  # ~16x the intersections of `small`: does not fit the capacity learnt from it
+    big = big.to(cuda)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=cuda)
+
+    def run(fs, s):
+        out = fs.step(s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, 3, s.gt_rgb, s.gt_depth, bg)
+        return out.render.clone(), out.alphas.clone(), out.loss.clone(), {k: v.clone() for k, v in out.grads.items()}, out.n_isects
+
+    sync = FusedSplatStep(cuda, defer_sync=False, exact_tile_lists=exact)
+    defer = FusedSplatStep(cuda, defer_sync=True, exact_tile_lists=exact)
+    ref_small, ref_big = run(sync, small), run(sync, big)
+    first = run(defer, small)       # first call: capacity unknown -> synchronous
+    second = run(defer, small)      # deferred
+    assert defer._cap_isects > 0 and defer.overflow_repeats == 0
+    third = run(defer, big)         # deferred, overflows, repeated
+    assert defer.overflow_repeats == 1 and ref_big[4] > 4 * ref_small[4]
+    fourth = run(defer, big)        # deferred, fits now
+    assert defer.overflow_repeats == 1
+    for got, ref in ((first, ref_small), (second, ref_small), (third, ref_big), (fourth, ref_big)):
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and got[4] == ref[4]
+        assert float(got[2][0]) == pytest.approx(float(ref[2][0]), rel=1e-6)
+        for k in ref[3]:
+            scale = float(ref[3][k].abs().mean()) + 1e-20
+            assert_close_frac(got[3][k], ref[3][k], 1e-4, 1e-5 * scale, 1e-3, f"deferred v_{k}")
+    # forward-only use resolves by itself
+    r1, a1 = defer.forward(small.means, small.quats, small.scales, small.opacities, small.sh, small.viewmats, small.Ks, 96, 96, 3)
+    assert torch.equal(r1, ref_small[0]) and torch.equal(a1, ref_small[1])
