@@ -158,10 +158,7 @@ int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* k
  *   dropped if it cannot touch a pixel centre of the tile (about half of them; no pixel changes).  The number of
  *   survivors stays on the device: it is written to n_exact_dev[1] (int64), flatten_ids / isect_ids are filled for
  *   that many entries (buffers sized for n_isects), and isect_offsets must have C*tile_height*tile_width + 1
- *   elements, the last one receiving the end of the last range (QED_LIST_HAS_END for the compositors).  When
- *   C * N <= 2^28 every flatten id additionally carries, in bits 28..31, the mask of the 8x8 blocks of its tile the
- *   Gaussian can touch (QED_LIST_BLOCK_MASKS: pass it to qed_raster_fwd / qed_raster_bwd, which then skip their own
- *   per-warp tests; strip the bits with & 0x0fffffff to recover the flat index).
+ *   elements, the last one receiving the end of the last range (pass offsets_has_end = 1 to qed_raster_fwd).
  *
  * counts_dev != NULL (= the counts_dev of qed_isect_prepare): NO host synchronisation is needed between prepare and fill.
  *   n_visible / n_isects are then CAPACITIES (n_visible = C*N is always enough; n_isects = what the caller sized
@@ -193,18 +190,12 @@ int qed_tile_ranges(int64_t n_isects, const int64_t* isect_ids_sorted, int C, in
  *  outputs: render[C,H,W,D], alphas[C,H,W], last_ids[C,H,W] i32 (index in sorted list of the last
  *  composited Gaussian; 0 if none).  For normalize_last the un-normalised last channel is
  *  recoverable as render*max(alpha,1e-10) (the backward does so).
- *  list_flags & QED_LIST_HAS_END : isect_offsets has one more element holding the end of the last range (lists of
- *  qed_isect_fill whose entry count lives on the device); n_isects is then only an upper bound.
- *  list_flags & QED_LIST_BLOCK_MASKS : exact tile lists of qed_isect_fill: flatten id = flat index | mask << 28, where bit
- *  (by * 2 + bx) of the mask says the Gaussian can reach alpha >= 1/255 at a pixel centre of the 8x8 block (bx, by) of its
- *  tile (the compositor's own conservative test, run ONCE by the intersection stage instead of once per warp in the
- *  forward and again in the backward).  Needs C * N <= 2^28.
+ *  offsets_has_end != 0 : isect_offsets has one more element holding the end of the last range (exact tile
+ *  lists of qed_isect_fill, whose entry count lives on the device); n_isects is then only an upper bound.
  */
-#define QED_LIST_HAS_END 1      /* isect_offsets has one more element: the end of the last range */
-#define QED_LIST_BLOCK_MASKS 2  /* bits 28..31 of every flatten id: 2x2 mask of the tile's 8x8 blocks the Gaussian can touch */
 int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
                    const float* backgrounds, int width, int height, int tile_size, int tile_width,
-                   int tile_height, const int32_t* isect_offsets, int list_flags, const int32_t* flatten_ids,
+                   int tile_height, const int32_t* isect_offsets, int offsets_has_end, const int32_t* flatten_ids,
                    int normalize_last, float* render, float* alphas, int32_t* last_ids, qed_stream_t stream);
 
 /* (d) compositing backward.
@@ -217,7 +208,7 @@ int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, con
  */
 int qed_raster_bwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
                    const float* backgrounds, int width, int height, int tile_size, int tile_width,
-                   int tile_height, const int32_t* isect_offsets, int list_flags, const int32_t* flatten_ids,
+                   int tile_height, const int32_t* isect_offsets, const int32_t* flatten_ids,
                    int normalize_last, const float* render, const float* alphas, const int32_t* last_ids,
                    const float* v_render, const float* v_alphas, float* packed_grads, qed_stream_t stream);
 

@@ -42,7 +42,7 @@ SIGNATURES = {
     "qed_tile_ranges": (c_int, [c_int64, P, c_int, c_int, c_int, P, P]),
     "qed_raster_fwd": (c_int, [c_int, c_int, c_int64, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P,
                                c_int, P, P, P, P]),
-    "qed_raster_bwd": (c_int, [c_int, c_int, c_int64, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P,
+    "qed_raster_bwd": (c_int, [c_int, c_int, c_int64, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P,
                                c_int, P, P, P, P, P, P, P]),
     "qed_unpack_grads": (c_int, [c_int, c_int, P, P, P, P, P, P, P]),
     "qed_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_float]),

@@ -299,22 +299,7 @@ struct ExactEmit {
     int32_t* seg_counts;   // survivors per block
     unsigned long long* n_out;  // device scalar: total number of survivors (zeroed by the caller)
     int width, height;
-    int block_masks;  // also test the survivors against the 2x2 8x8 blocks of their tile; mask -> bits 28..31 of the value
 };
-
-// tile (tx, ty) of a key (camera | tile id)
-__device__ __forceinline__ void tile_of_key(uint32_t key, uint32_t tile_mask, int tile_w, float inv_tile_w, int& tx, int& ty) {
-    const int tile = (int)(key & tile_mask);
-    ty = (int)(((float)tile + 0.5f) * inv_tile_w);  // exact below 2^22 tiles; corrected below anyway
-    tx = tile - ty * tile_w;
-    if (tx < 0) {
-        --ty;
-        tx += tile_w;
-    } else if (tx >= tile_w) {
-        ++ty;
-        tx -= tile_w;
-    }
-}
 
 template <bool EXACT>
 __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis, int64_t n_isects, const int64_t* __restrict__ clamped, int N,
@@ -428,8 +413,16 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
     for (int k = 0; k < kPer; ++k) {
         const int t = threadIdx.x * kPer + k;
         if (t < cnt) {
-            int tx, ty;
-            tile_of_key(key[k], tile_mask, tile_w, inv_tile_w, tx, ty);
+            const int tile = (int)(key[k] & tile_mask);
+            int ty = (int)(((float)tile + 0.5f) * inv_tile_w);  // exact below 2^22 tiles; corrected below anyway
+            int tx = tile - ty * tile_w;
+            if (tx < 0) {
+                --ty;
+                tx += tile_w;
+            } else if (tx >= tile_w) {
+                ++ty;
+                tx -= tile_w;
+            }
             const float4 ga = ex.geom[(int64_t)val[k] * 2], gb = ex.geom[(int64_t)val[k] * 2 + 1];
             const float x0 = (float)(tx * (int)tile_size) + 0.5f, y0 = (float)(ty * (int)tile_size) + 0.5f;
             const float x1 = (float)min(tx * (int)tile_size + (int)tile_size - 1, ex.width - 1) + 0.5f;
@@ -470,29 +463,9 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
         }
     }
     __syncthreads();
-    // The survivors are compacted, so every lane has work: test each against the four 8x8 blocks of its tile (the
-    // compositors' cull granularity: one warp = two blocks) with the same conservative test and ship the 4-bit mask in the
-    // top bits of the value.  The forward and the backward compositor then need no ellipse test at all.
     for (int t = threadIdx.x; t < total; t += kEmitThreads) {
-        const uint32_t k = s_okey[t];
-        int32_t v = s_oval[t];
-        if (ex.block_masks) {
-            int tx, ty;
-            tile_of_key(k, tile_mask, tile_w, inv_tile_w, tx, ty);
-            const float4 ga = ex.geom[(int64_t)v * 2], gb = ex.geom[(int64_t)v * 2 + 1];
-            const float A = 0.5f * kLog2e * gb.x, B = kLog2e * gb.y, Cq = 0.5f * kLog2e * gb.z, tau2 = __log2f(ga.z) + kLog2_255;
-            uint32_t m4 = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int sx = tx * (int)tile_size + (b & 1) * 8, sy = ty * (int)tile_size + (b >> 1) * 8;
-                const float x0 = (float)sx + 0.5f, y0 = (float)sy + 0.5f;
-                const float x1 = (float)min(sx + 7, ex.width - 1) + 0.5f, y1 = (float)min(sy + 7, ex.height - 1) + 0.5f;
-                if (ellipse_hits_rect(ga.x, ga.y, A, B, Cq, tau2, x0, y0, x1, y1)) m4 |= 1u << b;
-            }
-            v = (int32_t)((uint32_t)v | (m4 << 28));
-        }
-        tkeys[e0 + t] = k;
-        tvals[e0 + t] = v;
+        tkeys[e0 + t] = s_okey[t];
+        tvals[e0 + t] = s_oval[t];
     }
 }
 
@@ -502,9 +475,8 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
 // 16-byte key load): the kernel is a 28 MB stream and was latency-bound at one entry per thread.
 constexpr int kComposePer = 4;
 __global__ void __launch_bounds__(256) compose_ids_ranges_kernel(int64_t n_host, const int64_t* __restrict__ n_dev, const uint32_t* __restrict__ tkeys,
-                                                                 const int32_t* __restrict__ flat, int32_t id_mask, const float* __restrict__ depths, int C,
-                                                                 int n_tiles, int tile_n_bits, int64_t* __restrict__ isect_ids,
-                                                                 int32_t* __restrict__ offsets) {
+                                                                 const int32_t* __restrict__ flat, const float* __restrict__ depths, int C, int n_tiles,
+                                                                 int tile_n_bits, int64_t* __restrict__ isect_ids, int32_t* __restrict__ offsets) {
     const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kComposePer;
     const int64_t n = n_dev ? *n_dev : n_host;
     if (n_dev && offsets && i0 == 0) {
@@ -528,7 +500,7 @@ __global__ void __launch_bounds__(256) compose_ids_ranges_kernel(int64_t n_host,
         const int64_t i = i0 + k;
         if (i >= n) break;
         if (isect_ids) {
-            const uint32_t db = (uint32_t)__float_as_int(depths[flat[i] & id_mask]);
+            const uint32_t db = (uint32_t)__float_as_int(depths[flat[i]]);
             isect_ids[i] = (int64_t)(((uint64_t)key[k] << 32) | db);
         }
         if (offsets) {
@@ -623,8 +595,6 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     // exact tile lists are requested by passing n_exact_dev (geom may legitimately be NULL for an empty scene):
     // offsets has C * n_tiles + 1 elements, the count stays on the device
     const bool exact = n_exact_dev != nullptr;
-    // exact lists carry the 2x2 block mask of every entry in bits 28..31 of its flatten id whenever the ids leave room
-    const bool block_masks = exact && CN <= ((int64_t)1 << 28);
     if (exact && (!isect_offsets || image_width <= 0 || image_height <= 0)) return QED_ERR_BAD_ARG;
     if (exact && n_isects > 0 && CN > 0 && (!geom || (reinterpret_cast<uintptr_t>(geom) & 15))) return QED_ERR_BAD_ARG;
     if (!exact && geom) return QED_ERR_BAD_ARG;  // geom without n_exact_dev: the caller would not learn the count
@@ -669,7 +639,6 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
         ex.n_out = reinterpret_cast<unsigned long long*>(n_exact_dev);
         ex.width = image_width;
         ex.height = image_height;
-        ex.block_masks = block_masks ? 1 : 0;
         emit_sorted_kernel<true><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, clamped, N, sorted_vals, cum2, first_j,
                                                                            reinterpret_cast<const float2*>(means2d), radii, (float)tile_size,
                                                                            tile_width, tile_height, tile_n_bits, k0, v0, ex);
@@ -688,7 +657,7 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     }
     int rc = radix_sort_pairs<uint32_t>(n_isects, n_dev, k0, v0, k1, flatten_ids, k2, v2, hist, tile_n_bits + cam_bits, stream, sc);
     if (rc != QED_OK) return rc;
-    compose_ids_ranges_kernel<<<(unsigned)((n_isects + 256 * kComposePer - 1) / (256 * kComposePer)), 256, 0, stream>>>(n_isects, n_dev, k1, flatten_ids, block_masks ? 0x0fffffff : -1, depths, C, n_tiles,
+    compose_ids_ranges_kernel<<<(unsigned)((n_isects + 256 * kComposePer - 1) / (256 * kComposePer)), 256, 0, stream>>>(n_isects, n_dev, k1, flatten_ids, depths, C, n_tiles,
                                                                                    tile_n_bits, isect_ids, isect_offsets);
     QED_LAUNCH_CHECK();
     return QED_OK;

@@ -32,12 +32,9 @@
 namespace qed {
 
 constexpr int kTile = 16;
-constexpr int kIdBits = 28;                       // flat (camera, Gaussian) index bits of a list entry when it carries a block mask
-constexpr int kIdMask = (1 << kIdBits) - 1;
 
 struct RasterParams {
     int C, N, D, width, height, tile_w, tile_h, normalize_last, offsets_has_end;
-    int ids_have_masks;  // exact tile lists: bits 28..31 of a flatten id = which 8x8 blocks of the tile the Gaussian can touch
     int64_t n_isects;
     const float4* geom;
     const float* colors;
@@ -124,7 +121,6 @@ __device__ __forceinline__ int stage_batch(const RasterParams& p, Staging<PX>& s
     bool keep = false;
     if (have) {
         g = p.flatten_ids[e];
-        if (p.ids_have_masks) g &= kIdMask;  // (the scalar cross-check kernels do their own culling tests)
         const float4 ga = p.geom[g * 2];      // mx, my, opacity, depth
         const float4 gb = p.geom[g * 2 + 1];  // conic a, b, c
         const float lo = __log2f(ga.z);
@@ -438,19 +434,15 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 14) raster_fwd_ws_kernel(c
     int alive = sr.present;  // warp-uniform: 8x8 blocks that still have a live pixel
 
     // batch i covers sorted indices [range_start + 32 i, + 32), lane l owns range_start + 32 i + l
-    // (list entries: flat index, plus -- exact lists -- the 2x2 mask of 8x8 blocks the Gaussian can touch in bits 28..31,
-    //  computed once by the intersection stage with the same conservative test this kernel would run per warp)
-    const int idm = p.ids_have_masks ? kIdMask : -1;
-    const int mshift = kIdBits + 2 * warp;
     const int n_batches = (range_end - range_start + 31) / 32;
     int e_cur = range_start + lane;
     int g_cur = e_cur < range_end ? p.flatten_ids[e_cur] : 0;
-    stream_fetch<D>(p, ws, 0, lane, e_cur < range_end, g_cur & idm);
+    stream_fetch<D>(p, ws, 0, lane, e_cur < range_end, g_cur);
     int g_nxt = (e_cur + 32 < range_end) ? p.flatten_ids[e_cur + 32] : 0;
 
     for (int i = 0; i < n_batches && alive; ++i, e_cur += 32) {
         const int buf = i & 1;
-        stream_fetch<D>(p, ws, buf ^ 1, lane, e_cur + 32 < range_end, g_nxt & idm);  // batch i+1: geom + colour
+        stream_fetch<D>(p, ws, buf ^ 1, lane, e_cur + 32 < range_end, g_nxt);       // batch i+1: geom + colour
         const int g_n2 = (e_cur + 64 < range_end) ? p.flatten_ids[e_cur + 64] : 0;  // batch i+2: id
         cp_async_wait<1>();                                                         // batch i has landed
         const bool have = e_cur < range_end;
@@ -462,17 +454,13 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 14) raster_fwd_ws_kernel(c
             const float4 gb = ws.rb[buf][lane];  // conic a, b, c
             const float lo = __log2f(ga.z);
             A = make_float4(ga.x, ga.y, lo, __int_as_float(e_cur));
-            B = make_float4(-0.5f * kLog2e * gb.x, -kLog2e * gb.y, -0.5f * kLog2e * gb.z, __int_as_float(g_cur & idm));
-            if (CULL && p.ids_have_masks) {
-                mask = alive & (int)(((unsigned)g_cur >> mshift) & 3u);
-            } else {
-                const float tau2 = lo + kLog2_255;
+            B = make_float4(-0.5f * kLog2e * gb.x, -kLog2e * gb.y, -0.5f * kLog2e * gb.z, __int_as_float(g_cur));
+            const float tau2 = lo + kLog2_255;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    bool hit = (alive >> k) & 1;
-                    if (CULL && hit) hit = ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, tau2, sr.x0[k], sr.y0[k], sr.x1[k], sr.y1[k]);
-                    if (hit) mask |= 1 << k;
-                }
+            for (int k = 0; k < 2; ++k) {
+                bool hit = (alive >> k) & 1;
+                if (CULL && hit) hit = ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, tau2, sr.x0[k], sr.y0[k], sr.x1[k], sr.y1[k]);
+                if (hit) mask |= 1 << k;
             }
         }
         st.add(1, mask ? 1 : 0);
@@ -971,17 +959,15 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(c
 
     // batch i covers sorted indices (top - 32 i - 31 .. top - 32 i], lane l owns top - 32 i - l
     const int top = wmax;
-    const int idm = p.ids_have_masks ? kIdMask : -1;  // see raster_fwd_ws_kernel
-    const int mshift = kIdBits + 2 * warp;
     const int n_batches = (top - range_start) / 32 + 1;
     int e_cur = top - lane;
     int g_cur = e_cur >= range_start ? p.flatten_ids[e_cur] : 0;
-    stream_fetch<D>(p, ws, 0, lane, e_cur >= range_start, g_cur & idm);
+    stream_fetch<D>(p, ws, 0, lane, e_cur >= range_start, g_cur);
     int g_nxt = (e_cur - 32 >= range_start) ? p.flatten_ids[e_cur - 32] : 0;
 
     for (int i = 0; i < n_batches; ++i, e_cur -= 32) {
         const int buf = i & 1;
-        stream_fetch<D>(p, ws, buf ^ 1, lane, e_cur - 32 >= range_start, g_nxt & idm);  // batch i+1: geom + colour
+        stream_fetch<D>(p, ws, buf ^ 1, lane, e_cur - 32 >= range_start, g_nxt);       // batch i+1: geom + colour
         const int g_n2 = (e_cur - 64 >= range_start) ? p.flatten_ids[e_cur - 64] : 0;  // batch i+2: id
         cp_async_wait<1>();                                                            // batch i has landed
         const bool have = e_cur >= range_start;
@@ -993,13 +979,12 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(c
             const float4 gb = ws.rb[buf][lane];  // conic a, b, c
             const float lo = __log2f(ga.z);
             A = make_float4(ga.x, ga.y, lo, __int_as_float(e_cur));
-            B = make_float4(-0.5f * kLog2e * gb.x, -kLog2e * gb.y, -0.5f * kLog2e * gb.z, __int_as_float(g_cur & idm));
+            B = make_float4(-0.5f * kLog2e * gb.x, -kLog2e * gb.y, -0.5f * kLog2e * gb.z, __int_as_float(g_cur));
             const float tau2 = lo + kLog2_255;
-            const int pre = (CULL && p.ids_have_masks) ? (int)(((unsigned)g_cur >> mshift) & 3u) : 3;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                bool hit = ((want >> k) & 1) && (e_cur <= sub_max[k]) && ((pre >> k) & 1);
-                if (CULL && !p.ids_have_masks && hit) hit = ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, tau2, sr.x0[k], sr.y0[k], sr.x1[k], sr.y1[k]);
+                bool hit = ((want >> k) & 1) && (e_cur <= sub_max[k]);
+                if (CULL && hit) hit = ellipse_hits_rect(A.x, A.y, -B.x, -B.y, -B.z, tau2, sr.x0[k], sr.y0[k], sr.x1[k], sr.y1[k]);
                 if (hit) mask |= 1 << k;
             }
         }
@@ -1213,7 +1198,7 @@ extern "C" int qed_debug_set_raster_px(int px_fwd, int px_bwd) {
 
 extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
                               const float* backgrounds, int width, int height, int tile_size, int tile_width,
-                              int tile_height, const int32_t* isect_offsets, int list_flags, const int32_t* flatten_ids,
+                              int tile_height, const int32_t* isect_offsets, int offsets_has_end, const int32_t* flatten_ids,
                               int normalize_last, float* render, float* alphas, int32_t* last_ids, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = check_raster_args(C, N, n_isects, D, width, height, tile_size, tile_width, tile_height);
@@ -1227,9 +1212,7 @@ extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float
     p.render = render;
     p.alphas = alphas;
     p.last_ids = last_ids;
-    p.offsets_has_end = (list_flags & QED_LIST_HAS_END) ? 1 : 0;
-    p.ids_have_masks = (list_flags & QED_LIST_BLOCK_MASKS) ? 1 : 0;
-    if (p.ids_have_masks && (int64_t)C * N > (int64_t)kIdMask + 1) return QED_ERR_BAD_ARG;
+    p.offsets_has_end = offsets_has_end ? 1 : 0;
     switch (D) {
         case 1: return launch_raster<1, false>(p, stream);
         case 3: return launch_raster<3, false>(p, stream);
@@ -1239,7 +1222,7 @@ extern "C" int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float
 
 extern "C" int qed_raster_bwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
                               const float* backgrounds, int width, int height, int tile_size, int tile_width,
-                              int tile_height, const int32_t* isect_offsets, int list_flags, const int32_t* flatten_ids,
+                              int tile_height, const int32_t* isect_offsets, const int32_t* flatten_ids,
                               int normalize_last, const float* render, const float* alphas, const int32_t* last_ids,
                               const float* v_render, const float* v_alphas, float* packed_grads, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -1257,8 +1240,6 @@ extern "C" int qed_raster_bwd(int C, int N, int64_t n_isects, int D, const float
     p.v_render = v_render;
     p.v_alphas = v_alphas;
     p.packed_grads = packed_grads;
-    p.ids_have_masks = (list_flags & QED_LIST_BLOCK_MASKS) ? 1 : 0;
-    if (p.ids_have_masks && (int64_t)C * N > (int64_t)kIdMask + 1) return QED_ERR_BAD_ARG;
     switch (D) {
         case 1: return launch_raster<1, true>(p, stream);
         case 3: return launch_raster<3, true>(p, stream);

@@ -21,14 +21,6 @@ from ._lib import check, current_stream, ptr
 
 GRAD_FLOATS = 12
 GEOM_FLOATS = 8
-LIST_HAS_END, LIST_BLOCK_MASKS = 1, 2  # `list_flags` of qed_raster_fwd / qed_raster_bwd (include/qed_splat.h)
-ID_BITS = 28
-
-
-def exact_lists_have_block_masks(C: int, N: int) -> bool:
-    """qed_isect_fill ships the 2x2 block mask of every entry of an EXACT list in bits 28..31 of its flatten id whenever
-    the flat (camera, Gaussian) indices leave room for it."""
-    return C * N <= (1 << ID_BITS)
 _SORT_IMPL = "two_level"  # "two_level" (product path) | "own" | "cub" — identical output
 SORT_IMPLS = ("two_level", "own", "cub")
 
@@ -257,9 +249,7 @@ def isect_tiles_exact(means2d: Tensor, radii: Tensor, depths: Tensor, geom: Tens
     """EXACT tile lists for the compositor (not gsplat's `info` lists): every (Gaussian, tile) candidate of gsplat's
     bounding-box lists that cannot reach alpha = 1/255 at a pixel centre of the tile is dropped before the tile sort
     (DESIGN.md section 5).  -> flatten_ids[M] i32 (M = gsplat's count; only the first n_exact entries are filled),
-    isect_offsets[C*th*tw + 1] i32 (last element = n_exact = end of the last range), n_exact[1] i64 on the device,
-    block_masks (bool): bits 28..31 of every flatten id hold the mask of the 8x8 blocks of its tile the Gaussian can touch
-    (flat index = id & 0x0fffffff); pass it on to rasterize_to_pixels."""
+    isect_offsets[C*th*tw + 1] i32 (last element = n_exact = end of the last range), n_exact[1] i64 on the device."""
     lib = _lib.load()
     _lib.require_cuda(means2d, radii, depths, geom)
     means2d, depths = _f32c(means2d.detach()), _f32c(depths.detach())
@@ -279,7 +269,7 @@ def isect_tiles_exact(means2d: Tensor, radii: Tensor, depths: Tensor, geom: Tens
     check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), ptr(geom), width, height, tile_size,
                              tile_width, tile_height, ptr(pws), ptr(fws), fws_bytes, None, None, ptr(flatten_ids) if n_isects else None,
                              ptr(offsets), ptr(counts[2:]), stream), "qed_isect_fill")
-    return flatten_ids, offsets, counts[2:], exact_lists_have_block_masks(C, N)
+    return flatten_ids, offsets, counts[2:]
 
 
 @torch.no_grad()
@@ -299,7 +289,7 @@ def isect_offset_encode(isect_ids: Tensor, C: int, tile_width: int, tile_height:
 class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, backgrounds, geom, width, height, tile_size, isect_offsets,
-                flatten_ids, absgrad, normalize_last, block_masks):
+                flatten_ids, absgrad, normalize_last):
         lib = _lib.load()
         _lib.require_cuda(means2d, conics, colors, opacities, isect_offsets, flatten_ids)
         C, N = opacities.shape
@@ -318,13 +308,12 @@ class _RasterizeToPixels(torch.autograd.Function):
         render = torch.empty(C, height, width, D, device=dev)
         alphas = torch.empty(C, height, width, 1, device=dev)
         last_ids = torch.empty(C, height, width, dtype=torch.int32, device=dev)
-        flags = (LIST_HAS_END if has_end else 0) | (LIST_BLOCK_MASKS if block_masks else 0)
         check(lib.qed_raster_fwd(C, N, n_isects, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile_size,
-                                 tile_width, tile_height, ptr(isect_offsets), flags, ptr(flatten_ids), int(normalize_last),
+                                 tile_width, tile_height, ptr(isect_offsets), int(has_end), ptr(flatten_ids), int(normalize_last),
                                  ptr(render), ptr(alphas), ptr(last_ids), current_stream()), "qed_raster_fwd")
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, geom, isect_offsets, flatten_ids, render,
                               alphas, last_ids)
-        ctx.cfg = (width, height, tile_size, absgrad, normalize_last, flags)
+        ctx.cfg = (width, height, tile_size, absgrad, normalize_last)
         ctx.mark_non_differentiable(last_ids)
         return render, alphas, last_ids
 
@@ -332,7 +321,7 @@ class _RasterizeToPixels(torch.autograd.Function):
     def backward(ctx, v_render, v_alphas, _v_last):
         lib = _lib.load()
         means2d, conics, colors, opacities, backgrounds, geom, isect_offsets, flatten_ids, render, alphas, last_ids = ctx.saved_tensors
-        width, height, tile_size, absgrad, normalize_last, flags = ctx.cfg
+        width, height, tile_size, absgrad, normalize_last = ctx.cfg
         C, N = opacities.shape
         D = colors.shape[-1]
         dev = means2d.device
@@ -340,7 +329,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         packed = torch.zeros(C * N, GRAD_FLOATS, device=dev)
         v_render = _f32c(v_render) if v_render is not None else torch.zeros_like(render)
         check(lib.qed_raster_bwd(C, N, flatten_ids.numel(), D, ptr(geom), ptr(colors), ptr(backgrounds), width, height,
-                                 tile_size, tile_width, tile_height, ptr(isect_offsets), flags, ptr(flatten_ids),
+                                 tile_size, tile_width, tile_height, ptr(isect_offsets), ptr(flatten_ids),
                                  int(normalize_last), ptr(render), ptr(alphas), ptr(last_ids), ptr(v_render),
                                  ptr(_f32c(v_alphas)), ptr(packed), current_stream()), "qed_raster_bwd")
         v_means2d = torch.empty(C, N, 2, device=dev)
@@ -359,16 +348,14 @@ class _RasterizeToPixels(torch.autograd.Function):
                 g = g.clone()
                 g[..., -1:] = g[..., -1:] / alphas.clamp(min=1e-10)
             v_bg = (g * (1.0 - alphas)).sum(dim=(1, 2))
-        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None, None
+        return v_means2d, v_conics, v_colors, v_opac, v_bg, None, None, None, None, None, None, None, None
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, image_width: int,
                         image_height: int, tile_size: int, isect_offsets: Tensor, flatten_ids: Tensor,
                         backgrounds: Optional[Tensor] = None, packed: bool = False, absgrad: bool = False,
-                        geom: Optional[Tensor] = None, normalize_last: bool = False, return_last_ids: bool = False,
-                        block_masks: bool = False):
-    """gsplat `rasterize_to_pixels` -> (render[C,H,W,D], alphas[C,H,W,1]) (+ last_ids when asked).
-    `block_masks`: flatten_ids come from `isect_tiles_exact` and carry the per-entry block masks (its 4th return value)."""
+                        geom: Optional[Tensor] = None, normalize_last: bool = False, return_last_ids: bool = False):
+    """gsplat `rasterize_to_pixels` -> (render[C,H,W,D], alphas[C,H,W,1]) (+ last_ids when asked)."""
     if packed:
         raise NotImplementedError("packed mode is not reachable from qed_splatter/model.py:267-288")
     if colors.shape[-1] not in (1, 3, 4):
@@ -377,7 +364,7 @@ def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opaciti
         raise NotImplementedError("tile_size is 16 on this path (qed_splatter/model.py:243)")
     render, alphas, last_ids = _RasterizeToPixels.apply(
         means2d, conics, colors, opacities, backgrounds, geom, int(image_width), int(image_height), int(tile_size),
-        isect_offsets.contiguous(), flatten_ids.contiguous(), bool(absgrad), bool(normalize_last), bool(block_masks))
+        isect_offsets.contiguous(), flatten_ids.contiguous(), bool(absgrad), bool(normalize_last))
     if return_last_ids:
         return render, alphas, last_ids
     return render, alphas

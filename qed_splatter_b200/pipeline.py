@@ -192,14 +192,13 @@ class FusedSplatStep:
             self._mark("sort")
             check(lib.qed_tile_ranges(M, ptr(ids) if M else None, C, tw, th, ptr(offsets), stream), "qed_tile_ranges")
             self._mark("ranges")
-        list_flags = (ops.LIST_HAS_END if (exact or deferred) else 0) | (ops.LIST_BLOCK_MASKS if (exact and ops.exact_lists_have_block_masks(C, N)) else 0)
         render = self._get("render", (C, height, width, D))
         alphas = self._get("alphas", (C, height, width, 1))
         last_ids = self._get("last_ids", (C, height, width), torch.int32)
-        check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets), list_flags,
+        check(lib.qed_raster_fwd(C, N, M, D, ptr(geom), ptr(colors), ptr(backgrounds), width, height, tile, tw, th, ptr(offsets), int(exact or deferred),
                                  ptr(flat) if M else None, normalize, ptr(render), ptr(alphas), ptr(last_ids), stream), "qed_raster_fwd")
         self._mark("raster_fwd")
-        self._fwd = dict(C=C, N=N, D=D, M=M, exact=exact, deferred=deferred, has_end=int(exact or deferred), list_flags=list_flags, n_visible=None if deferred else n_vis, activations=int(activations), K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
+        self._fwd = dict(C=C, N=N, D=D, M=M, exact=exact, deferred=deferred, has_end=int(exact or deferred), n_visible=None if deferred else n_vis, activations=int(activations), K=K, deg=deg, n_color=n_color, append=append, normalize=normalize, comp=comp, tw=tw,
                          th=th, width=width, height=height, eps2d=eps2d, radii=radii, conics=conics, comps=comps, colors=colors,
                          geom=geom, offsets=offsets, flat=flat, render=render, alphas=alphas, last_ids=last_ids, backgrounds=backgrounds,
                          inputs=(means, quats, scales, opacities, sh, viewmats, Ks))
@@ -253,7 +252,7 @@ class FusedSplatStep:
             self._mark("zero_grads")
             if M:
                 check(lib.qed_raster_bwd(C, N, M, D, ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]), f["width"], f["height"], 16,
-                                         f["tw"], f["th"], ptr(f["offsets"]), f["list_flags"], ptr(f["flat"]), f["normalize"], ptr(f["render"]),
+                                         f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"], ptr(f["render"]),
                                          ptr(f["alphas"]), ptr(f["last_ids"]), ptr(v_r), ptr(v_a), ptr(packed), stream), "qed_raster_bwd")
             self._mark("raster_bwd")
             return packed
@@ -416,13 +415,13 @@ class FusedSplatStep:
             try:
                 if which == "fwd":
                     check(lib.qed_raster_fwd(f["C"], f["N"], f["M"], f["D"], ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]),
-                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), f["list_flags"], ptr(f["flat"]),
+                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), int(f["has_end"]), ptr(f["flat"]),
                                              f["normalize"], ptr(f["render"]), ptr(f["alphas"]), ptr(f["last_ids"]), stream), "qed_raster_fwd(stats)")
                 else:
                     v_render, v_alphas = self._last_v
                     scratch = torch.zeros(f["C"] * f["N"], 12, device=self.device)
                     check(lib.qed_raster_bwd(f["C"], f["N"], f["M"], f["D"], ptr(f["geom"]), ptr(f["colors"]), ptr(f["backgrounds"]),
-                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), f["list_flags"], ptr(f["flat"]), f["normalize"],
+                                             f["width"], f["height"], 16, f["tw"], f["th"], ptr(f["offsets"]), ptr(f["flat"]), f["normalize"],
                                              ptr(f["render"]), ptr(f["alphas"]), ptr(f["last_ids"]), ptr(v_render), ptr(v_alphas),
                                              ptr(scratch), stream), "qed_raster_bwd(stats)")
                 torch.cuda.synchronize()

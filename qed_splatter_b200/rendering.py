@@ -141,7 +141,7 @@ def rasterization(
     tile_width, tile_height = ops.tile_grid(width, height, tile_size)
     # the compositor's lists (exact: about half of gsplat's entries, no pixel changes); gsplat's own lists are built
     # on demand by LazyInfo from the same projection outputs
-    flatten_ids, isect_offsets, _, block_masks = ops.isect_tiles_exact(means2d, radii, depths, geom, width, height, tile_size, tile_width, tile_height,
+    flatten_ids, isect_offsets, _ = ops.isect_tiles_exact(means2d, radii, depths, geom, width, height, tile_size, tile_width, tile_height,
                                                           tiles_per_gauss)
 
     def gsplat_lists(m=means2d.detach(), r=radii, d=depths.detach(), t=tiles_per_gauss):
@@ -158,7 +158,7 @@ def rasterization(
 
     render_colors, render_alphas = ops.rasterize_to_pixels(
         means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
-        absgrad=absgrad, geom=geom, normalize_last=normalize, block_masks=block_masks)
+        absgrad=absgrad, geom=geom, normalize_last=normalize)
 
     info = LazyInfo({
         "camera_ids": None,

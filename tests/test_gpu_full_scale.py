@@ -98,26 +98,24 @@ def test_sampled_tiles_forward_backward_match_oracle_at_full_size(cuda, name, li
     tw, th = ops.tile_grid(W, H, TILE)
     n_tiles = tw * th
     if lists == "exact":
-        flat, offsets, n_exact, block_masks = ops.isect_tiles_exact(g["means2d"], g["radii"], g["depths"], g["geom"], W, H, TILE, tw, th, g["tiles"])
-        assert block_masks
+        flat, offsets, n_exact = ops.isect_tiles_exact(g["means2d"], g["radii"], g["depths"], g["geom"], W, H, TILE, tw, th, g["tiles"])
         bounds = offsets.cpu().long()
         assert int(bounds[-1]) == int(n_exact.item())
     else:
         _, _, flat, off = ops.isect_tiles(g["means2d"], g["radii"], g["depths"], TILE, tw, th, tiles_per_gauss=g["tiles"], return_offsets=True)
-        offsets, block_masks = off, False
+        offsets = off
         bounds = torch.cat([off.flatten().cpu().long(), torch.tensor([flat.numel()])])
     starts, ends = bounds[:-1], bounds[1:]
     picks = _sample_tiles(starts, ends, tw, th)
     assert len(picks) >= 64
-    flat_c = flat.cpu().long() & (0x0FFFFFFF if block_masks else -1)  # exact lists: bits 28..31 carry the 8x8-block masks
+    flat_c = flat.cpu().long()
 
     # ---- CUDA: forward over the whole image, backward with gradients on the sampled tiles only ----
     leaf = {k: g[k].detach().clone().requires_grad_(True) for k in ("means2d", "conics", "cols", "opac")}
     render, alphas, last_ids = ops.rasterize_to_pixels(leaf["means2d"], leaf["conics"], leaf["cols"], leaf["opac"], W, H, TILE, offsets, flat,
-                                                       absgrad=True, geom=g["geom"], normalize_last=False, return_last_ids=True,
-                                                       block_masks=block_masks)
+                                                       absgrad=True, geom=g["geom"], normalize_last=False, return_last_ids=True)
     render_ed, _ = ops.rasterize_to_pixels(g["means2d"], g["conics"], g["cols"], g["opac"], W, H, TILE, offsets, flat, geom=g["geom"],
-                                           normalize_last=True, block_masks=block_masks)
+                                           normalize_last=True)
     gen = torch.Generator().manual_seed(3)
     sel = torch.zeros(1, H, W, 1)
     for t in picks:

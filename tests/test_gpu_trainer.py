@@ -198,13 +198,8 @@ def test_exact_tile_lists(cuda, size, scale):
         n = fs.n_isects_exact()
         n_tiles = s.C * f["tw"] * f["th"]
         off = f["offsets"][:n_tiles].tolist() + [n]
-        raw = f["flat"][:n].cpu()
-        has_masks = bool(f["list_flags"] & 2)
-        assert has_masks == exact
-        ids = (raw & 0x0FFFFFFF) if has_masks else raw  # exact lists: bits 28..31 = mask of the tile's 8x8 blocks
         res[exact] = dict(render=out.render.clone(), alphas=out.alphas.clone(), loss=out.loss.clone(), grads={k: v.clone() for k, v in out.grads.items()},
-                          flat=ids.tolist(), masks=((raw >> 28) & 0xF).tolist(), off=off, n=n, M=out.n_isects, geom=f["geom"].clone(), tw=f["tw"],
-                          th=f["th"])
+                          flat=f["flat"][:n].tolist(), off=off, n=n, M=out.n_isects, geom=f["geom"].clone(), tw=f["tw"], th=f["th"])
     a, b = res[False], res[True]
     assert a["n"] == a["M"] == b["M"] and 0 < b["n"] < a["n"]
     assert torch.equal(a["render"], b["render"]) and torch.equal(a["alphas"], b["alphas"]) and torch.equal(a["loss"], b["loss"])
@@ -213,42 +208,27 @@ def test_exact_tile_lists(cuda, size, scale):
         assert_close_frac(b["grads"][k], a["grads"][k], 1e-4, 1e-4 * sc, 1e-3, f"v_{k}")
     geom = a["geom"].view(-1, 8).cpu()
     tw, th = a["tw"], a["th"]
-    dropped = masked_blocks = 0
+    dropped = 0
     for t in range(s.C * tw * th):
         full, kept = a["flat"][a["off"][t]:a["off"][t + 1]], b["flat"][b["off"][t]:b["off"][t + 1]]
         it = iter(full)
         assert all(any(x == y for y in it) for x in kept), f"tile {t}: not an ordered subset"
         gone = sorted(set(full) - set(kept))  # a Gaussian appears at most once per tile
         assert len(gone) == len(full) - len(kept)
+        if not gone:
+            continue
+        dropped += len(gone)
         tile = t % (tw * th)
         ty, tx = divmod(tile, tw)
         ys = torch.arange(ty * 16, min(ty * 16 + 16, s.height)).float() + 0.5
         xs = torch.arange(tx * 16, min(tx * 16 + 16, s.width)).float() + 0.5
-
-        def alpha_of(rows):  # [G, h, w] float64 alpha of Gaussians `rows` at the tile's pixel centres
-            gg = geom[rows].double()  # mx, my, opacity, depth, a, b, c, -
-            dx = gg[:, 0, None, None] - xs[None, None, :].double()
-            dy = gg[:, 1, None, None] - ys[None, :, None].double()
-            sigma = 0.5 * (gg[:, 4, None, None] * dx * dx + gg[:, 6, None, None] * dy * dy) + gg[:, 5, None, None] * dx * dy
-            return gg[:, 2, None, None] * torch.exp(-sigma)
-
-        if gone:
-            dropped += len(gone)
-            alpha = alpha_of(gone)
-            assert float(alpha.max()) < 1.0 / 255.0, f"tile {t}: a dropped entry reaches alpha {float(alpha.max())}"
-        if kept and t % 3 == 0:
-            # the 2x2 block masks the compositors trust: a cleared bit means no pixel centre of that 8x8 block reaches 1/255
-            alpha = alpha_of(kept)
-            km = torch.tensor(b["masks"][b["off"][t]:b["off"][t + 1]])
-            for blk in range(4):
-                sub = alpha[:, (blk >> 1) * 8:(blk >> 1) * 8 + 8, (blk & 1) * 8:(blk & 1) * 8 + 8]
-                if sub.numel() == 0:
-                    continue
-                cleared = ((km >> blk) & 1) == 0
-                if bool(cleared.any()):
-                    assert float(sub[cleared].max()) < 1.0 / 255.0, f"tile {t} block {blk}: masked-out block reaches alpha >= 1/255"
-                masked_blocks += int(cleared.sum())
-    assert dropped == a["n"] - b["n"] and masked_blocks > 0
+        gg = geom[gone].double()  # mx, my, opacity, depth, a, b, c, -
+        dx = gg[:, 0, None, None] - xs[None, None, :].double()
+        dy = gg[:, 1, None, None] - ys[None, :, None].double()
+        sigma = 0.5 * (gg[:, 4, None, None] * dx * dx + gg[:, 6, None, None] * dy * dy) + gg[:, 5, None, None] * dx * dy
+        alpha = gg[:, 2, None, None] * torch.exp(-sigma)
+        assert float(alpha.max()) < 1.0 / 255.0, f"tile {t}: a dropped entry reaches alpha {float(alpha.max())}"
+    assert dropped == a["n"] - b["n"]
 
 
 def test_folded_activations_match_torch_chain_rule(cuda):
