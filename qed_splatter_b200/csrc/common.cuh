@@ -17,7 +17,44 @@
         if (_e != cudaSuccess) return (int)_e;    \
     } while (0)
 
+#include <cstdlib>
+#include <utility>
+
 namespace qed {
+
+// ---- programmatic dependent launch (sm_90+): a step is a chain of ~28 mostly short kernels on one stream.  Every
+// hot-path kernel starts with pdl_enter(): `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be
+// scheduled as soon as every CTA of this one has started (its CTAs then fill the slots this kernel's tail leaves
+// empty), `griddepcontrol.wait` holds this kernel until every kernel before it has completed and flushed -- nothing of a
+// predecessor is read, and nothing it may still read is written, before that.  Launches go through launch_pdl(), which
+// sets cudaLaunchAttributeProgrammaticStreamSerialization; QED_PDL=0 in the environment turns the attribute off (A/B).
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("QED_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 constexpr float kAlphaThreshold = 1.0f / 255.0f;
 constexpr float kTransmittanceThreshold = 1e-4f;

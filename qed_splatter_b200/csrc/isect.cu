@@ -270,6 +270,7 @@ constexpr int kEmitTile = 1024;
 // larger buffers.
 __global__ void emit_boundaries_kernel(int64_t n_vis, int64_t n_isects, const int64_t* __restrict__ counts_dev, int64_t* __restrict__ clamped,
                                        const int64_t* __restrict__ cum2, int32_t* __restrict__ first_j) {
+    pdl_enter();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (counts_dev) {
         const int64_t real_vis = counts_dev[0], real_isects = counts_dev[1];
@@ -317,6 +318,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
     __shared__ __align__(16) int32_t s_oval[kEmitTile];
     __shared__ int s_nlarge;
     __shared__ int s_wsum[kEmitThreads / 32];
+    pdl_enter();
     const uint32_t vb = blockIdx.x;
     const int64_t e0 = (int64_t)vb * kEmitTile;
     if (clamped) {  // device-side counts: the grid covers the capacity, blocks behind the real count have nothing to do
@@ -477,6 +479,7 @@ constexpr int kComposePer = 4;
 __global__ void __launch_bounds__(256) compose_ids_ranges_kernel(int64_t n_host, const int64_t* __restrict__ n_dev, const uint32_t* __restrict__ tkeys,
                                                                  const int32_t* __restrict__ flat, const float* __restrict__ depths, int C, int n_tiles,
                                                                  int tile_n_bits, int64_t* __restrict__ isect_ids, int32_t* __restrict__ offsets) {
+    pdl_enter();
     const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kComposePer;
     const int64_t n = n_dev ? *n_dev : n_host;
     if (n_dev && offsets && i0 == 0) {
@@ -629,8 +632,8 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
                                                                align_up((nb + 1) * 8 + 8, 256))
                                   : nullptr;
     if (n_visible == 0) return QED_ERR_BAD_ARG;  // n_isects > 0 needs at least one visible entry (capacity when counts_dev)
-    emit_boundaries_kernel<<<(unsigned)((n_visible + 255) / 256), 256, 0, stream>>>(n_visible, n_isects, counts_dev, clamped, cum2, first_j);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(emit_boundaries_kernel, dim3((unsigned)((n_visible + 255) / 256)), dim3(256), 0, stream, n_visible, n_isects, counts_dev,
+                            clamped, cum2, first_j));
     ExactEmit ex{};
     if (exact) {
         QED_CUDA_TRY(cudaMemsetAsync(n_exact_dev, 0, 8, stream));
@@ -639,15 +642,14 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
         ex.n_out = reinterpret_cast<unsigned long long*>(n_exact_dev);
         ex.width = image_width;
         ex.height = image_height;
-        emit_sorted_kernel<true><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, clamped, N, sorted_vals, cum2, first_j,
-                                                                           reinterpret_cast<const float2*>(means2d), radii, (float)tile_size,
-                                                                           tile_width, tile_height, tile_n_bits, k0, v0, ex);
+        QED_CUDA_TRY(launch_pdl(emit_sorted_kernel<true>, dim3((unsigned)nb), dim3(kEmitThreads), 0, stream, n_visible, n_isects, clamped, N, sorted_vals,
+                                cum2, first_j, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width, tile_height,
+                                tile_n_bits, k0, v0, ex));
     } else {
-        emit_sorted_kernel<false><<<(unsigned)nb, kEmitThreads, 0, stream>>>(n_visible, n_isects, clamped, N, sorted_vals, cum2, first_j,
-                                                                            reinterpret_cast<const float2*>(means2d), radii, (float)tile_size,
-                                                                            tile_width, tile_height, tile_n_bits, k0, v0, ex);
+        QED_CUDA_TRY(launch_pdl(emit_sorted_kernel<false>, dim3((unsigned)nb), dim3(kEmitThreads), 0, stream, n_visible, n_isects, clamped, N, sorted_vals,
+                                cum2, first_j, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width, tile_height,
+                                tile_n_bits, k0, v0, ex));
     }
-    QED_LAUNCH_CHECK();
     const int64_t* n_dev = exact ? n_exact_dev : (clamped ? clamped + 1 : nullptr);
     SegCounts sc;
     if (exact) {
@@ -657,8 +659,7 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     }
     int rc = radix_sort_pairs<uint32_t>(n_isects, n_dev, k0, v0, k1, flatten_ids, k2, v2, hist, tile_n_bits + cam_bits, stream, sc);
     if (rc != QED_OK) return rc;
-    compose_ids_ranges_kernel<<<(unsigned)((n_isects + 256 * kComposePer - 1) / (256 * kComposePer)), 256, 0, stream>>>(n_isects, n_dev, k1, flatten_ids, depths, C, n_tiles,
-                                                                                   tile_n_bits, isect_ids, isect_offsets);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(compose_ids_ranges_kernel, dim3((unsigned)((n_isects + 256 * kComposePer - 1) / (256 * kComposePer))), dim3(256), 0, stream,
+                            n_isects, n_dev, k1, flatten_ids, depths, C, n_tiles, tile_n_bits, isect_ids, isect_offsets));
     return QED_OK;
 }

@@ -150,6 +150,7 @@ __device__ __forceinline__ void sh_bases_vjp(float x, float y, float z, const fl
 template <int DEG, bool VEC, bool XCH = false>
 __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const ProjBwdParams p) {
     extern __shared__ float4 smem4[];
+    pdl_enter();
     CamB* cams = reinterpret_cast<CamB*>(smem4);
     constexpr int DG = DEG < 0 ? 0 : DEG;
     using Sh = ShShapeB<DG>;
@@ -544,8 +545,7 @@ static int launch_project_bwd(const ProjBwdParams& p, cudaStream_t stream) {
     auto kern = project_bwd_kernel<DEG, VEC, XCH>;
     if (smem > 48 * 1024) QED_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (p.N + kProjBwdThreads - 1) / kProjBwdThreads;
-    kern<<<blocks, kProjBwdThreads, smem, stream>>>(p);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(kern, dim3(blocks), dim3(kProjBwdThreads), smem, stream, p));
     return QED_OK;
 }
 
@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(kShGradThreads) sh_grad_from_view_colors_kerne
                                                                                  float* __restrict__ v_sh) {
     using Sh = ShShapeB<DEG>;
     extern __shared__ float4 smem4[];
+    pdl_enter();
     float4* rows = smem4;  // [kShGradThreads][kStrideVec]
     const int n = blockIdx.x * kShGradThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -620,8 +621,8 @@ template <int DEG>
 static int launch_sh_grad(int V, int N, int K, const float* means, const float4* xch, float tag, float* v_sh, cudaStream_t stream) {
     using Sh = ShShapeB<DEG>;
     const size_t smem = (size_t)kShGradThreads * Sh::kStrideVec * 16;
-    sh_grad_from_view_colors_kernel<DEG><<<(N + kShGradThreads - 1) / kShGradThreads, kShGradThreads, smem, stream>>>(V, N, K, means, xch, tag, v_sh);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(sh_grad_from_view_colors_kernel<DEG>, dim3((N + kShGradThreads - 1) / kShGradThreads), dim3(kShGradThreads), smem, stream, V, N,
+                            K, means, xch, tag, v_sh));
     return QED_OK;
 }
 

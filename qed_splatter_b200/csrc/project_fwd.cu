@@ -131,6 +131,7 @@ struct ShShape {
 template <int DEG, bool VEC>
 __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwdParams p) {
     extern __shared__ float4 smem4[];
+    pdl_enter();
     Cam* cams = reinterpret_cast<Cam*>(smem4);
     float* shbuf = reinterpret_cast<float*>(smem4 + p.Cc * (kCamFloats / 4));
 
@@ -371,8 +372,7 @@ static int launch_project_fwd(const ProjFwdParams& p, cudaStream_t stream) {
     auto kern = project_fwd_kernel<DEG, VEC>;
     if (smem > 48 * 1024) QED_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (p.N + kProjThreads - 1) / kProjThreads;
-    kern<<<blocks, kProjThreads, smem, stream>>>(p);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(kern, dim3(blocks), dim3(kProjThreads), smem, stream, p));
     return QED_OK;
 }
 

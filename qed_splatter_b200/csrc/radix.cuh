@@ -29,6 +29,7 @@ template <typename KeyT, bool SEG>
 __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(int64_t n_host, const int64_t* n_dev, const KeyT* __restrict__ keys, int shift,
                                                                     uint32_t mask, int nblocks, uint32_t* __restrict__ hist /* [kRadix][nblocks] */, SegCounts seg) {
     __shared__ uint32_t sh[kRadix];
+    pdl_enter();
     const int64_t n = n_dev ? *n_dev : n_host;
     sh[threadIdx.x] = 0;
     __syncthreads();
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(int64_t n_h
 // grid = kRadix blocks: block d scans hist[d][0..nblocks) exclusively in place, totals[d] = digit count
 __global__ void __launch_bounds__(256) radix_scan_kernel(int nblocks, uint32_t* __restrict__ hist, uint32_t* __restrict__ totals) {
     __shared__ uint32_t sw[9];
+    pdl_enter();
     uint32_t* row = hist + (int64_t)blockIdx.x * nblocks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t carry = 0;
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_downsweep_kernel(int64_
     uint32_t* global_base = digit_start + kRadix;                // global output index of the run's first element
     uint32_t* sscan = global_base + kRadix;                      // [16]
 
+    pdl_enter();
     const int64_t n = n_dev ? *n_dev : n_host;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
@@ -260,6 +263,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads) radix_histogram_kernel(int64_t n_host, const int64_t* n_dev, const KeyT* __restrict__ keys, int passes,
                                                                       int end_bit, uint32_t* __restrict__ hist_all /* [kMaxPasses][kRadix] */) {
     __shared__ uint32_t sh[kMaxPasses][kRadix];
+    pdl_enter();
     const int64_t n = n_dev ? *n_dev : n_host;
     for (int i = threadIdx.x; i < passes * kRadix; i += kSortThreads) (&sh[0][0])[i] = 0;
     __syncthreads();
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(int64_t
     uint32_t* sscan = global_base + kRadix;  // [16]
     __shared__ uint32_t s_ticket;
 
+    pdl_enter();
     const int64_t n = n_dev ? *n_dev : n_host;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_ticket = atomicAdd(tickets + pass, 1u);
@@ -485,8 +490,7 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
         uint32_t* hist_all = reinterpret_cast<uint32_t*>(ows + status_bytes);
         uint32_t* tickets = hist_all + kMaxPasses * kRadix;
         QED_CUDA_TRY(cudaMemsetAsync(ows, 0, status_bytes + (size_t)(kMaxPasses * kRadix + kMaxPasses) * 4, stream));
-        radix_histogram_kernel<KeyT><<<nb, kSortThreads, 0, stream>>>(capacity, n_dev, keys_in, passes, end_bit, hist_all);
-        QED_LAUNCH_CHECK();
+        QED_CUDA_TRY(launch_pdl(radix_histogram_kernel<KeyT>, dim3(nb), dim3(kSortThreads), 0, stream, capacity, n_dev, keys_in, passes, end_bit, hist_all));
         auto one = radix_onesweep_kernel<KeyT>;
         QED_CUDA_TRY(cudaFuncSetAttribute(one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RadixSmem<KeyT>::kBytes));
         const KeyT* sk = keys_in;
@@ -496,9 +500,8 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
             KeyT* dk = to_out ? keys_out : tmp_keys;
             int32_t* dv = to_out ? vals_out : tmp_vals;
             const int bits = (end_bit - pass * 8) < 8 ? (end_bit - pass * 8) : 8;
-            one<<<nb, kSortThreads, RadixSmem<KeyT>::kBytes, stream>>>(capacity, n_dev, sk, sv, dk, dv, pass * 8, (1u << bits) - 1u, pass, hist_all,
-                                                                      status, tickets);
-            QED_LAUNCH_CHECK();
+            QED_CUDA_TRY(launch_pdl(one, dim3(nb), dim3(kSortThreads), RadixSmem<KeyT>::kBytes, stream, capacity, n_dev, sk, sv, dk, dv, pass * 8,
+                                    (1u << bits) - 1u, pass, hist_all, status, tickets));
             sk = dk;
             sv = dv;
         }
@@ -528,15 +531,14 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
         const SegCounts sg = pass == 0 ? seg : SegCounts();
         const int64_t* nd = (pass == 0 && seg.counts) ? nullptr : n_dev;
         if (sg.counts)
-            radix_upsweep_kernel<KeyT, true><<<nb, kSortThreads, 0, stream>>>(capacity, nd, src_k, pass * 8, pass_mask(pass), nb, hist, sg);
+            QED_CUDA_TRY(launch_pdl(radix_upsweep_kernel<KeyT, true>, dim3(nb), dim3(kSortThreads), 0, stream, capacity, nd, src_k, pass * 8,
+                                    pass_mask(pass), nb, hist, sg));
         else
-            radix_upsweep_kernel<KeyT, false><<<nb, kSortThreads, 0, stream>>>(capacity, nd, src_k, pass * 8, pass_mask(pass), nb, hist, sg);
-        QED_LAUNCH_CHECK();
-        radix_scan_kernel<<<kRadix, 256, 0, stream>>>(nb, hist, totals);
-        QED_LAUNCH_CHECK();
-        (sg.counts ? down_seg : down)<<<nb, kSortThreads, RadixSmem<KeyT>::kBytes, stream>>>(capacity, nd, src_k, src_v, dst_k, dst_v, pass * 8,
-                                                                                          pass_mask(pass), nb, hist, totals, nullptr, 0, 0u, sg);
-        QED_LAUNCH_CHECK();
+            QED_CUDA_TRY(launch_pdl(radix_upsweep_kernel<KeyT, false>, dim3(nb), dim3(kSortThreads), 0, stream, capacity, nd, src_k, pass * 8,
+                                    pass_mask(pass), nb, hist, sg));
+        QED_CUDA_TRY(launch_pdl(radix_scan_kernel, dim3(kRadix), dim3(256), 0, stream, nb, hist, totals));
+        QED_CUDA_TRY(launch_pdl(sg.counts ? down_seg : down, dim3(nb), dim3(kSortThreads), RadixSmem<KeyT>::kBytes, stream, capacity, nd, src_k, src_v,
+                                dst_k, dst_v, pass * 8, pass_mask(pass), nb, hist, totals, (uint32_t*)nullptr, 0, 0u, sg));
         src_k = dst_k;
         src_v = dst_v;
     }

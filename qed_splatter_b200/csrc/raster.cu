@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 14) raster_fwd_ws_kernel(c
     using S = Shape<4>;
     __shared__ WarpStream wss[S::kWarps];
     StatCounters<STATS> st;
+    pdl_enter();
     const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStream& ws = wss[warp];
@@ -936,6 +937,7 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(c
     __shared__ WarpStream wss[S::kWarps];
     __shared__ GradTranspose reds[S::kWarps];
     StatCounters<STATS> st;
+    pdl_enter();
     const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStream& ws = wss[warp];
@@ -1088,11 +1090,11 @@ static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
     const bool cull = g_raster_cull != 0, stats = p.counters != nullptr;
     if (!BWD && PX == 4 && g_raster_packed) {
         if (stats) {
-            if (cull) raster_fwd_ws_kernel<D, true, true><<<grid, T, 0, stream>>>(p);
-            else raster_fwd_ws_kernel<D, false, true><<<grid, T, 0, stream>>>(p);
+            if (cull) (void)launch_pdl(raster_fwd_ws_kernel<D, true, true>, grid, dim3(T), 0, stream, p);
+            else (void)launch_pdl(raster_fwd_ws_kernel<D, false, true>, grid, dim3(T), 0, stream, p);
         } else {
-            if (cull) raster_fwd_ws_kernel<D, true, false><<<grid, T, 0, stream>>>(p);
-            else raster_fwd_ws_kernel<D, false, false><<<grid, T, 0, stream>>>(p);
+            if (cull) (void)launch_pdl(raster_fwd_ws_kernel<D, true, false>, grid, dim3(T), 0, stream, p);
+            else (void)launch_pdl(raster_fwd_ws_kernel<D, false, false>, grid, dim3(T), 0, stream, p);
         }
     } else if (!BWD) {
         if (stats) {
@@ -1104,11 +1106,11 @@ static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
         }
     } else if (PX == 4 && g_raster_packed) {
         if (stats) {
-            if (cull) raster_bwd_ws_kernel<D, true, true><<<grid, T, 0, stream>>>(p);
-            else raster_bwd_ws_kernel<D, false, true><<<grid, T, 0, stream>>>(p);
+            if (cull) (void)launch_pdl(raster_bwd_ws_kernel<D, true, true>, grid, dim3(T), 0, stream, p);
+            else (void)launch_pdl(raster_bwd_ws_kernel<D, false, true>, grid, dim3(T), 0, stream, p);
         } else {
-            if (cull) raster_bwd_ws_kernel<D, true, false><<<grid, T, 0, stream>>>(p);
-            else raster_bwd_ws_kernel<D, false, false><<<grid, T, 0, stream>>>(p);
+            if (cull) (void)launch_pdl(raster_bwd_ws_kernel<D, true, false>, grid, dim3(T), 0, stream, p);
+            else (void)launch_pdl(raster_bwd_ws_kernel<D, false, false>, grid, dim3(T), 0, stream, p);
         }
     } else {
         if (stats) {

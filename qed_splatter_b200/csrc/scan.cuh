@@ -55,6 +55,7 @@ struct ScanGather {  // in[index[i]]
 template <typename F>
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(int64_t n_host, const int64_t* n_dev, F f, int64_t* __restrict__ block_sums) {
     __shared__ int64_t sw[kScanThreads / 32 + 1];
+    pdl_enter();
     const int64_t n = n_dev ? *n_dev : n_host;
     int64_t base = (int64_t)blockIdx.x * kScanTile;
     int64_t s = 0;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(int64_t n_hos
 // single block: exclusive scan of block sums in place; writes the grand total
 __global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int64_t nb, int64_t* __restrict__ block_sums, int64_t* __restrict__ total_dev) {
     __shared__ int64_t sw[kScanThreads / 32 + 1];
+    pdl_enter();
     int64_t carry = 0;
     for (int64_t base = 0; base < nb; base += kScanThreads) {
         int64_t i = base + threadIdx.x;
@@ -95,6 +97,7 @@ template <typename F, typename Sink>
 __global__ void __launch_bounds__(kScanThreads) scan_final_kernel(int64_t n_host, const int64_t* n_dev, F f, const int64_t* __restrict__ block_sums,
                                                                  Sink sink) {
     __shared__ int64_t sw[kScanThreads / 32 + 1];
+    pdl_enter();
     const int64_t n = n_dev ? *n_dev : n_host;
     // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems) of the tile
     int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
@@ -128,12 +131,9 @@ inline int scan_inclusive_to(int64_t capacity, const int64_t* n_dev, F f, Sink s
     int64_t nb = (capacity + kScanTile - 1) / kScanTile;
     if (nb == 0) nb = 1;
     int64_t* sums = reinterpret_cast<int64_t*>(workspace);
-    scan_reduce_kernel<F><<<(unsigned)nb, kScanThreads, 0, stream>>>(capacity, n_dev, f, sums);
-    QED_LAUNCH_CHECK();
-    scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(nb, sums, total_dev);
-    QED_LAUNCH_CHECK();
-    scan_final_kernel<F, Sink><<<(unsigned)nb, kScanThreads, 0, stream>>>(capacity, n_dev, f, sums, sink);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(scan_reduce_kernel<F>, dim3((unsigned)nb), dim3(kScanThreads), 0, stream, capacity, n_dev, f, sums));
+    QED_CUDA_TRY(launch_pdl(scan_sums_kernel, dim3(1), dim3(kScanThreads), 0, stream, nb, sums, total_dev));
+    QED_CUDA_TRY(launch_pdl(scan_final_kernel<F, Sink>, dim3((unsigned)nb), dim3(kScanThreads), 0, stream, capacity, n_dev, f, sums, sink));
     return QED_OK;
 }
 

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_fwd_kernel(int W, int H, co
     float(*sy)[kSsimIn + 1] = sx + kSsimIn;                                                   // [42][43]
     float(*h)[kSsimIn][kSsimTile + 1] = reinterpret_cast<float(*)[kSsimIn][kSsimTile + 1]>(&sy[kSsimIn][0]);  // [5][42][33]
     __shared__ double red[kSsimThreads / 32];
+    pdl_enter();
     const int OW = W - kHalo, OH = H - kHalo;
     const int cam = blockIdx.z / 3, ch = blockIdx.z % 3;
     const int ox0 = blockIdx.x * kSsimTile, oy0 = blockIdx.y * kSsimTile;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(kSsimThreads) ssim_bwd_kernel(int W, int H, co
     extern __shared__ float ssim_smem[];
     float(*sd)[kSsimIn][kSsimIn + 1] = reinterpret_cast<float(*)[kSsimIn][kSsimIn + 1]>(ssim_smem);                      // [3][42][43]
     float(*h)[kSsimIn][kSsimTile + 1] = reinterpret_cast<float(*)[kSsimIn][kSsimTile + 1]>(&sd[3][0][0]);               // [3][42][33]
+    pdl_enter();
     const int OW = W - kHalo, OH = H - kHalo;
     const int cam = blockIdx.z / 3, ch = blockIdx.z % 3;
     const int x0 = blockIdx.x * kSsimTile, y0 = blockIdx.y * kSsimTile;
@@ -255,10 +257,8 @@ int qed_ssim_launch(int C, int W, int H, const float* pred, qed::GtImage gt, qed
     QED_CUDA_TRY(cudaFuncSetAttribute(ssim_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimFwdSmem));
     QED_CUDA_TRY(cudaFuncSetAttribute(ssim_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimBwdSmem));
     dim3 g1((OW + kSsimTile - 1) / kSsimTile, (OH + kSsimTile - 1) / kSsimTile, C * 3);
-    ssim_fwd_kernel<<<g1, kSsimThreads, kSsimFwdSmem, stream>>>(W, H, pred, gt, mask, win, dmaps, stats);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(ssim_fwd_kernel, g1, dim3(kSsimThreads), kSsimFwdSmem, stream, W, H, pred, gt, mask, win, dmaps, stats));
     dim3 g2((W + kSsimTile - 1) / kSsimTile, (H + kSsimTile - 1) / kSsimTile, C * 3);
-    ssim_bwd_kernel<<<g2, kSsimThreads, kSsimBwdSmem, stream>>>(W, H, pred, gt, mask, win, dmaps, scale, v_pred);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(ssim_bwd_kernel, g2, dim3(kSsimThreads), kSsimBwdSmem, stream, W, H, pred, gt, mask, win, dmaps, scale, v_pred));
     return QED_OK;
 }

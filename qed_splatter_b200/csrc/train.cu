@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, co
                                                                  const float* __restrict__ gt_depth, const PixelMask mask, double* __restrict__ stats) {
     __shared__ float s_max[kLossThreads / 32];
     __shared__ int s_na[kLossThreads / 32], s_nb[kLossThreads / 32];
+    pdl_enter();
     const int cam = blockIdx.y;
     float maxd = 0.0f;
     int na = 0, nb = 0;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
                                                                 const float* __restrict__ bg, float rgb_weight, float depth_lambda, float grad_scale,
                                                                 double* __restrict__ stats, float4* __restrict__ v_render, float* __restrict__ v_alphas,
                                                                 float* __restrict__ pred_rgb, const float* __restrict__ v_rgb_extra) {
+    pdl_enter();
     const int cam = blockIdx.y;
     const float maxd = __int_as_float(*reinterpret_cast<const int*>(stats + cam * 8 + 3));
     const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
 
 __global__ void loss_finalize_kernel(int C, int64_t HW, float rgb_weight, float depth_lambda, float ssim_lambda, double ssim_count,
                                      double* __restrict__ stats, float* __restrict__ loss) {
+    pdl_enter();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double lr = 0.0, ld = 0.0, ls = 0.0;
     for (int c = 0; c < C; ++c) {
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(256) adam_arena_kernel(int64_t n, float* __res
     __shared__ int64_t s_ends[16];
     __shared__ float s_lr[16], s_lr_alt[16];
     __shared__ int s_period[16], s_split[16];
+    pdl_enter();
     if (threadIdx.x < G) {
         s_ends[threadIdx.x] = group_ends[threadIdx.x];
         s_lr[threadIdx.x] = lr_by_group[threadIdx.x];
@@ -258,6 +262,7 @@ __global__ void __launch_bounds__(256) adam_arena_kernel(int64_t n, float* __res
 __global__ void strategy_update_kernel(int C, int N, const float4* __restrict__ packed, int use_absgrad, const int32_t* __restrict__ radii,
                                        float sx, float sy, float inv_max_wh, float* __restrict__ grad2d, float* __restrict__ count,
                                        float* __restrict__ radii_max) {
+    pdl_enter();
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float g = 0.0f, cnt = 0.0f, rm = radii_max ? radii_max[n] : 0.0f;
@@ -317,24 +322,23 @@ extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* rende
     QED_CUDA_TRY(cudaMemsetAsync(stats_dev, 0, (size_t)C * 8 * sizeof(double), stream));
     const int bx = (int)((HW + kLossThreads * kLossUnroll - 1) / (kLossThreads * kLossUnroll));
     dim3 grid(bx, C);
-    loss_stats_kernel<<<grid, kLossThreads, 0, stream>>>(HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, mask, stats_dev);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(loss_stats_kernel, grid, dim3(kLossThreads), 0, stream, HW, reinterpret_cast<const float4*>(render), alphas, gt_depth, mask,
+                            stats_dev));
     const double ssim_count = (double)(width - 10) * (double)(height - 10) * 3.0;
     if (use_ssim) {
-        loss_grad_kernel<true><<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, mask, bg,
-                                                                  rgb_weight, depth_lambda, grad_scale, stats_dev, nullptr, nullptr, pred_rgb, nullptr);
-        QED_LAUNCH_CHECK();
+        QED_CUDA_TRY(launch_pdl(loss_grad_kernel<true>, grid, dim3(kLossThreads), 0, stream, HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb,
+                                gt_depth, mask, bg, rgb_weight, depth_lambda, grad_scale, stats_dev, (float4*)nullptr, (float*)nullptr, pred_rgb,
+                                (const float*)nullptr));
         // loss term = ssim_lambda * (1 - mean(map)) per camera, mean over cameras
         const float scale = -ssim_lambda * grad_scale / ((float)C * (float)ssim_count);
         int rc = qed_ssim_launch(C, width, height, pred_rgb, gt_rgb, mask, dmaps, stats_dev, scale, v_ssim, stream);
         if (rc != QED_OK) return rc;
     }
-    loss_grad_kernel<false><<<grid, kLossThreads, 0, stream>>>(HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb, gt_depth, mask, bg,
-                                                               rgb_weight, depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render),
-                                                               v_alphas, nullptr, v_ssim);
-    QED_LAUNCH_CHECK();
-    loss_finalize_kernel<<<1, 32, 0, stream>>>(C, HW, rgb_weight, depth_lambda, use_ssim ? ssim_lambda : 0.0f, ssim_count, stats_dev, loss_dev);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(loss_grad_kernel<false>, grid, dim3(kLossThreads), 0, stream, HW, C, reinterpret_cast<const float4*>(render), alphas, gt_rgb,
+                            gt_depth, mask, bg, rgb_weight, depth_lambda, grad_scale, stats_dev, reinterpret_cast<float4*>(v_render), v_alphas,
+                            (float*)nullptr, (const float*)v_ssim));
+    QED_CUDA_TRY(launch_pdl(loss_finalize_kernel, dim3(1), dim3(32), 0, stream, C, HW, rgb_weight, depth_lambda, use_ssim ? ssim_lambda : 0.0f, ssim_count,
+                            stats_dev, loss_dev));
     return QED_OK;
 }
 
@@ -353,15 +357,14 @@ extern "C" int qed_adam_arena(int64_t n, float* param, const float* grad, float*
     const bool vec = (n % 4 == 0) && al16(param) && al16(grad) && al16(exp_avg) && al16(exp_avg_sq);
     if (vec) {
         const int64_t threads = (n / 4 + 1) / 2;  // two float4 per thread
-        adam_arena_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group,
-                                                                                     lr_alt_by_group, group_period, group_split, (float)beta1,
-                                                                                     (float)beta2, (float)eps, inv_bias1, inv_bias2_sqrt);
+        QED_CUDA_TRY(launch_pdl(adam_arena_kernel<true>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, n, param, grad, exp_avg, exp_avg_sq, G,
+                                group_ends, lr_by_group, lr_alt_by_group, group_period, group_split, (float)beta1, (float)beta2, (float)eps,
+                                inv_bias1, inv_bias2_sqrt));
     } else {
-        adam_arena_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, param, grad, exp_avg, exp_avg_sq, G, group_ends, lr_by_group,
-                                                                                lr_alt_by_group, group_period, group_split, (float)beta1,
-                                                                                (float)beta2, (float)eps, inv_bias1, inv_bias2_sqrt);
+        QED_CUDA_TRY(launch_pdl(adam_arena_kernel<false>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, n, param, grad, exp_avg, exp_avg_sq, G,
+                                group_ends, lr_by_group, lr_alt_by_group, group_period, group_split, (float)beta1, (float)beta2, (float)eps,
+                                inv_bias1, inv_bias2_sqrt));
     }
-    QED_LAUNCH_CHECK();
     return QED_OK;
 }
 
@@ -375,9 +378,8 @@ extern "C" int qed_strategy_update(int C, int N, const float* packed_grads, int 
     if (n_cameras <= 0) n_cameras = C;
     const float sx = (float)width / 2.0f * (float)n_cameras, sy = (float)height / 2.0f * (float)n_cameras;
     const float inv = 1.0f / (float)(width > height ? width : height);
-    strategy_update_kernel<<<(N + 255) / 256, 256, 0, stream>>>(C, N, reinterpret_cast<const float4*>(packed_grads), use_absgrad, radii, sx, sy, inv,
-                                                               grad2d, count, radii_max);
-    QED_LAUNCH_CHECK();
+    QED_CUDA_TRY(launch_pdl(strategy_update_kernel, dim3((N + 255) / 256), dim3(256), 0, stream, C, N, reinterpret_cast<const float4*>(packed_grads),
+                            use_absgrad, radii, sx, sy, inv, grad2d, count, radii_max));
     return QED_OK;
 }
 
