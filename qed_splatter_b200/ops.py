@@ -243,13 +243,25 @@ def sort_pairs(keys: Tensor, vals: Tensor, end_bit: int = 64, impl: Optional[str
     return keys_out, vals_out
 
 
+# Sizing hints for `isect_tiles_exact(defer=True)`: largest intersection count seen per (device, C, N, width, height), + 25 %.
+# Only buffer SIZES come from here; a list that does not fit is detected and rebuilt, results never depend on the hint.
+_CAPACITY_HINT = {}
+
+
 @torch.no_grad()
 def isect_tiles_exact(means2d: Tensor, radii: Tensor, depths: Tensor, geom: Tensor, width: int, height: int, tile_size: int,
-                      tile_width: int, tile_height: int, tiles_per_gauss: Tensor):
+                      tile_width: int, tile_height: int, tiles_per_gauss: Tensor, defer: bool = False):
     """EXACT tile lists for the compositor (not gsplat's `info` lists): every (Gaussian, tile) candidate of gsplat's
     bounding-box lists that cannot reach alpha = 1/255 at a pixel centre of the tile is dropped before the tile sort
-    (DESIGN.md section 5).  -> flatten_ids[M] i32 (M = gsplat's count; only the first n_exact entries are filled),
-    isect_offsets[C*th*tw + 1] i32 (last element = n_exact = end of the last range), n_exact[1] i64 on the device."""
+    (DESIGN.md section 5).  -> flatten_ids[M] i32 (M >= gsplat's count; only the first n_exact entries are filled),
+    isect_offsets[C*th*tw + 1] i32 (last element = n_exact = end of the last range), n_exact[1] i64 on the device,
+    resolve.
+
+    The list sizes are only known on the device.  defer=False: the host reads them between the two phases (the one
+    host sync gsplat has too) and `resolve` is None.  defer=True: when an earlier call with the same shapes left a size
+    hint, the lists are built into buffers of that capacity without waiting, and `resolve()` -- call it AFTER queueing
+    the work that consumes the lists, so the device never idles on the read -- returns False if they did not fit (the
+    device then built empty lists): build them again with defer=False."""
     lib = _lib.load()
     _lib.require_cuda(means2d, radii, depths, geom)
     means2d, depths = _f32c(means2d.detach()), _f32c(depths.detach())
@@ -259,17 +271,35 @@ def isect_tiles_exact(means2d: Tensor, radii: Tensor, depths: Tensor, geom: Tens
     pws_bytes = lib.qed_isect_prepare_workspace_bytes(C * N)
     pws = torch.empty(pws_bytes, dtype=torch.uint8, device=dev)
     counts = torch.zeros(3, dtype=torch.int64, device=dev)
-    check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles_per_gauss), ptr(pws), pws_bytes, ptr(counts), None, stream),
+    key = (dev.index, C, N, int(width), int(height))
+    cap = _CAPACITY_HINT.get(key, 0) if defer else 0
+    deferred = cap > 0 and C * N > 0
+    counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True) if deferred else None
+    check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles_per_gauss), ptr(pws), pws_bytes, ptr(counts), ptr(counts_host), stream),
           "qed_isect_prepare")
-    n_visible, n_isects, _ = (int(v) for v in counts.tolist())  # the one host sync of the forward (gsplat has the same one)
+    resolve = None
+    if deferred:
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        n_visible, n_isects = C * N, cap  # capacities; the real counts stay on the device
+
+        def resolve() -> bool:
+            ready.synchronize()
+            real = int(counts_host[1])
+            _CAPACITY_HINT[key] = max(_CAPACITY_HINT.get(key, 0), real + real // 4 + 4096)
+            return real <= cap
+    else:
+        n_visible, n_isects, _ = (int(v) for v in counts.tolist())  # the one host sync of the forward (gsplat has the same one)
+        if defer:
+            _CAPACITY_HINT[key] = max(_CAPACITY_HINT.get(key, 0), n_isects + n_isects // 4 + 4096)
     flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
     offsets = torch.empty(C * tile_height * tile_width + 1, dtype=torch.int32, device=dev)
     fws_bytes = lib.qed_isect_fill_workspace_bytes(n_isects)
     fws = torch.empty(fws_bytes, dtype=torch.uint8, device=dev)
     check(lib.qed_isect_fill(C, N, n_visible, n_isects, ptr(means2d), ptr(radii), ptr(depths), ptr(geom), width, height, tile_size,
-                             tile_width, tile_height, ptr(pws), ptr(fws), fws_bytes, None, None, ptr(flatten_ids) if n_isects else None,
-                             ptr(offsets), ptr(counts[2:]), stream), "qed_isect_fill")
-    return flatten_ids, offsets, counts[2:]
+                             tile_width, tile_height, ptr(pws), ptr(fws), fws_bytes, ptr(counts) if deferred else None, None,
+                             ptr(flatten_ids) if n_isects else None, ptr(offsets), ptr(counts[2:]), stream), "qed_isect_fill")
+    return flatten_ids, offsets, counts[2:], resolve
 
 
 @torch.no_grad()

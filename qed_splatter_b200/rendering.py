@@ -141,8 +141,10 @@ def rasterization(
     tile_width, tile_height = ops.tile_grid(width, height, tile_size)
     # the compositor's lists (exact: about half of gsplat's entries, no pixel changes); gsplat's own lists are built
     # on demand by LazyInfo from the same projection outputs
-    flatten_ids, isect_offsets, _ = ops.isect_tiles_exact(means2d, radii, depths, geom, width, height, tile_size, tile_width, tile_height,
-                                                          tiles_per_gauss)
+    # (sizes of the lists live on the device: from the second call with these shapes on they are read only after the
+    # compositor has been queued -- `resolve` -- so the device does not idle on the host)
+    flatten_ids, isect_offsets, _, resolve = ops.isect_tiles_exact(means2d, radii, depths, geom, width, height, tile_size, tile_width,
+                                                                   tile_height, tiles_per_gauss, defer=True)
 
     def gsplat_lists(m=means2d.detach(), r=radii, d=depths.detach(), t=tiles_per_gauss):
         return ops.isect_tiles(m, r, d, tile_size, tile_width, tile_height, tiles_per_gauss=t, return_offsets=True)[1:]
@@ -159,6 +161,14 @@ def rasterization(
     render_colors, render_alphas = ops.rasterize_to_pixels(
         means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
         absgrad=absgrad, geom=geom, normalize_last=normalize)
+    if resolve is not None and not resolve():
+        # the lists did not fit the buffers sized from earlier calls (the device built empty ones): rebuild with the sizes
+        # now known and composite again (rare: first frames of a new viewpoint / after densification)
+        flatten_ids, isect_offsets, _, _ = ops.isect_tiles_exact(means2d, radii, depths, geom, width, height, tile_size, tile_width,
+                                                                 tile_height, tiles_per_gauss, defer=False)
+        render_colors, render_alphas = ops.rasterize_to_pixels(
+            means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
+            absgrad=absgrad, geom=geom, normalize_last=normalize)
 
     info = LazyInfo({
         "camera_ids": None,

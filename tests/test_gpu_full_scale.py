@@ -98,7 +98,7 @@ def test_sampled_tiles_forward_backward_match_oracle_at_full_size(cuda, name, li
     tw, th = ops.tile_grid(W, H, TILE)
     n_tiles = tw * th
     if lists == "exact":
-        flat, offsets, n_exact = ops.isect_tiles_exact(g["means2d"], g["radii"], g["depths"], g["geom"], W, H, TILE, tw, th, g["tiles"])
+        flat, offsets, n_exact, _ = ops.isect_tiles_exact(g["means2d"], g["radii"], g["depths"], g["geom"], W, H, TILE, tw, th, g["tiles"])
         bounds = offsets.cpu().long()
         assert int(bounds[-1]) == int(n_exact.item())
     else:

@@ -139,3 +139,34 @@ def test_advisor_guards(cuda):
         fs.step(a["means"], a["quats"], a["scales"], a["opacities"], a["colors"], a["viewmats"], a["Ks"], 48, 48, 3, gt_rgb, s.gt_depth, bg[0])
     with pytest.raises(TypeError):
         fs.step(a["means"], a["quats"], a["scales"], a["opacities"], a["colors"], a["viewmats"], a["Ks"], 48, 48, 3, gt_rgb, gt_depth, bg[0].double())
+
+
+def test_rasterization_deferred_list_sizes_and_overflow(cuda):
+    """rasterization() sizes its tile-list buffers from earlier calls with the same shapes and reads the real sizes only
+    after the compositor is queued; a frame whose lists do not fit is rebuilt.  Results never depend on the hint."""
+    from qed_splatter_b200 import ops
+
+    small = scene_s0(N=2500, C=1, size=80)
+    big = scene_s0(N=2500, C=1, size=80)
+    big.scales = big.scales * 4.0
+    ops._CAPACITY_HINT.clear()
+    outs = {}
+    for name, s in (("small_first", small), ("small_again", small), ("big_overflow", big), ("big_again", big)):
+        a = scene_args(s, cuda)
+        a["means"].requires_grad_(True)
+        r, al, info = rasterization(**a, width=80, height=80, sh_degree=3, render_mode="RGB+D", absgrad=True)
+        (r.sum() + al.sum()).backward()
+        outs[name] = (r.detach().clone(), al.detach().clone(), a["means"].grad.clone(), info["isect_ids"].numel())
+    n_small, n_big = outs["small_first"][3], outs["big_overflow"][3]
+    assert len(ops._CAPACITY_HINT) == 1 and n_big > n_small + n_small // 4 + 4096  # did not fit the capacity learnt from `small`
+    ops._CAPACITY_HINT.clear()
+    for name, s in (("small_again", small), ("big_overflow", big)):  # fresh hint -> synchronous path: the reference result
+        a = scene_args(s, cuda)
+        a["means"].requires_grad_(True)
+        r, al, _ = rasterization(**a, width=80, height=80, sh_degree=3, render_mode="RGB+D", absgrad=True)
+        (r.sum() + al.sum()).backward()
+        first = "small_first" if name == "small_again" else "big_again"
+        for got in (outs[name], outs[first]):
+            assert torch.equal(got[0], r) and torch.equal(got[1], al)
+            scale = float(a["means"].grad.abs().mean()) + 1e-20
+            assert_close_frac(got[2], a["means"].grad, 1e-4, 1e-5 * scale, 1e-3, f"{name} v_means")
