@@ -3,7 +3,10 @@
 
 Forward only (projection -> intersections -> compositing) through the fused pipeline, CUDA-event timed,
 reported per stage with the work counters that make throughput meaningful (n_visible, n_isects, Gaussians
-composited per pixel).  One JSON line per (N, resolution, mode) on stdout; `--md` prints a markdown table.
+composited per pixel) and, per point, the fraction of the roofline that bounds each stage: projection vs the measured HBM
+copy peak (MEASURED_PEAKS.json) on its algorithmic bytes, compositing vs the FP32 peak at the max SM
+clock on 30 FLOP per composited (pixel, Gaussian) pair.  One JSON line per (N, resolution, mode) on stdout; `--md` prints a
+markdown table.
 """
 import argparse
 import json
@@ -30,6 +33,12 @@ def main():
     ap.add_argument("--md", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     rows = []
     for n in (int(x) for x in a.gaussians.split(",")):
         base = scene_s1(N=n, targets=False)
@@ -58,21 +67,32 @@ def main():
                     acc[name] = x.elapsed_time(y)
                 fs.marks = None
                 f = fs._fwd
+                n_vis = int((f["radii"] > 0).sum())
+                pairs = fs.count_pairs(which=("fwd",)).get("fwd_pairs_contributing", 0)
+                D = f["D"]
+                flop_pair = 22.0 + 2.0 * D  # 30 FLOP + 1 ex2 per pair at D = 4 (8 of them the D fused multiply-adds)
+                proj_bytes = n * 44.0 + n_vis * ((192.0 if f["n_color"] else 0.0) + 100.0)
+                t_proj, t_ras = acc.get("project_fwd"), acc.get("raster_fwd")
                 row = {"gaussians": n, "res": res, "width": W, "height": H, "mode": mode, "ms": ms, "mpix_s": W * H / ms / 1e3,
-                       "n_visible": int((f["radii"] > 0).sum()), "n_isects": f["M"], "alpha_mean": float(f["alphas"].mean()),
+                       "n_visible": n_vis, "n_isects": f.get("n_isects_real", f["M"]), "n_isects_exact": fs.n_isects_exact(),
+                       "alpha_mean": float(f["alphas"].mean()), "composited_per_pixel": pairs / float(W * H),
+                       "project_hbm_frac": (proj_bytes / (t_proj * 1e-3) / 1e9 / hbm_peak) if t_proj else None,
+                       "raster_fp32_frac": (pairs * flop_pair / (t_ras * 1e-3) / 1e12 / fp32_peak) if t_ras else None,
                        "stage_ms": {k: round(v, 4) for k, v in acc.items()}}
                 rows.append(row)
                 print(json.dumps(row), flush=True)
         del g
         torch.cuda.empty_cache()
     if a.md:
-        print("\n| Gaussians | res | mode | ms | Mpix/s | visible | isects | project | isect | composite |")
-        print("|---|---|---|---|---|---|---|---|---|---|")
+        print(f"\nroofline denominators: HBM {hbm_peak:.0f} GB/s (measured copy), FP32 {fp32_peak:.1f} TFLOP/s (148 SM x 128 lanes x 2 x max SM clock)")
+        print("\n| Gaussians | res | mode | ms | Mpix/s | visible | isects (exact) | composited/pixel | project ms (of HBM) | isect ms | composite ms (of FP32) |")
+        print("|---|---|---|---|---|---|---|---|---|---|---|")
         for r in rows:
             s = r["stage_ms"]
             isect = s.get("isect_prepare", 0) + s.get("sync", 0) + s.get("isect_fill", 0)
-            print(f"| {r['gaussians'] / 1e6:g}M | {r['res']} | {r['mode']} | {r['ms']:.3f} | {r['mpix_s']:.0f} | {r['n_visible']} | {r['n_isects']} | "
-                  f"{s.get('project_fwd', 0):.3f} | {isect:.3f} | {s.get('raster_fwd', 0):.3f} |")
+            print(f"| {r['gaussians'] / 1e6:g}M | {r['res']} | {r['mode']} | {r['ms']:.3f} | {r['mpix_s']:.0f} | {r['n_visible']} | {r['n_isects']} ({r['n_isects_exact']}) | "
+                  f"{r['composited_per_pixel']:.1f} | {s.get('project_fwd', 0):.3f} ({r['project_hbm_frac'] or 0:.2f}) | {isect:.3f} | "
+                  f"{s.get('raster_fwd', 0):.3f} ({r['raster_fp32_frac'] or 0:.2f}) |")
 
 
 if __name__ == "__main__":

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--refine-every", type=int, default=100)
     ap.add_argument("--start-step", type=int, default=600, help="schedule position (SH degree / densify windows)")
+    ap.add_argument("--comm", default="auto", choices=["auto", "exchange", "nccl"], help="TrainConfig.comm (N > 1): this library's NVLink path or NCCL")
     ap.add_argument("--comm-chunks", type=int, default=None, help="override TrainConfig.comm_chunks")
     ap.add_argument("--no-chunk-bwd", action="store_true")
     a = ap.parse_args()
@@ -40,7 +41,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     make = scene_s2 if a.scene == "s2" else scene_s3
     s = make(N=a.gaussians, C=1, view_offset=rank, total_views=world)
-    cfg = TrainConfig(refine_every=a.refine_every, render_mode="RGB+D")
+    cfg = TrainConfig(refine_every=a.refine_every, render_mode="RGB+D", comm=a.comm)
     if a.comm_chunks is not None:
         cfg.comm_chunks = a.comm_chunks
     cfg.chunk_project_bwd = not a.no_chunk_bwd
@@ -79,11 +80,19 @@ def main():
         dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
         assert int(nmin) == int(nmax), "replicas diverged"
     ms = float(t) / a.steps
+    identical = None
+    if world > 1:  # replicas hold bit-identical parameters (also after the refine steps inside the window)
+        p_ = tr.arena.param
+        chk = torch.stack([p_.double().sum(), p_.view(torch.int32).sum().double(), p_[::101].double().abs().sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        identical = all(torch.equal(allc[0], c_) for c_ in allc)
     if rank == 0:
         print(json.dumps({"scene": a.scene, "gaussians_start": a.gaussians, "gaussians_end": tr.arena.N, "n_gpus": world, "steps": a.steps,
                           "ms_per_step": ms, "train_iters_per_s": 1e3 / ms, "views_per_s": world * 1e3 / ms,
-                          "mpix_per_s": world * W * H / ms / 1e3, "comm_chunks": cfg.comm_chunks, "width": W, "height": H, "refines": refines[:4], "loss": [float(x) for x in loss.tolist()],
-                          "n_isects_last": tr._fused._fwd["M"]}))
+                          "mpix_per_s": world * W * H / ms / 1e3, "comm": tr.comm, "comm_chunks": cfg.comm_chunks if tr.comm == "nccl" else None,
+                          "replicas_bit_identical": identical, "n_refines_in_window": len(refines), "overflow_repeats": tr._fused.overflow_repeats, "width": W, "height": H, "refines": refines[:4], "loss": [float(x) for x in loss.tolist()],
+                          "n_isects_last": tr._fused._fwd.get("n_isects_real", tr._fused._fwd["M"])}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -87,24 +87,39 @@ class ViewShardedGradients:
 
     No NCCL call, no host synchronisation; collective: every rank makes the same calls in the same order."""
 
-    def __init__(self, N: int, views_per_rank: int, device, group=None, force_peer_path: bool = False):
-        from .trainer import GROUPS, GaussianArena
+    def __init__(self, N: int, views_per_rank: int, device, group=None, force_peer_path: bool = False, headroom: float = 0.0):
+        """`headroom`: allocate for N * (1 + headroom) Gaussians so that `resize()` after a densification step usually
+        needs no new symmetric allocation (a collective)."""
+        from .trainer import GaussianArena
 
-        self.N, self.views_per_rank = int(N), int(views_per_rank)
-        self.offsets, total = GaussianArena.layout(self.N)
+        self.views_per_rank = int(views_per_rank)
+        self.capacity = int(N * (1.0 + headroom)) + 4
+        _, total = GaussianArena.layout(self.capacity)
         self.arena = SymmetricArena(total, device, group, force_peer_path=force_peer_path)
         self.rank, self.world = self.arena.rank, self.arena.world
         self.slots = self.world * self.views_per_rank
-        n_xch = (self.slots * self.N + self.slots) * 4
+        n_xch = (self.slots * self.capacity + self.slots) * 4
         self.xch = [SymmetricArena(n_xch, device, group, force_peer_path=force_peer_path) for _ in range(2)]
         self.step = 0
-        self._groups = GROUPS
         self._side = torch.cuda.Stream(device=self.arena.device)
         self._fork, self._join = torch.cuda.Event(), torch.cuda.Event()
+        self.resize(N)
+
+    def resize(self, N: int) -> bool:
+        """Use the buffers for N Gaussians (N <= capacity; same N on every rank).  False = does not fit: build a new object."""
+        from .trainer import GaussianArena
+
+        if N > self.capacity:
+            return False
+        if getattr(self, "N", None) not in (None, int(N)):
+            self.arena.buf.zero_()  # the group boundaries move: padding floats between the groups must read as zero gradients
+        self.N = int(N)
+        self.offsets, self.total = GaussianArena.layout(self.N)
+        return True
 
     @property
     def grad(self) -> torch.Tensor:
-        return self.arena.buf
+        return self.arena.buf[:self.total]
 
     def views(self):
         N = self.N
@@ -135,7 +150,7 @@ class ViewShardedGradients:
         self._fork.record(main)
         self._side.wait_event(self._fork)
         _lib.check(lib.qed_sh_grad_from_view_colors(self.slots, self.N, K, deg, _lib.ptr(means), _lib.ptr(x.buf), self._tag(),
-                                                    _lib.ptr(self.arena.buf[sh0:]), ctypes.c_void_p(self._side.cuda_stream)),
+                                                    _lib.ptr(self.arena.buf[sh0:self.total]), ctypes.c_void_p(self._side.cuda_stream)),
                    "qed_sh_grad_from_view_colors")
         self._join.record(self._side)
         self.arena.all_reduce_(0, sh0)  # means | quats | scales | opacities (+ padding, zero)

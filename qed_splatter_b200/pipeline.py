@@ -401,15 +401,15 @@ class FusedSplatStep:
         return 1 + isect + 1 + 3 + 1 + 1
 
     @torch.no_grad()
-    def count_pairs(self) -> Dict[str, int]:
-        """Re-run the two compositing kernels of the last step() with the instrumented (STATS) variants and
-        return the work counters used for the FP32 roofline."""
+    def count_pairs(self, which=("fwd", "bwd")) -> Dict[str, int]:
+        """Re-run the compositing kernels of the last step() (or, which=("fwd",), of the last forward()) with the
+        instrumented (STATS) variants and return the work counters used for the FP32 roofline."""
         lib, stream, f = self.lib, current_stream(), self._fwd
         out = {}
         if not f["M"]:
             return out
         names = ("entries_loaded", "entries_staged", "warp_candidates", "pairs_evaluated", "pairs_contributing", "reduction_groups")
-        for which in ("fwd", "bwd"):
+        for which in which:
             cnt = torch.zeros(6, dtype=torch.int64, device=self.device)
             check(lib.qed_debug_set_raster_counters(ptr(cnt)), "set counters")
             try:

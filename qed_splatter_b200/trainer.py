@@ -424,8 +424,10 @@ class SplatTrainer:
         from .comm import ViewShardedGradients
 
         x = self._xg
-        if x is None or x.N != self.arena.N or x.views_per_rank != views_per_rank:
-            self._xg = x = ViewShardedGradients(self.arena.N, views_per_rank, self.device, self.pg)
+        if x is None or x.views_per_rank != views_per_rank or (x.N != self.arena.N and not x.resize(self.arena.N)):
+            # headroom: densification grows the set gradually; most refine steps then reuse the symmetric buffers
+            self._xg = x = ViewShardedGradients(self.arena.N, views_per_rank, self.device, self.pg,
+                                                headroom=0.25 if self.step_count < self.cfg.stop_split_at else 0.0)
         if self.arena.grad.data_ptr() != x.grad.data_ptr():
             assert x.grad.numel() == self.arena.grad.numel()
             self.arena.grad = x.grad  # Adam reads the summed gradients straight from the symmetric arena
