@@ -323,7 +323,7 @@ def main_reference(args):
 # ------------------------------------------------------------------------------------------------
 # N > 1: the view-sharded step equals the single-rank step (SURVEY.md section 8e "Check"); never inside a timed region
 # ------------------------------------------------------------------------------------------------
-def run_multi_gpu_check(torch, dist, dev, rank, world):
+def run_multi_gpu_check(torch, dist, dev, rank, world, with_exchange=True):
     """1. N ranks x 1 view, gradients summed over the ranks  ==  1 rank x N views (the whole batch in one process).
     2. 3 trainer steps (render, loss, backward, gradient reduction, Adam): every replica holds bit-identical parameters,
        and they equal (to float tolerance: the reduction order differs) a single-process trainer fed all N views."""
@@ -353,6 +353,8 @@ def run_multi_gpu_check(torch, dist, dev, rank, world):
     # the same through this library's NVLink path (view-colour exchange + all-reduce kernel)
     from qed_splatter_b200.comm import ViewShardedGradients
 
+    if not with_exchange:
+        return _multi_gpu_check_trainer(torch, dist, dev, rank, world, s, mine, bg, res, ok, "nccl")
     xg = ViewShardedGradients(s.N, 1, dev)
     res["comm_path"] = xg.arena.path
     for rep in range(2):  # twice: both exchange buffers, stale records of the previous step present
@@ -370,9 +372,15 @@ def run_multi_gpu_check(torch, dist, dev, rank, world):
     dist.all_gather(allc, chk)
     res["exchange_arena_bit_identical_on_all_ranks"] = all(torch.equal(allc[0], c_) for c_ in allc)
     ok = ok and res["exchange_arena_bit_identical_on_all_ranks"]
+    return _multi_gpu_check_trainer(torch, dist, dev, rank, world, s, mine, bg, res, ok, "auto")
+
+
+def _multi_gpu_check_trainer(torch, dist, dev, rank, world, s, mine, bg, res, ok, comm):
+    from qed_splatter_b200.trainer import SplatTrainer, TrainConfig
+
     identical, vs_single = True, None
     log_s, logit_o = torch.log(s.scales), torch.logit(s.opacities)
-    tr = SplatTrainer(s.means.clone(), s.quats.clone(), log_s.clone(), logit_o.clone(), s.sh.clone(), cfg=TrainConfig(), rank=rank, world_size=world, backend="cuda")
+    tr = SplatTrainer(s.means.clone(), s.quats.clone(), log_s.clone(), logit_o.clone(), s.sh.clone(), cfg=TrainConfig(comm=comm), rank=rank, world_size=world, backend="cuda")
     tr.step_count = 3000
     for _ in range(3):
         tr.step(mine["viewmats"], mine["Ks"], s.width, s.height, mine["gt_rgb"], mine["gt_depth"], bg, total_views=world)
@@ -455,13 +463,21 @@ def main_ours(args):
         # backward of the next range is still running (NCCL runs on its own stream)
         pending.append(dist.all_reduce(arena[sh_begin + 48 * n0: sh_begin + 48 * n1], async_op=True))
 
-    xg = None
+    xg, comm_fallback = None, None
     if world > 1 and args.comm == "exchange":
         from qed_splatter_b200.comm import ViewShardedGradients
 
-        xg = ViewShardedGradients(N, 1, dev)
-        del arena
-        arena, views = xg.grad, xg.views()
+        try:  # symmetric memory (peer mappings / NVSwitch multicast) must be available on this box -- on every rank
+            xg = ViewShardedGradients(N, 1, dev)
+        except Exception as e:  # noqa: BLE001
+            comm_fallback = f"{type(e).__name__}: {e}"[:300]
+        ok_all = torch.tensor([0.0 if xg is None else 1.0], device=dev)
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        if float(ok_all.item()) < 1.0:
+            xg, comm_fallback = None, comm_fallback or "symmetric memory unavailable on another rank"
+        else:
+            del arena
+            arena, views = xg.grad, xg.views()
 
     def step():
         if xg is not None:
@@ -553,7 +569,7 @@ def main_ours(args):
     if world > 1:
         comm_info = {"impl": "exchange" if xg is not None else "nccl", "path": xg.arena.path if xg is not None else "torch.distributed all_reduce",
                      "bytes_all_reduced_per_rank": (xg.offsets["sh"][0] * 4) if xg is not None else PARAM_FLOATS * N * 4,
-                     "bytes_exchanged_per_rank": (n_visible * 16) if xg is not None else 0}
+                     "bytes_exchanged_per_rank": (n_visible * 16) if xg is not None else 0, "fallback_reason": comm_fallback}
 
     # ---- second half of the metric: train iters/s (full qed-splatter step through trainer.SplatTrainer: render,
     # 0.8 L1 + 0.2 (1-SSIM) + 0.2 depth-L1, backward, gradient all-reduce pipelined with Adam, strategy statistics) ----
@@ -677,7 +693,7 @@ def main_ours(args):
     # ---- N > 1: N ranks x 1 view == 1 rank x N views, replicas identical (outside every timed region) ----
     multi_gpu_check = None
     if world > 1 and not args.no_multi_gpu_check:
-        multi_gpu_check = run_multi_gpu_check(torch, dist, dev, rank, world)
+        multi_gpu_check = run_multi_gpu_check(torch, dist, dev, rank, world, with_exchange=xg is not None)
 
     if rank == 0:
         peaks = {}

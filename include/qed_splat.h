@@ -14,8 +14,8 @@
  * Conventions
  *   - plain C: raw device pointers + extents; contiguous row-major tensors; no torch types.
  *   - every function returns int: 0 = ok, < 0 = QED_ERR_* argument error, > 0 = cudaError_t.
- *   - never throws, never exits, never synchronises the device, holds no global mutable
- *     state (the qed_debug_* test hooks, which are not declared here, are the only exception);
+ *   - never throws, never exits, never synchronises the device, holds no mutable state shared
+ *     between threads (the qed_debug_* test hooks, which are not declared here, are thread-local);
  *     all work is enqueued on the `stream` argument (a cudaStream_t).
  *   - caller owns every buffer.  Outputs are fully overwritten unless stated "accumulates".
  *   - float = IEEE binary32.  "flat index" = c*N + n into the [C,N,...] arrays.
@@ -224,7 +224,10 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  *  render[C,H,W,4] (RGB + depth; depth normalised iff normalize_last), alphas[C,H,W],
  *  gt_rgb[C,H,W,3]: float32 in [0,1], or (gt_rgb_is_u8 != 0) the uint8 image cache of the data side
  *      (qed_splatter/config.py:37 cache_images_type="uint8"), converted as splatfacto's `image.float() / 255.0` does on CUDA (u8 * (1.0f / 255.0f)) at the point of use;
- *  gt_depth[C,H,W] (<=0 or non-finite = invalid), bg[3].
+ *  gt_depth[C,H,W] (<=0 or non-finite = invalid): float32 metres, or (gt_depth_is_u16 != 0) the raw uint16 sensor image,
+ *      converted at the point of use as nerfstudio's depth loader does with the reference's unit scale
+ *      (qed_splatter/dataparser.py:15 depth_unit_scale_factor = 0.001, times the scene scale): float(double(u16) *
+ *      depth_unit_scale); bg[3].
  *  mask[C,H,W] or NULL: the batch's `mask` (qed_splatter/model.py:93-97), float32 or (mask_is_u8 != 0) uint8 / bool.
  *      As in the reference, rendered and ground-truth depth are both multiplied by it BEFORE the validity test
  *      (model.py:96-97), and -- splatfacto's parent loss, model.py:83-85 -- so are the predicted and ground-truth
@@ -241,8 +244,8 @@ int qed_unpack_grads(int CN, int D, const float* packed_grads, float* v_means2d,
  */
 size_t qed_loss_workspace_bytes(int C, int width, int height, float ssim_lambda);
 int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
-                     const void* gt_rgb, int gt_rgb_is_u8, const float* gt_depth, const void* mask, int mask_is_u8,
-                     const float* bg, float rgb_weight,
+                     const void* gt_rgb, int gt_rgb_is_u8, const void* gt_depth, int gt_depth_is_u16, double depth_unit_scale,
+                     const void* mask, int mask_is_u8, const float* bg, float rgb_weight,
                      float depth_lambda, float ssim_lambda, float grad_scale, double* stats_dev, float* loss_dev,
                      float* v_render, float* v_alphas, void* workspace, size_t workspace_bytes, qed_stream_t stream);
 

@@ -89,6 +89,19 @@ struct GtImage {
     }
 };
 
+// Ground-truth depth as the data side holds it: float32 metres, or the raw uint16 sensor image (millimetres for the
+// reference's datasets) with the unit scale of qed_splatter/dataparser.py:15 (depth_unit_scale_factor = 0.001, times the
+// dataparser's scene scale) applied at the point of use -- nerfstudio's loader computes `image.astype(float64) * scale`,
+// which is what `at()` returns, rounded to float32.  Keeps the depth cache at 2 B/pixel and removes a preprocessing pass.
+struct GtDepth {
+    const void* p;
+    int u16;
+    double scale;
+    __device__ __forceinline__ float at(int64_t pix) const {
+        return u16 ? (float)((double)reinterpret_cast<const uint16_t*>(p)[pix] * scale) : reinterpret_cast<const float*>(p)[pix];
+    }
+};
+
 // Optional per-pixel loss mask of the batch (`batch["mask"]`, qed_splatter/model.py:93-97; splatfacto multiplies the
 // RGB images by it too): float32 or uint8 / bool [C,H,W]; NULL = all ones.
 struct PixelMask {

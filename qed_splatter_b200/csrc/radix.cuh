@@ -9,7 +9,7 @@
 
 namespace qed {
 
-static int g_radix_onesweep = 1;  // test hook (qed_debug_set_radix_onesweep): 0 = three kernels per pass
+static thread_local int g_radix_onesweep = 1;  // test hook (qed_debug_set_radix_onesweep), thread-local: 0 = three kernels per pass
 
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;

@@ -1077,11 +1077,13 @@ __global__ void unpack_grads_kernel(int64_t CN, int D, const float4* __restrict_
     }
 }
 
-// test / instrumentation hooks (process-global; not part of the reference surface)
-static int g_raster_cull = 1;                           // 0 disables the culling (identical results, slower)
-static unsigned long long* g_raster_counters = nullptr;  // device uint64[6] -> STATS kernels
-static int g_px_fwd = 4, g_px_bwd = 4;                   // pixels per lane
-static int g_raster_packed = 1;                          // f32x2 kernels where they exist (backward, 4 px/lane)
+// test / instrumentation hooks (not part of the reference surface).  THREAD-LOCAL: a test or the benchmark's pair
+// counters change them for the calling host thread only, so another thread (nerfstudio's viewer rendering through
+// the same library) never sees them -- the library holds no cross-thread mutable state.
+static thread_local int g_raster_cull = 1;                           // 0 disables the culling (identical results, slower)
+static thread_local unsigned long long* g_raster_counters = nullptr;  // device uint64[6] -> STATS kernels
+static thread_local int g_px_fwd = 4, g_px_bwd = 4;                   // pixels per lane
+static thread_local int g_raster_packed = 1;                          // f32x2 kernels where they exist (backward, 4 px/lane)
 
 template <int D, int PX, bool BWD>
 static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {

@@ -22,7 +22,7 @@ __device__ __forceinline__ bool finitef(float x) { return fabsf(x) <= 3.40282346
 // float bits is the float order and atomicMax on the bits works.  stats[2] = valid pixels with alpha > 0,
 // stats[6] = pixels with alpha == 0 whose ground truth is usable (valid iff the fill value is finite).
 __global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, const float4* __restrict__ render, const float* __restrict__ alphas,
-                                                                 const float* __restrict__ gt_depth, const PixelMask mask, double* __restrict__ stats) {
+                                                                 const GtDepth gt_depth, const PixelMask mask, double* __restrict__ stats) {
     __shared__ float s_max[kLossThreads / 32];
     __shared__ int s_na[kLossThreads / 32], s_nb[kLossThreads / 32];
     pdl_enter();
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_stats_kernel(int64_t HW, co
         const int64_t pix = cam * HW + (in ? i : 0);
         d[u] = in ? render[pix].w : 0.0f;
         a[u] = in ? alphas[pix] : 1.0f;
-        gd[u] = in ? gt_depth[pix] : 0.0f;
+        gd[u] = in ? gt_depth.at(pix) : 0.0f;
         mk[u] = in ? mask.at(pix) : 0.0f;
     }
 #pragma unroll
@@ -80,7 +80,7 @@ __device__ __forceinline__ double n_valid_of(const double* s, float maxd) { retu
 //   otherwise  : loss sums + gradients (v_rgb_extra = gradient of the SSIM term w.r.t. the clamped rgb, or NULL)
 template <bool WRITE_PRED>
 __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int C, const float4* __restrict__ render, const float* __restrict__ alphas,
-                                                                const GtImage gt_rgb, const float* __restrict__ gt_depth, const PixelMask mask,
+                                                                const GtImage gt_rgb, const GtDepth gt_depth, const PixelMask mask,
                                                                 const float* __restrict__ bg, float rgb_weight, float depth_lambda, float grad_scale,
                                                                 double* __restrict__ stats, float4* __restrict__ v_render, float* __restrict__ v_alphas,
                                                                 float* __restrict__ pred_rgb, const float* __restrict__ v_rgb_extra) {
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_grad_kernel(int64_t HW, int
         }
         const float e0 = __fmul_rn(c0, mk) - __fmul_rn(gt_rgb.at(pix * 3 + 0), mk), e1 = __fmul_rn(c1, mk) - __fmul_rn(gt_rgb.at(pix * 3 + 1), mk),
                     e2 = __fmul_rn(c2, mk) - __fmul_rn(gt_rgb.at(pix * 3 + 2), mk);
-        const float gd = __fmul_rn(gt_depth[pix], mk);                 // model.py:96-97
+        const float gd = __fmul_rn(gt_depth.at(pix), mk);              // model.py:96-97
         const float d = __fmul_rn((a > 0.0f) ? r.w : maxd, mk);
         const bool valid = finitef(d) && finitef(gd) && (gd > 0.0f);
         s_rgb += (double)(fabsf(e0) + fabsf(e1) + fabsf(e2));
@@ -298,15 +298,16 @@ extern "C" size_t qed_loss_workspace_bytes(int C, int width, int height, float s
 }
 
 extern "C" int qed_loss_fwd_bwd(int C, int width, int height, const float* render, const float* alphas,
-                                const void* gt_rgb_, int gt_rgb_is_u8, const float* gt_depth, const void* mask_, int mask_is_u8,
-                                const float* bg, float rgb_weight,
+                                const void* gt_rgb_, int gt_rgb_is_u8, const void* gt_depth_, int gt_depth_is_u16, double depth_unit_scale,
+                                const void* mask_, int mask_is_u8, const float* bg, float rgb_weight,
                                 float depth_lambda, float ssim_lambda, float grad_scale, double* stats_dev, float* loss_dev,
                                 float* v_render, float* v_alphas, void* workspace, size_t workspace_bytes, qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (C <= 0 || width <= 0 || height <= 0) return QED_ERR_BAD_ARG;
-    if (!render || !alphas || !gt_rgb_ || !gt_depth || !bg || !stats_dev || !loss_dev || !v_render || !v_alphas) return QED_ERR_BAD_ARG;
+    if (!render || !alphas || !gt_rgb_ || !gt_depth_ || !bg || !stats_dev || !loss_dev || !v_render || !v_alphas) return QED_ERR_BAD_ARG;
     const GtImage gt_rgb{gt_rgb_, gt_rgb_is_u8 ? 1 : 0};
     const PixelMask mask{mask_, mask_is_u8 ? 1 : 0};
+    const GtDepth gt_depth{gt_depth_, gt_depth_is_u16 ? 1 : 0, depth_unit_scale};
     if (C > 21845) return QED_ERR_UNSUPPORTED;
     const bool use_ssim = ssim_lambda > 0.0f;
     if (use_ssim) {

@@ -26,12 +26,12 @@ from ._lib import check, current_stream, ptr
 class _DepthSupervisedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, render: Tensor, alphas: Tensor, gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, rgb_weight: float,
-                depth_lambda: float, ssim_lambda: float, mask: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
+                depth_lambda: float, ssim_lambda: float, mask: Optional[Tensor], depth_unit_scale: float) -> Tuple[Tensor, Tensor, Tensor]:
         # raw pointers cross the C-ABI: a CPU tensor (e.g. nerfstudio's image cache under cache_images="cpu") or one
         # on another device would hand the kernel a pointer it cannot read -> raise here instead
         _lib.require_cuda(render, alphas, gt_rgb, gt_depth, background, mask)
         _lib.require_dtype(gt_rgb, (torch.float32, torch.uint8), "gt_rgb")
-        _lib.require_dtype(gt_depth, (torch.float32,), "gt_depth")
+        _lib.require_dtype(gt_depth, (torch.float32, torch.uint16, torch.int16), "gt_depth")
         _lib.require_dtype(background, (torch.float32,), "background")
         _lib.require_dtype(render, (torch.float32,), "render")
         _lib.require_dtype(alphas, (torch.float32,), "alphas")
@@ -61,7 +61,8 @@ class _DepthSupervisedLoss(torch.autograd.Function):
         v_alphas = torch.empty_like(a)
         ws_bytes = lib.qed_loss_workspace_bytes(C, W, H, float(ssim_lambda))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-        check(lib.qed_loss_fwd_bwd(C, W, H, ptr(r), ptr(a), ptr(rgb), int(rgb.dtype == torch.uint8), ptr(dep), ptr(mk), int(mk is not None and mk.dtype == torch.uint8), ptr(bg), float(rgb_weight), float(depth_lambda),
+        check(lib.qed_loss_fwd_bwd(C, W, H, ptr(r), ptr(a), ptr(rgb), int(rgb.dtype == torch.uint8), ptr(dep), int(dep.dtype != torch.float32), float(depth_unit_scale),
+                                   ptr(mk), int(mk is not None and mk.dtype == torch.uint8), ptr(bg), float(rgb_weight), float(depth_lambda),
                                    float(ssim_lambda), 1.0, ptr(stats), ptr(loss), ptr(v_render), ptr(v_alphas), ptr(ws), ws_bytes,
                                    current_stream()), "qed_loss_fwd_bwd")
         ctx.save_for_backward(v_render, v_alphas)
@@ -73,21 +74,24 @@ class _DepthSupervisedLoss(torch.autograd.Function):
     def backward(ctx, g_total, g_rgb, g_depth):
         v_render, v_alphas = ctx.saved_tensors
         # d(total)/d(render, alphas) was computed by the forward launch; the components are reported for logging only
-        return v_render * g_total, v_alphas * g_total, None, None, None, None, None, None, None
+        return v_render * g_total, v_alphas * g_total, None, None, None, None, None, None, None, None
 
 
 def depth_supervised_loss(render: Tensor, alphas: Tensor, gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, rgb_weight: float = 0.8,
-                          depth_lambda: float = 0.2, ssim_lambda: float = 0.0, mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+                          depth_lambda: float = 0.2, ssim_lambda: float = 0.0, mask: Optional[Tensor] = None,
+                          depth_unit_scale: float = 0.001) -> Tuple[Tensor, Tensor, Tensor]:
     """-> (total, rgb_term, depth_term), 0-dim tensors; `total` carries the gradient to `render` and `alphas`.
 
     render [C,H,W,4] (RGB + depth; expected depth for 'RGB+ED'), alphas [C,H,W,1], gt_rgb [C,H,W,3] float in [0,1] or uint8
     (nerfstudio's image cache, config.py:37; converted as splatfacto's `image.float() / 255.0` inside the kernels),
-    gt_depth [C,H,W] or [C,H,W,1] (<= 0 or non-finite = no supervision), background [3]; mask [C,H,W(,1)] float32 / uint8 /
+    gt_depth [C,H,W] or [C,H,W,1] (<= 0 or non-finite = no supervision): float32 metres, or the raw uint16 sensor image
+    (torch.uint16, or its bits as torch.int16), converted in-kernel with `depth_unit_scale` (qed_splatter/dataparser.py:15:
+    0.001, times the dataparser's scene scale) as nerfstudio's depth loader does; background [3]; mask [C,H,W(,1)] float32 / uint8 /
     bool or None = `batch["mask"]`: rendered and ground-truth depth are multiplied by it before the validity test
     (model.py:93-97), predicted and ground-truth RGB before L1 / SSIM (splatfacto's parent loss).  All tensors must be
     on the render's CUDA device (CPU tensors raise; copy nerfstudio's CPU image cache explicitly).
     total = rgb_weight * mean|clamp(rgb + (1 - alpha) bg, 0, 1) - gt| + ssim_lambda * (1 - SSIM) + depth_lambda *
     mean_valid|depth_filled - gt_depth|  (qed-splatter: depth_lambda = 0.2; splatfacto: rgb_weight = 0.8, ssim_lambda = 0.2).
     """
-    total, l_rgb, l_depth = _DepthSupervisedLoss.apply(render, alphas, gt_rgb, gt_depth, background, rgb_weight, depth_lambda, ssim_lambda, mask)
+    total, l_rgb, l_depth = _DepthSupervisedLoss.apply(render, alphas, gt_rgb, gt_depth, background, rgb_weight, depth_lambda, ssim_lambda, mask, depth_unit_scale)
     return total, l_rgb, l_depth

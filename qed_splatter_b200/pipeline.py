@@ -316,7 +316,7 @@ class FusedSplatStep:
              gt_rgb: Tensor, gt_depth: Tensor, background: Tensor, render_mode: str = "RGB+ED", rgb_weight: float = 0.8,
              depth_lambda: float = 0.2, grad_scale: float = 1.0, rasterize_mode: str = "classic",
              grad_out: Optional[Dict[str, Tensor]] = None, ssim_lambda: float = 0.0, n_chunks: int = 1, on_chunk=None,
-             activations: int = 0, mask: Optional[Tensor] = None, exchange=None) -> StepOutput:
+             activations: int = 0, mask: Optional[Tensor] = None, exchange=None, depth_unit_scale: float = 0.001) -> StepOutput:
         """`render_mode` RGB+ED (north_star) or RGB+D (what qed_splatter/model.py:257 passes).
         loss = rgb_weight * L1 + ssim_lambda * (1 - SSIM) + depth_lambda * masked depth-L1 (splatfacto: 0.8 / 0.2 / 0.2).
         `mask` [C,H,W(,1)] float32 / uint8 / bool = `batch["mask"]` (model.py:93-97), see losses.depth_supervised_loss.
@@ -327,7 +327,7 @@ class FusedSplatStep:
         # raw pointers cross the C-ABI: wrong device / dtype must raise here, not fault in the kernel
         _lib.require_cuda(means, gt_rgb, gt_depth, background, mask)
         _lib.require_dtype(gt_rgb, (torch.float32, torch.uint8), "gt_rgb")
-        _lib.require_dtype(gt_depth, (torch.float32,), "gt_depth")
+        _lib.require_dtype(gt_depth, (torch.float32, torch.uint16, torch.int16), "gt_depth")  # raw uint16: scaled in-kernel by depth_unit_scale
         _lib.require_dtype(background, (torch.float32,), "background")
         _lib.require_dtype(mask, (torch.float32, torch.uint8, torch.bool), "mask")
         C_, HW_ = viewmats.shape[0], width * height
@@ -351,8 +351,8 @@ class FusedSplatStep:
             v_alphas = self._get("v_alphas", (C, height, width, 1))
             lws_bytes = lib.qed_loss_workspace_bytes(C, width, height, ssim_lambda)
             lws = self._get("loss_ws", (lws_bytes,), torch.uint8) if lws_bytes else None
-            check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), int(gt_rgb.dtype == torch.uint8), ptr(gt_depth), ptr(mask),
-                                       int(mask is not None and mask.dtype == torch.uint8), ptr(background), rgb_weight,
+            check(lib.qed_loss_fwd_bwd(C, width, height, ptr(render), ptr(alphas), ptr(gt_rgb), int(gt_rgb.dtype == torch.uint8), ptr(gt_depth), int(gt_depth.dtype != torch.float32),
+                                       float(depth_unit_scale), ptr(mask), int(mask is not None and mask.dtype == torch.uint8), ptr(background), rgb_weight,
                                        depth_lambda, ssim_lambda, grad_scale, ptr(self._stats), ptr(self._loss), ptr(v_render), ptr(v_alphas),
                                        ptr(lws), lws_bytes, stream), "qed_loss_fwd_bwd")
             self._mark("loss")

@@ -51,6 +51,7 @@ class TrainConfig:
     adam_eps: float = 1e-15
     adam_betas: Tuple[float, float] = (0.9, 0.999)
     depth_lambda: float = 0.2
+    depth_unit_scale: float = 0.001  # qed_splatter/dataparser.py:15 (x the dataparser's scene scale); used when gt_depth is raw uint16
     ssim_lambda: float = 0.2
     sh_degree: int = 3
     sh_degree_interval: int = 1000
@@ -426,8 +427,22 @@ class SplatTrainer:
         x = self._xg
         if x is None or x.views_per_rank != views_per_rank or (x.N != self.arena.N and not x.resize(self.arena.N)):
             # headroom: densification grows the set gradually; most refine steps then reuse the symmetric buffers
-            self._xg = x = ViewShardedGradients(self.arena.N, views_per_rank, self.device, self.pg,
-                                                headroom=0.25 if self.step_count < self.cfg.stop_split_at else 0.0)
+            import torch.distributed as dist
+
+            err = None
+            try:
+                x = ViewShardedGradients(self.arena.N, views_per_rank, self.device, self.pg,
+                                         headroom=0.25 if self.step_count < self.cfg.stop_split_at else 0.0)
+            except Exception as e:  # noqa: BLE001  (no peer mappings / symmetric memory on this box)
+                x, err = None, e
+            ok = torch.tensor([0.0 if x is None else 1.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)  # every rank takes the same path
+            if float(ok.item()) < 1.0:
+                if self.cfg.comm == "exchange":
+                    raise RuntimeError(f"comm='exchange': symmetric memory is not available on every rank ({err})")
+                self.comm, self._xg = "nccl", None
+                return None
+            self._xg = x
         if self.arena.grad.data_ptr() != x.grad.data_ptr():
             assert x.grad.numel() == self.arena.grad.numel()
             self.arena.grad = x.grad  # Adam reads the summed gradients straight from the symmetric arena
@@ -547,12 +562,12 @@ class SplatTrainer:
         gv = a.views(a.grad)
         # the stored parameters go straight in: exp / sigmoid (model.py:269-271) and their chain rule run inside the
         # projection kernels, the gradients land in the arena
-        if self.comm == "exchange":
-            xg = self._exchange_for(C)
+        xg = self._exchange_for(C) if self.comm == "exchange" else None  # may fall back to "nccl" (comm="auto", no symmetric memory)
+        if xg is not None:
             out = self._fused.step(pv["means"], pv["quats"], pv["scales"], pv["opacities"], pv["sh"], viewmats, Ks, width, height,
                                    self.sh_degree_to_use(), gt_rgb, gt_depth, background, render_mode=c.render_mode, rgb_weight=1.0 - c.ssim_lambda,
                                    depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, activations=3,
-                                   mask=mask, ssim_lambda=c.ssim_lambda, exchange=xg)
+                                   mask=mask, ssim_lambda=c.ssim_lambda, exchange=xg, depth_unit_scale=c.depth_unit_scale)
             self.accumulate_stats(out.packed_grads, out.radii, width, height, packed=True, n_cameras=total)
             self.optimizer_step()
             loss = out.loss.clone()
@@ -574,7 +589,8 @@ class SplatTrainer:
                                gt_rgb, gt_depth, background, render_mode=c.render_mode, rgb_weight=1.0 - c.ssim_lambda,
                                depth_lambda=c.depth_lambda, grad_scale=C / float(total), rasterize_mode=c.rasterize_mode, grad_out=gv,
                                activations=3,  # ACT_LOG_SCALES | ACT_LOGIT_OPACITIES (pipeline.py / include/qed_splat.h)
-                               mask=mask, ssim_lambda=c.ssim_lambda, n_chunks=c.comm_chunks if (pipelined and c.chunk_project_bwd) else 1,
+                               mask=mask, depth_unit_scale=c.depth_unit_scale, ssim_lambda=c.ssim_lambda,
+                               n_chunks=c.comm_chunks if (pipelined and c.chunk_project_bwd) else 1,
                                on_chunk=on_chunk if (pipelined and c.chunk_project_bwd) else None)
         self.accumulate_stats(out.packed_grads, out.radii, width, height, packed=True, n_cameras=total)
         if pipelined:

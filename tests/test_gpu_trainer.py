@@ -10,7 +10,7 @@ from qed_splatter_b200 import _lib, rasterization
 from qed_splatter_b200.pipeline import FusedSplatStep
 from qed_splatter_b200.scenes import scene_s0
 from qed_splatter_b200.trainer import GROUPS, GaussianArena, SplatTrainer, TrainConfig, adam_step_torch
-from helpers import assert_close_frac
+from helpers import assert_close_frac, scene_args
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -387,3 +387,38 @@ def test_deferred_size_read_equals_synchronous_path_and_survives_overflow(cuda, 
     # forward-only use resolves by itself
     r1, a1 = defer.forward(small.means, small.quats, small.scales, small.opacities, small.sh, small.viewmats, small.Ks, 96, 96, 3)
     assert torch.equal(r1, ref_small[0]) and torch.equal(a1, ref_small[1])
+
+
+@pytest.mark.parametrize("ssim", [0.0, 0.2])
+def test_uint16_depth_is_scaled_in_kernel(cuda, ssim):
+    """The raw uint16 depth image + the dataparser's unit scale (qed_splatter/dataparser.py:15) consumed by the loss kernels
+    == the float32 image nerfstudio's loader would have produced (float64 product, rounded): bit-identical loss and
+    gradients, through both the autograd drop-in and the fused step."""
+    from qed_splatter_b200 import depth_supervised_loss, rasterization
+
+    s = scene_s0(N=3000, C=2, size=64)
+    g = torch.Generator().manual_seed(9)
+    raw = torch.randint(0, 6000, (2, 64, 64, 1), generator=g, dtype=torch.int32)
+    raw[torch.rand(2, 64, 64, 1, generator=g) < 0.15] = 0  # holes
+    scale = 0.001 * 1.37  # unit scale x scene scale
+    as_float = (raw.double() * scale).float().to(cuda)
+    raw16 = raw.to(torch.uint16).to(cuda)
+    a = scene_args(s, cuda)
+    bg = torch.tensor([0.2, 0.4, 0.6], device=cuda)
+    render, alpha, _ = rasterization(**a, width=64, height=64, sh_degree=3, render_mode="RGB+D")
+    render, alpha = render.detach().requires_grad_(True), alpha.detach().requires_grad_(True)
+    outs = []
+    for d in (as_float, raw16, raw16.view(torch.int16)):
+        render.grad = alpha.grad = None
+        total, l_rgb, l_d = depth_supervised_loss(render, alpha, s.gt_rgb.to(cuda), d, bg, ssim_lambda=ssim, depth_unit_scale=scale)
+        total.backward()
+        outs.append((total.detach().clone(), l_d.clone(), render.grad.clone(), alpha.grad.clone()))
+    for o in outs[1:]:
+        assert all(torch.equal(x, y) for x, y in zip(o, outs[0]))
+    fs = FusedSplatStep(cuda)
+    ref = fs.step(a["means"], a["quats"], a["scales"], a["opacities"], a["colors"], a["viewmats"], a["Ks"], 64, 64, 3, s.gt_rgb.to(cuda), as_float, bg,
+                  render_mode="RGB+D", ssim_lambda=ssim)
+    ref_loss = ref.loss.clone()
+    got = fs.step(a["means"], a["quats"], a["scales"], a["opacities"], a["colors"], a["viewmats"], a["Ks"], 64, 64, 3, s.gt_rgb.to(cuda), raw16, bg,
+                  render_mode="RGB+D", ssim_lambda=ssim, depth_unit_scale=scale)
+    assert torch.equal(got.loss, ref_loss)
