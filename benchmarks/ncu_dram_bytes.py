@@ -54,6 +54,10 @@ def stage_of(name, state):
         return "loss"
     if any(k in n for k in ("scan_", "radix_", "emit_", "compose_ids")):
         return state["s"] if state["s"] in ("isect_prepare", "isect_fill") else "isect_other"
+    if "adam_arena" in n:
+        return "adam"
+    if "strategy_update" in n:
+        return "strategy_update"
     return "other"
 
 
@@ -62,6 +66,7 @@ def main():
     ap.add_argument("report")
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02"))
     ap.add_argument("--workload", default=None)
+    ap.add_argument("--what", default="ONE fused step (benchmarks/profile_step.py)")
     a = ap.parse_args()
     out = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -103,7 +108,7 @@ def main():
     for S in stages.values():
         S["dram_gbs_over_stage_kernel_time"] = S["dram_bytes"] / (S["duration_us"] * 1e-6) / 1e9 if S["duration_us"] else None
     total_us = sum(S["duration_us"] for S in stages.values())
-    head = [f"# ncu --set full --clock-control none of ONE fused step (benchmarks/profile_step.py), {len(rows)} launches, {total_us:.1f} us of kernel time",
+    head = [f"# ncu --set full --clock-control none of {a.what}, {len(rows)} launches, {total_us:.1f} us of kernel time",
             "# (cold-cache, serialised replays: compare SHARES and bytes, not absolute times); HBM peak = MEASURED_PEAKS.json",
             "# stage                launches   kernel us   share    DRAM MB (read + write)      GB/s over kernel time"]
     for st, S in sorted(stages.items(), key=lambda kv: -kv[1]["duration_us"]):

@@ -29,17 +29,35 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--mode", default="RGB+ED")
+    ap.add_argument("--train", action="store_true", help="profile trainer.SplatTrainer steps (SSIM + L1 + depth loss, Adam, strategy statistics)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     s = scene_s1(N=a.gaussians, width=a.width, height=a.height).to(dev)
     bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
-    fs = FusedSplatStep(dev)
-    grads = {k: torch.zeros_like(getattr(s, k)) for k in ("means", "quats", "scales", "opacities", "sh")}
+    if a.train:
+        from qed_splatter_b200.trainer import SplatTrainer, TrainConfig
 
-    def step():
-        return fs.step(s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, 3, s.gt_rgb, s.gt_depth, bg,
-                       render_mode=a.mode, grad_out=grads)
+        tr = SplatTrainer(s.means.clone(), s.quats.clone(), torch.log(s.scales), torch.logit(s.opacities.clamp(1e-4, 1 - 1e-4)), s.sh.clone(),
+                          cfg=TrainConfig(render_mode=a.mode, refine_every=10 ** 9), backend="cuda")
+        tr.step_count = 3000
+        fs = tr._fused
+
+        class _Out:
+            pass
+
+        def step():
+            o = _Out()
+            o.loss, _ = tr.step(s.viewmats, s.Ks, s.width, s.height, s.gt_rgb, s.gt_depth, bg)
+            o.n_isects = fs._fwd.get("n_isects_real", fs._fwd["M"])
+            return o
+    else:
+        fs = FusedSplatStep(dev)
+        grads = {k: torch.zeros_like(getattr(s, k)) for k in ("means", "quats", "scales", "opacities", "sh")}
+
+        def step():
+            return fs.step(s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, 3, s.gt_rgb, s.gt_depth, bg,
+                           render_mode=a.mode, grad_out=grads)
 
     for _ in range(a.warmup):
         out = step()
