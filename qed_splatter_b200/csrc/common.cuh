@@ -166,6 +166,42 @@ __device__ __forceinline__ bool ellipse_hits_rect(float mx, float my, float A, f
     return !(best > tau2 * 1.01f + 0.03f + 2e-5f * mag);
 }
 
+// Conservative x-extent of {pixel centres (x, y) : Q(mean - (x, y)) <= tau2, ya <= y <= yb}: the part of the alpha >= 1/255
+// ellipse inside one horizontal strip (a tile row).  The set is convex, so a tile of that row can be touched iff its
+// pixel-centre interval [xa, xb] meets [xlo, xhi].  One evaluation serves every tile of a (Gaussian, tile row) pair, where
+// ellipse_hits_rect costs four edge minimisations per tile.  Returns false if the ellipse misses the strip.
+//   fixed dy: A dx^2 + B dy dx + C dy^2 - t <= 0  ->  dx in (-B dy -+ sqrt(disc)) / 2A,  disc = 4 A t - det dy^2,  det = 4AC - B^2
+//   the right end dx_hi(dy) is concave with its maximum dxmax = sqrt(4 C t / det) at dy = -B dxmax / 2C, the left end mirrors it.
+// Margins: tau2 is inflated exactly as in ellipse_hits_rect, and the interval is widened by 0.1 px + 0.5 % of the
+// ellipse's half-width (cancellation in det for thin, tilted ellipses).
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ bool ellipse_strip_x_extent(float mx, float my, float A, float B, float C, float tau2, float ya, float yb, float& xlo,
+                                                       float& xhi) {
+    // straight-line code, approximate rcp / rsqrt (relative error ~1e-7, far inside the slack below): ~50 instructions
+    const float t = tau2 * 1.01f + 0.03f;
+    const float det = fmaxf(4.0f * A * C - B * B, 1e-30f);
+    const float rdet = rcp_approx(det);
+    const float ey = 4.0f * A * t * rdet, ex = 4.0f * C * t * rdet;            // squared half-extents of the ellipse in y / x
+    const float dymax = ey * rsqrt_approx(fmaxf(ey, 1e-30f)) * 1.0001f + 1e-3f;  // sqrt(e) = e * rsqrt(e)
+    const float dxmax = ex * rsqrt_approx(fmaxf(ex, 1e-30f));
+    const float dl = fmaxf(my - yb, -dymax), dh = fminf(my - ya, dymax);  // dy = my - y over the strip, cut to the ellipse's y-extent
+    const float dys = -0.5f * B * dxmax * rcp_approx(C);                  // dy of the right extreme point (the left one sits at -dys)
+    const float r2A = 0.5f * rcp_approx(A);
+    const float dy_hi = fminf(fmaxf(dys, dl), dh), dy_lo = fminf(fmaxf(-dys, dl), dh);
+    const float disc_hi = fmaxf(4.0f * A * t - det * dy_hi * dy_hi, 0.0f), disc_lo = fmaxf(4.0f * A * t - det * dy_lo * dy_lo, 0.0f);
+    const float s_hi = disc_hi * rsqrt_approx(fmaxf(disc_hi, 1e-30f)), s_lo = disc_lo * rsqrt_approx(fmaxf(disc_lo, 1e-30f));
+    const float dx_hi = (-B * dy_hi + s_hi) * r2A, dx_lo = (-B * dy_lo - s_lo) * r2A;
+    const float slack = 0.1f + 0.005f * dxmax;
+    xlo = mx - dx_hi - slack;  // x = mx - dx
+    xhi = mx - dx_lo + slack;
+    return (tau2 >= 0.0f) && (dl <= dh);  // opacity < 1/255 can never pass the alpha test; the ellipse may miss the strip
+}
+
 // ---- packed float pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot, two IEEE fp32 results) -------------
 // ptxas folds bc2(s) into a scalar-broadcast operand (`R.F32`), neg2/abs2 into operand modifiers and pk2 of
 // two freshly produced scalars into adjacent registers, so these helpers cost no extra instructions.

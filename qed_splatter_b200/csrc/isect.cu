@@ -411,30 +411,39 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
     }
     const float inv_tile_w = 1.0f / (float)tile_w;
     int keep = 0, mine = 0;
+    // One strip evaluation per entry, straight-line (all four geometry records are requested before any is used); the
+    // extent of a (Gaussian, tile row) pair is the same for every tile of the row, but a branch that reuses it across a
+    // thread's four entries serialises the loads and measured slower.
+    float4 ga[kPer], gb[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int64_t v = threadIdx.x * kPer + k < cnt ? val[k] : 0;  // (slots behind the block's count hold stale shared memory)
+        ga[k] = ex.geom[v * 2];
+        gb[k] = ex.geom[v * 2 + 1];
+    }
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
         const int t = threadIdx.x * kPer + k;
-        if (t < cnt) {
-            const int tile = (int)(key[k] & tile_mask);
-            int ty = (int)(((float)tile + 0.5f) * inv_tile_w);  // exact below 2^22 tiles; corrected below anyway
-            int tx = tile - ty * tile_w;
-            if (tx < 0) {
-                --ty;
-                tx += tile_w;
-            } else if (tx >= tile_w) {
-                ++ty;
-                tx -= tile_w;
-            }
-            const float4 ga = ex.geom[(int64_t)val[k] * 2], gb = ex.geom[(int64_t)val[k] * 2 + 1];
-            const float x0 = (float)(tx * (int)tile_size) + 0.5f, y0 = (float)(ty * (int)tile_size) + 0.5f;
-            const float x1 = (float)min(tx * (int)tile_size + (int)tile_size - 1, ex.width - 1) + 0.5f;
-            const float y1 = (float)min(ty * (int)tile_size + (int)tile_size - 1, ex.height - 1) + 0.5f;
-            const bool hit = ellipse_hits_rect(ga.x, ga.y, 0.5f * kLog2e * gb.x, kLog2e * gb.y, 0.5f * kLog2e * gb.z,
-                                               __log2f(ga.z) + kLog2_255, x0, y0, x1, y1);
-            if (hit) {
-                keep |= 1 << k;
-                ++mine;
-            }
+        const int tile = (int)(key[k] & tile_mask);
+        int ty = (int)(((float)tile + 0.5f) * inv_tile_w);  // exact below 2^22 tiles; corrected below anyway
+        int tx = tile - ty * tile_w;
+        if (tx < 0) {
+            --ty;
+            tx += tile_w;
+        } else if (tx >= tile_w) {
+            ++ty;
+            tx -= tile_w;
+        }
+        const float ya = (float)(ty * (int)tile_size) + 0.5f;
+        const float yb = (float)min(ty * (int)tile_size + (int)tile_size - 1, ex.height - 1) + 0.5f;
+        float xlo, xhi;
+        const bool strip_hit = ellipse_strip_x_extent(ga[k].x, ga[k].y, 0.5f * kLog2e * gb[k].x, kLog2e * gb[k].y, 0.5f * kLog2e * gb[k].z,
+                                                      __log2f(ga[k].z) + kLog2_255, ya, yb, xlo, xhi);
+        const float xa = (float)(tx * (int)tile_size) + 0.5f;
+        const float xb = (float)min(tx * (int)tile_size + (int)tile_size - 1, ex.width - 1) + 0.5f;
+        if (t < cnt && strip_hit && xa <= xhi && xb >= xlo) {
+            keep |= 1 << k;
+            ++mine;
         }
     }
     // exclusive scan of the per-thread counts over the block
