@@ -556,8 +556,8 @@ def main_ours(args):
             stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / K
     fs.marks = None
     n_visible = int((out.radii > 0).sum())
-    M = out.n_isects
-    n_exact = fs.n_isects_exact()
+    M = int(fs._buf["tiles"][:N].sum())  # gsplat's bounding-box intersection count (one local view)
+    n_exact = fs.n_isects_exact()        # entries of the exact tile lists the step actually builds, sorts and composites
     loss = [float(x) for x in out.loss.tolist()]
 
     # ---- pair counters for the compositing roofline (instrumented launches, outside any timed region) ----

@@ -40,7 +40,7 @@ def main():
     run()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
-    print(f"profile_render ok: {a.gaussians} Gaussians {a.res} n_isects {fs._fwd.get('n_isects_real', fs._fwd['M'])} exact {fs.n_isects_exact()}")
+    print(f"profile_render ok: {a.gaussians} Gaussians {a.res} n_isects (gsplat) {int(fs._buf['tiles'][:a.gaussians].sum())} exact {fs.n_isects_exact()}")
 
 
 if __name__ == "__main__":

@@ -74,7 +74,7 @@ def main():
                 proj_bytes = n * 44.0 + n_vis * ((192.0 if f["n_color"] else 0.0) + 100.0)
                 t_proj, t_ras = acc.get("project_fwd"), acc.get("raster_fwd")
                 row = {"gaussians": n, "res": res, "width": W, "height": H, "mode": mode, "ms": ms, "mpix_s": W * H / ms / 1e3,
-                       "n_visible": n_vis, "n_isects": f.get("n_isects_real", f["M"]), "n_isects_exact": fs.n_isects_exact(),
+                       "n_visible": n_vis, "n_isects": int(fs._buf["tiles"][:n].sum()), "n_isects_exact": fs.n_isects_exact(),
                        "alpha_mean": float(f["alphas"].mean()), "composited_per_pixel": pairs / float(W * H),
                        "project_hbm_frac": (proj_bytes / (t_proj * 1e-3) / 1e9 / hbm_peak) if t_proj else None,
                        "raster_fp32_frac": (pairs * flop_pair / (t_ras * 1e-3) / 1e12 / fp32_peak) if t_ras else None,

@@ -69,6 +69,9 @@ const char* qed_error_string(int code);
  *  outputs (all [C,N,...]):
  *      radii i32, means2d[.,2], depths, conics[.,3], compensations (NULL unless calc_compensations),
  *      colors_out[.,D], opacities_out (opacity * compensation), tiles_per_gauss i32,
+ *      tiles_exact i32 (NULL to skip): how many of those tiles the Gaussian can reach with alpha >= 1/255 at a pixel centre
+ *      (one interval of tile columns per tile row of the bounding box; conservative) -- the count EXACT tile lists are
+ *      built from: pass it to qed_isect_prepare instead of tiles_per_gauss and geom to qed_isect_fill.
  *      geom[.,8] packed {mx,my,opacity,depth | conic a,b,c, 0} = the record the compositor gathers.
  *  Culled entries (radii == 0) get zeros everywhere.
  */
@@ -78,7 +81,7 @@ int qed_project_fwd(int C, int N, const float* means, const float* quats, const 
                     float eps2d, float near_plane, float far_plane, float radius_clip,
                     int calc_compensations, int tile_size, int n_color, int append_depth,
                     int32_t* radii, float* means2d, float* depths, float* conics, float* compensations,
-                    float* colors_out, float* opacities_out, int32_t* tiles_per_gauss, float* geom,
+                    float* colors_out, float* opacities_out, int32_t* tiles_per_gauss, int32_t* tiles_exact, float* geom,
                     qed_stream_t stream);
 
 /* Backward of qed_project_fwd.
@@ -151,14 +154,14 @@ int qed_sort_pairs_cub(int64_t n, int64_t* keys_in, int32_t* vals_in, int64_t* k
  *            flatten_ids + isect_offsets).
  * `prepare_workspace` must be the buffer qed_isect_prepare filled for the same (C, N).
  *
- * n_exact_dev == NULL (and geom == NULL): gsplat's lists, bit for bit (every tile of each Gaussian's 3-sigma
- *   bounding box; n_isects entries).
- * n_exact_dev != NULL, geom = the packed [C*N,8] records of qed_project_fwd: EXACT tile lists -- every
- *   candidate (Gaussian, tile) is tested with the compositor's own conservative alpha >= 1/255 ellipse test and
- *   dropped if it cannot touch a pixel centre of the tile (about half of them; no pixel changes).  The number of
- *   survivors stays on the device: it is written to n_exact_dev[1] (int64), flatten_ids / isect_ids are filled for
- *   that many entries (buffers sized for n_isects), and isect_offsets must have C*tile_height*tile_width + 1
- *   elements, the last one receiving the end of the last range (pass offsets_has_end = 1 to qed_raster_fwd).
+ * geom == NULL: gsplat's lists, bit for bit (every tile of each Gaussian's 3-sigma bounding box; prepare ran on
+ *   tiles_per_gauss; n_isects entries).
+ * geom != NULL (the packed [C*N,8] records of qed_project_fwd; prepare ran on its tiles_exact): EXACT tile lists -- only
+ *   the (Gaussian, tile) pairs that can reach alpha >= 1/255 at a pixel centre of the tile, about half of gsplat's
+ *   entries, and no pixel changes.  The projection kernel counted them, this call enumerates the same spans: n_visible /
+ *   n_isects are the counts of THAT prepare call.  isect_offsets must have C*tile_height*tile_width + 1 elements, the last
+ *   one receiving the end of the last range (pass offsets_has_end = 1 to qed_raster_fwd).
+ * n_exact_dev (optional, any mode): receives the number of entries written, on the device (int64).
  *
  * counts_dev != NULL (= the counts_dev of qed_isect_prepare): NO host synchronisation is needed between prepare and fill.
  *   n_visible / n_isects are then CAPACITIES (n_visible = C*N is always enough; n_isects = what the caller sized

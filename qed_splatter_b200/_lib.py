@@ -23,7 +23,7 @@ SIGNATURES = {
     "qed_error_string": (ctypes.c_char_p, [c_int]),
     "qed_project_fwd": (c_int, [c_int, c_int, P, P, P, P, c_int, P, c_int, c_int, c_int, P, P, c_int, c_int,
                                 c_float, c_float, c_float, c_float, c_int, c_int, c_int, c_int,
-                                P, P, P, P, P, P, P, P, P, P]),
+                                P, P, P, P, P, P, P, P, P, P, P]),
     "qed_project_bwd": (c_int, [c_int, c_int, P, P, P, P, c_int, P, c_int, c_int, c_int, P, P, c_int, c_int,
                                 c_float, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "qed_pack_geom": (c_int, [c_int, P, P, P, P, P, P]),

@@ -166,40 +166,72 @@ __device__ __forceinline__ bool ellipse_hits_rect(float mx, float my, float A, f
     return !(best > tau2 * 1.01f + 0.03f + 2e-5f * mag);
 }
 
-// Conservative x-extent of {pixel centres (x, y) : Q(mean - (x, y)) <= tau2, ya <= y <= yb}: the part of the alpha >= 1/255
-// ellipse inside one horizontal strip (a tile row).  The set is convex, so a tile of that row can be touched iff its
-// pixel-centre interval [xa, xb] meets [xlo, xhi].  One evaluation serves every tile of a (Gaussian, tile row) pair, where
-// ellipse_hits_rect costs four edge minimisations per tile.  Returns false if the ellipse misses the strip.
+// ---- EXACT tile lists: which tiles of a Gaussian's 3-sigma bounding box can be touched at all -------------------------
+// A Gaussian changes a pixel only if alpha >= 1/255, i.e. the pixel centre lies in the ellipse Q(mean - p) <= tau2,
+// Q = A dx^2 + B dx dy + C dy^2 (the compositor's log2 domain), tau2 = log2(255 opacity).  For one TILE ROW (a horizontal
+// strip ya <= y <= yb of pixel centres) the part of the ellipse inside the strip is convex, so the tiles of that row that
+// can be touched form ONE interval of tile columns [c0, c1):
 //   fixed dy: A dx^2 + B dy dx + C dy^2 - t <= 0  ->  dx in (-B dy -+ sqrt(disc)) / 2A,  disc = 4 A t - det dy^2,  det = 4AC - B^2
 //   the right end dx_hi(dy) is concave with its maximum dxmax = sqrt(4 C t / det) at dy = -B dxmax / 2C, the left end mirrors it.
-// Margins: tau2 is inflated exactly as in ellipse_hits_rect, and the interval is widened by 0.1 px + 0.5 % of the
-// ellipse's half-width (cancellation in det for thin, tilted ellipses).
+// exact_ctx() is evaluated once per Gaussian, exact_row_span() once per (Gaussian, tile row).  The projection kernel SUMS
+// the spans (the exact tile count that is scanned into the list offsets) and the emit kernel ENUMERATES them, so both must
+// produce identical integers: every float operation below is an explicitly rounded intrinsic or a hardware approximation
+// instruction (no contraction, no compiler-dependent reassociation).  Conservative: tau2 is inflated as in
+// ellipse_hits_rect and the interval is widened by 0.1 px + 0.5 % of the ellipse's half-width (cancellation in det for
+// thin, tilted ellipses); the compositor keeps its own per-warp test, so a tile too many costs time, never a pixel.
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
-__device__ __forceinline__ bool ellipse_strip_x_extent(float mx, float my, float A, float B, float C, float tau2, float ya, float yb, float& xlo,
-                                                       float& xhi) {
-    // straight-line code, approximate rcp / rsqrt (relative error ~1e-7, far inside the slack below): ~50 instructions
-    const float t = tau2 * 1.01f + 0.03f;
-    const float det = fmaxf(4.0f * A * C - B * B, 1e-30f);
-    const float rdet = rcp_approx(det);
-    const float ey = 4.0f * A * t * rdet, ex = 4.0f * C * t * rdet;            // squared half-extents of the ellipse in y / x
-    const float dymax = ey * rsqrt_approx(fmaxf(ey, 1e-30f)) * 1.0001f + 1e-3f;  // sqrt(e) = e * rsqrt(e)
-    const float dxmax = ex * rsqrt_approx(fmaxf(ex, 1e-30f));
-    const float dl = fmaxf(my - yb, -dymax), dh = fminf(my - ya, dymax);  // dy = my - y over the strip, cut to the ellipse's y-extent
-    const float dys = -0.5f * B * dxmax * rcp_approx(C);                  // dy of the right extreme point (the left one sits at -dys)
-    const float r2A = 0.5f * rcp_approx(A);
-    const float dy_hi = fminf(fmaxf(dys, dl), dh), dy_lo = fminf(fmaxf(-dys, dl), dh);
-    const float disc_hi = fmaxf(4.0f * A * t - det * dy_hi * dy_hi, 0.0f), disc_lo = fmaxf(4.0f * A * t - det * dy_lo * dy_lo, 0.0f);
-    const float s_hi = disc_hi * rsqrt_approx(fmaxf(disc_hi, 1e-30f)), s_lo = disc_lo * rsqrt_approx(fmaxf(disc_lo, 1e-30f));
-    const float dx_hi = (-B * dy_hi + s_hi) * r2A, dx_lo = (-B * dy_lo - s_lo) * r2A;
-    const float slack = 0.1f + 0.005f * dxmax;
-    xlo = mx - dx_hi - slack;  // x = mx - dx
-    xhi = mx - dx_lo + slack;
-    return (tau2 >= 0.0f) && (dl <= dh);  // opacity < 1/255 can never pass the alpha test; the ellipse may miss the strip
+struct ExactCtx {
+    float mx, my, negB, det, fourAt, dymax, dys, r2A, slack;
+    bool valid;  // false: opacity < 1/255, the Gaussian can never pass the alpha test
+};
+
+__device__ __forceinline__ ExactCtx exact_ctx(float mx, float my, float opacity, float ca, float cb, float cc) {
+    ExactCtx e;
+    const float A = mul(0.5f * kLog2e, ca), B = mul(kLog2e, cb), C = mul(0.5f * kLog2e, cc);
+    const float tau2 = add(lg2_approx(opacity), kLog2_255);
+    const float t = add(mul(tau2, 1.01f), 0.03f);
+    e.valid = tau2 >= 0.0f;
+    e.mx = mx;
+    e.my = my;
+    e.negB = -B;
+    e.det = fmaxf(sub(mul(mul(4.0f, A), C), mul(B, B)), 1e-30f);
+    const float rdet = rcp_approx(e.det);
+    e.fourAt = mul(mul(4.0f, A), t);
+    const float ey = mul(e.fourAt, rdet), ex = mul(mul(mul(4.0f, C), t), rdet);  // squared half-extents in y / x
+    e.dymax = add(mul(mul(ey, rsqrt_approx(fmaxf(ey, 1e-30f))), 1.0001f), 1e-3f);  // sqrt(e) = e * rsqrt(e)
+    const float dxmax = mul(ex, rsqrt_approx(fmaxf(ex, 1e-30f)));
+    e.dys = mul(mul(mul(-0.5f, B), dxmax), rcp_approx(C));  // dy of the right extreme point (the left one sits at -dys)
+    e.r2A = mul(0.5f, rcp_approx(A));
+    e.slack = add(0.1f, mul(0.005f, dxmax));
+    return e;
+}
+
+// tile columns [c0, c1) (inside the bounding box columns [bx0, bx1)) of tile row `ty` that the ellipse can touch; 16-pixel tiles
+__device__ __forceinline__ void exact_row_span(const ExactCtx& e, int ty, int height, int bx0, int bx1, int& c0, int& c1) {
+    const float ya = (float)(ty * 16) + 0.5f, yb = (float)min(ty * 16 + 15, height - 1) + 0.5f;
+    const float dl = fmaxf(sub(e.my, yb), -e.dymax), dh = fminf(sub(e.my, ya), e.dymax);  // dy = my - y over the strip, cut to the ellipse
+    const float dy_hi = fminf(fmaxf(e.dys, dl), dh), dy_lo = fminf(fmaxf(-e.dys, dl), dh);
+    const float disc_hi = fmaxf(sub(e.fourAt, mul(e.det, mul(dy_hi, dy_hi))), 0.0f);
+    const float disc_lo = fmaxf(sub(e.fourAt, mul(e.det, mul(dy_lo, dy_lo))), 0.0f);
+    const float s_hi = mul(disc_hi, rsqrt_approx(fmaxf(disc_hi, 1e-30f))), s_lo = mul(disc_lo, rsqrt_approx(fmaxf(disc_lo, 1e-30f)));
+    const float dx_hi = mul(add(mul(e.negB, dy_hi), s_hi), e.r2A), dx_lo = mul(sub(mul(e.negB, dy_lo), s_lo), e.r2A);
+    const float xlo = sub(sub(e.mx, dx_hi), e.slack), xhi = add(sub(e.mx, dx_lo), e.slack);  // x = mx - dx
+    // tile column tx has pixel centres [16 tx + 0.5, 16 tx + 15.5] (the clipped last column is treated as full: conservative)
+    const float f0 = fminf(fmaxf(ceilf(mul(sub(xlo, 15.5f), 0.0625f)), (float)bx0), (float)bx1);
+    const float f1 = fminf(fmaxf(add(floorf(mul(sub(xhi, 0.5f), 0.0625f)), 1.0f), (float)bx0), (float)bx1);
+    const bool hit = e.valid && (dl <= dh) && (f1 > f0);
+    c0 = (int)f0;
+    c1 = hit ? (int)f1 : c0;
 }
 
 // ---- packed float pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot, two IEEE fp32 results) -------------

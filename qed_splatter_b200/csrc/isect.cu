@@ -277,38 +277,23 @@ __global__ void emit_boundaries_kernel(int64_t n_vis, int64_t n_isects, const in
         n_vis = real_vis < n_vis ? real_vis : n_vis;
         n_isects = real_isects <= n_isects ? real_isects : 0;
         if (n_isects == 0) n_vis = 0;
-        if (j == 0) {
-            clamped[0] = n_vis;
-            clamped[1] = n_isects;
-        }
+    }
+    if (j == 0) {  // the counts the following kernels work with, on the device (also when the host knows them)
+        clamped[0] = n_vis;
+        clamped[1] = n_isects;
     }
     if (j >= n_vis) return;
     const int64_t start = j > 0 ? cum2[j - 1] : 0, end = cum2[j];
     for (int64_t b = (start + kEmitTile - 1) / kEmitTile; b * kEmitTile < end; ++b) first_j[b] = (int32_t)j;
 }
 
-// EXACT = exact tile lists for the compositor (gsplat's own lists hold every tile of the 3-sigma bounding box):
-// every candidate (Gaussian, tile) entry is tested with the compositor's own conservative alpha >= 1/255
-// ellipse test against the tile's pixel-centre rectangle and only survivors are written -- compacted in
-// order at the START of the block's own kEmitTile-slot segment, with the count in seg_counts[block].  There
-// is no global compaction (a decoupled look-back across the ~900 resident blocks cost more than the emit
-// itself): the first pass of the tile sort reads the segments (SegCounts) and scatters densely.  About half
-// of the candidates go (S1: 47 %), which halves the tile sort and the compositor's gather work and changes
-// no pixel: a removed entry cannot pass the alpha test anywhere in its tile.
-struct ExactEmit {
-    const float4* geom;    // [C*N][2]: {mx, my, opacity, depth | conic a, b, c, -}
-    int32_t* seg_counts;   // survivors per block
-    unsigned long long* n_out;  // device scalar: total number of survivors (zeroed by the caller)
-    int width, height;
-};
-
-template <bool EXACT>
+// gsplat's lists: every tile of each Gaussian's 3-sigma bounding box, emitted in depth order.
 __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis, int64_t n_isects, const int64_t* __restrict__ clamped, int N,
                                                                   const int32_t* __restrict__ sorted_vals,
                                                                   const int64_t* __restrict__ cum2, const int32_t* __restrict__ first_j,
                                                                   const float2* __restrict__ means2d, const int32_t* __restrict__ radii,
                                                                   float tile_size, int tile_w, int tile_h, int tile_n_bits,
-                                                                  uint32_t* __restrict__ tkeys, int32_t* __restrict__ tvals, ExactEmit ex) {
+                                                                  uint32_t* __restrict__ tkeys, int32_t* __restrict__ tvals) {
     // per staged Gaussian: the part [lo, hi) of its entries that falls into this block (block-relative), the
     // offset k0 of entry `lo` inside the Gaussian's own tile list, its box and its flat index
     __shared__ int16_t s_lo[kEmitTile + 1], s_hi[kEmitTile + 1];
@@ -324,10 +309,7 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
     if (clamped) {  // device-side counts: the grid covers the capacity, blocks behind the real count have nothing to do
         n_vis = clamped[0];
         n_isects = clamped[1];
-        if (e0 >= n_isects) {
-            if (EXACT && threadIdx.x == 0) ex.seg_counts[vb] = 0;
-            return;
-        }
+        if (e0 >= n_isects) return;
     }
     const int64_t e1 = min(e0 + kEmitTile, n_isects);
     const int64_t j0 = first_j[vb];
@@ -389,163 +371,135 @@ __global__ void __launch_bounds__(kEmitThreads) emit_sorted_kernel(int64_t n_vis
         }
     }
     __syncthreads();
-    if (!EXACT) {
-        for (int t = threadIdx.x; t < (int)(e1 - e0); t += kEmitThreads) {
-            tkeys[e0 + t] = s_okey[t];
-            tvals[e0 + t] = s_oval[t];
-        }
-        return;
-    }
-    // ---- exact lists: test, compact in order, look back for the block offset, write ----
-    constexpr int kPer = kEmitTile / kEmitThreads;  // consecutive entries per thread
-    const int cnt = (int)(e1 - e0);
-    const uint32_t tile_mask = (1u << tile_n_bits) - 1u;
-    static_assert(kPer == 4, "vector loads of the staged entries");
-    uint32_t key[kPer];
-    int32_t val[kPer];
-    {
-        const uint4 kk = reinterpret_cast<const uint4*>(s_okey)[threadIdx.x];
-        const int4 vv = reinterpret_cast<const int4*>(s_oval)[threadIdx.x];
-        key[0] = kk.x, key[1] = kk.y, key[2] = kk.z, key[3] = kk.w;
-        val[0] = vv.x, val[1] = vv.y, val[2] = vv.z, val[3] = vv.w;
-    }
-    const float inv_tile_w = 1.0f / (float)tile_w;
-    int keep = 0, mine = 0;
-    // One strip evaluation per entry, straight-line (all four geometry records are requested before any is used); the
-    // extent of a (Gaussian, tile row) pair is the same for every tile of the row, but a branch that reuses it across a
-    // thread's four entries serialises the loads and measured slower.
-    float4 ga[kPer], gb[kPer];
-#pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-        const int64_t v = threadIdx.x * kPer + k < cnt ? val[k] : 0;  // (slots behind the block's count hold stale shared memory)
-        ga[k] = ex.geom[v * 2];
-        gb[k] = ex.geom[v * 2 + 1];
-    }
-#pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-        const int t = threadIdx.x * kPer + k;
-        const int tile = (int)(key[k] & tile_mask);
-        int ty = (int)(((float)tile + 0.5f) * inv_tile_w);  // exact below 2^22 tiles; corrected below anyway
-        int tx = tile - ty * tile_w;
-        if (tx < 0) {
-            --ty;
-            tx += tile_w;
-        } else if (tx >= tile_w) {
-            ++ty;
-            tx -= tile_w;
-        }
-        const float ya = (float)(ty * (int)tile_size) + 0.5f;
-        const float yb = (float)min(ty * (int)tile_size + (int)tile_size - 1, ex.height - 1) + 0.5f;
-        float xlo, xhi;
-        const bool strip_hit = ellipse_strip_x_extent(ga[k].x, ga[k].y, 0.5f * kLog2e * gb[k].x, kLog2e * gb[k].y, 0.5f * kLog2e * gb[k].z,
-                                                      __log2f(ga[k].z) + kLog2_255, ya, yb, xlo, xhi);
-        const float xa = (float)(tx * (int)tile_size) + 0.5f;
-        const float xb = (float)min(tx * (int)tile_size + (int)tile_size - 1, ex.width - 1) + 0.5f;
-        if (t < cnt && strip_hit && xa <= xhi && xb >= xlo) {
-            keep |= 1 << k;
-            ++mine;
-        }
-    }
-    // exclusive scan of the per-thread counts over the block
-    int inc = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
-    }
-    if (lane == 31) s_wsum[warp] = inc;
-    __syncthreads();  // also: everyone has read its entries from s_okey / s_oval
-    int before = inc - mine, total = 0;
-#pragma unroll
-    for (int w = 0; w < kEmitThreads / 32; ++w) {
-        if (w < warp) before += s_wsum[w];
-        total += s_wsum[w];
-    }
-    if (threadIdx.x == 0) {
-        ex.seg_counts[vb] = total;
-        if (total) atomicAdd(ex.n_out, (unsigned long long)total);
-    }
-#pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-        if ((keep >> k) & 1) {
-            s_okey[before] = key[k];
-            s_oval[before] = val[k];
-            ++before;
-        }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < total; t += kEmitThreads) {
+    for (int t = threadIdx.x; t < (int)(e1 - e0); t += kEmitThreads) {
         tkeys[e0 + t] = s_okey[t];
         tvals[e0 + t] = s_oval[t];
     }
 }
 
-// The exact emit leaves its survivors at the start of every block's own kEmitTile-slot segment.  Two small kernels make
-// the list dense before the tile sort (ncu, 8 M Gaussians at 4K: a first radix pass that walks 154 M half-empty slots took
-// 1.48 ms, the dense pass over the 69.5 M survivors 0.63 ms; the copy costs 1.1 GB of traffic):
-//   seg_offsets_kernel : exclusive scan of the per-segment counts (one block, 8 counts per thread and round)
-//   seg_compact_kernel : one block per segment copies its survivors to their dense position (coalesced both ways)
-constexpr int kSegScanThreads = 1024, kSegScanPer = 8;
-__global__ void __launch_bounds__(kSegScanThreads) seg_offsets_kernel(int64_t nb_cap, const int64_t* __restrict__ clamped, const int32_t* __restrict__ counts,
-                                                                     int32_t* __restrict__ offsets) {
-    __shared__ int s_warp[kSegScanThreads / 32];
-    __shared__ int s_carry;
+// EXACT tile lists for the compositor: only the tiles a Gaussian can reach with alpha >= 1/255 at some pixel centre.
+// The projection kernel already COUNTED them (exact_row_span summed over the rows of the bounding box; that count was
+// scanned into cum2), so this kernel only ENUMERATES the same spans: no per-tile test, no compaction, dense output.
+// About half of gsplat's entries (S1: 53 %) never exist, which halves the tile sort, the range pass and the compositors'
+// gathers and changes no pixel.  Same entry-parallel layout as emit_sorted_kernel: a block owns kEmitTile consecutive
+// output entries and stages the Gaussians that overlap them;
+//   small pieces (<= 32 entries, bounding box <= 8 tile rows): one lane walks the rows of its Gaussian;
+//   large pieces: one warp per Gaussian, 32 rows at a time -- every lane evaluates one row's span, a warp prefix sum
+//   gives the rows' positions in the Gaussian's list and every lane writes its own row's part of the piece.
+__global__ void __launch_bounds__(kEmitThreads) emit_exact_kernel(int64_t n_vis, int64_t n_isects, const int64_t* __restrict__ clamped, int N,
+                                                                 const int32_t* __restrict__ sorted_vals, const int64_t* __restrict__ cum2,
+                                                                 const int32_t* __restrict__ first_j, const float2* __restrict__ means2d,
+                                                                 const int32_t* __restrict__ radii, const float4* __restrict__ geom, int height,
+                                                                 float tile_size, int tile_w, int tile_h, int tile_n_bits,
+                                                                 uint32_t* __restrict__ tkeys, int32_t* __restrict__ tvals) {
+    __shared__ int16_t s_lo[kEmitTile + 1], s_hi[kEmitTile + 1], s_large[kEmitTile + 1];
+    __shared__ int32_t s_k0[kEmitTile + 1], s_idx[kEmitTile + 1];
+    __shared__ __align__(16) uint32_t s_okey[kEmitTile];
+    __shared__ __align__(16) int32_t s_oval[kEmitTile];
+    __shared__ int s_nlarge;
     pdl_enter();
-    const int64_t nb = clamped ? min(nb_cap, (clamped[1] + kEmitTile - 1) / kEmitTile) : nb_cap;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    const uint32_t vb = blockIdx.x;
+    const int64_t e0 = (int64_t)vb * kEmitTile;
+    if (clamped) {
+        n_vis = clamped[0];
+        n_isects = clamped[1];
+    }
+    if (e0 >= n_isects) return;
+    const int64_t e1 = min(e0 + kEmitTile, n_isects);
+    const int64_t j0 = first_j[vb];
+    int64_t j1;  // Gaussian that owns entry e1 - 1
+    if (e1 >= n_isects) {
+        j1 = n_vis - 1;
+    } else {
+        const int64_t jn = first_j[vb + 1];
+        j1 = (jn > 0 && cum2[jn - 1] == e1) ? jn - 1 : jn;
+    }
+    const int G = (int)(j1 - j0) + 1;  // every listed Gaussian has >= 1 entry, so G <= kEmitTile
+    if (threadIdx.x == 0) s_nlarge = 0;
+    // (a count / enumeration mismatch must never leave stale shared memory in the output: keys index the range table)
+    for (int t = threadIdx.x; t < kEmitTile; t += kEmitThreads) {
+        s_okey[t] = 0u;
+        s_oval[t] = 0;
+    }
     __syncthreads();
-    for (int64_t base = 0; base < nb; base += kSegScanThreads * kSegScanPer) {
-        const int64_t i0 = base + (int64_t)threadIdx.x * kSegScanPer;
-        int v[kSegScanPer], sum = 0;
-#pragma unroll
-        for (int k = 0; k < kSegScanPer; ++k) {
-            v[k] = i0 + k < nb ? counts[i0 + k] : 0;
-            sum += v[k];
+    for (int g = threadIdx.x; g < G; g += kEmitThreads) {
+        const int64_t j = j0 + g;
+        const int idx = sorted_vals[j];
+        const float2 m = means2d[idx];
+        const TileBox tb = tile_box(m.x, m.y, radii[idx], tile_size, tile_w, tile_h);
+        const int64_t gs = j > 0 ? cum2[j - 1] : 0, ge = cum2[j];
+        const int64_t lo = max(gs, e0), hi = min(ge, e1);
+        s_lo[g] = (int16_t)(lo - e0);
+        s_hi[g] = (int16_t)(hi - e0);
+        s_k0[g] = (int32_t)(lo - gs);
+        s_idx[g] = idx;
+        if (hi - lo > 32 || tb.y1 - tb.y0 > 8) s_large[atomicAdd(&s_nlarge, 1)] = (int16_t)g;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // small pieces: one lane per Gaussian walks the rows of its bounding box
+    for (int g = threadIdx.x; g < G; g += kEmitThreads) {
+        const int idx = s_idx[g];
+        int pos = s_lo[g], remaining = s_hi[g] - pos, skip = s_k0[g];
+        const float2 m = means2d[idx];
+        const TileBox tb = tile_box(m.x, m.y, radii[idx], tile_size, tile_w, tile_h);
+        if (remaining > 32 || tb.y1 - tb.y0 > 8) continue;
+        const float4 ga = geom[(int64_t)idx * 2], gb = geom[(int64_t)idx * 2 + 1];
+        const ExactCtx ec = exact_ctx(ga.x, ga.y, ga.z, gb.x, gb.y, gb.z);
+        const uint32_t cam_bits = (uint32_t)(idx / N) << tile_n_bits;
+        for (int ty = tb.y0; ty < tb.y1 && remaining > 0; ++ty) {
+            int c0, c1;
+            exact_row_span(ec, ty, height, tb.x0, tb.x1, c0, c1);
+            const int w = c1 - c0;
+            if (skip >= w) {
+                skip -= w;
+                continue;
+            }
+            for (int cx = c0 + skip; cx < c1 && remaining > 0; ++cx) {
+                s_okey[pos] = cam_bits | (uint32_t)(ty * tile_w + cx);
+                s_oval[pos] = idx;
+                ++pos;
+                --remaining;
+            }
+            skip = 0;
         }
-        int inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            const int w = s_warp[lane];
-            int winc = w;
+    }
+    // large pieces: one warp per Gaussian, 32 rows per round
+    const int nlarge = s_nlarge;
+    for (int i = warp; i < nlarge; i += kEmitThreads / 32) {
+        const int g = s_large[i];
+        const int idx = s_idx[g];
+        const int lo = s_lo[g], n = s_hi[g] - lo, k0 = s_k0[g];
+        const float2 m = means2d[idx];
+        const TileBox tb = tile_box(m.x, m.y, radii[idx], tile_size, tile_w, tile_h);
+        const float4 ga = geom[(int64_t)idx * 2], gb = geom[(int64_t)idx * 2 + 1];
+        const ExactCtx ec = exact_ctx(ga.x, ga.y, ga.z, gb.x, gb.y, gb.z);
+        const uint32_t cam_bits = (uint32_t)(idx / N) << tile_n_bits;
+        int base = 0;  // entries of the rows before this round
+        for (int r0 = tb.y0; r0 < tb.y1 && base < k0 + n; r0 += 32) {
+            const int ty = r0 + lane;
+            int c0 = 0, c1 = 0;
+            if (ty < tb.y1) exact_row_span(ec, ty, height, tb.x0, tb.x1, c0, c1);
+            const int w = c1 - c0;
+            int inc = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
             }
-            s_warp[lane] = winc - w;
+            const int row_start = base + inc - w;  // position of this lane's row in the Gaussian's list
+            const int a = max(row_start, k0), b = min(row_start + w, k0 + n);
+            for (int q = a; q < b; ++q) {
+                s_okey[lo + (q - k0)] = cam_bits | (uint32_t)(ty * tile_w + c0 + (q - row_start));
+                s_oval[lo + (q - k0)] = idx;
+            }
+            base += __shfl_sync(0xffffffffu, inc, 31);
         }
-        __syncthreads();
-        int run = s_carry + s_warp[warp] + inc - sum;
-#pragma unroll
-        for (int k = 0; k < kSegScanPer; ++k) {
-            if (i0 + k < nb) offsets[i0 + k] = run;
-            run += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == kSegScanThreads - 1) s_carry = run;
-        __syncthreads();
     }
-}
-
-__global__ void __launch_bounds__(256) seg_compact_kernel(const int64_t* __restrict__ clamped, const int32_t* __restrict__ counts,
-                                                         const int32_t* __restrict__ offsets, const uint32_t* __restrict__ keys_in,
-                                                         const int32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-                                                         int32_t* __restrict__ vals_out) {
-    pdl_enter();
-    const int64_t seg = blockIdx.x;
-    if (clamped && seg * kEmitTile >= clamped[1]) return;
-    const int n = counts[seg];
-    const int64_t src = seg * kEmitTile, dst = offsets[seg];
-    for (int t = threadIdx.x; t < n; t += 256) {
-        keys_out[dst + t] = keys_in[src + t];
-        vals_out[dst + t] = vals_in[src + t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < (int)(e1 - e0); t += kEmitThreads) {
+        tkeys[e0 + t] = s_okey[t];
+        tvals[e0 + t] = s_oval[t];
     }
 }
 
@@ -673,19 +627,21 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     if (counts_dev && !isect_offsets) return QED_ERR_BAD_ARG;
     const int64_t CN = (int64_t)C * N;
     const int n_tiles = tile_width * tile_height;
-    // exact tile lists are requested by passing n_exact_dev (geom may legitimately be NULL for an empty scene):
-    // offsets has C * n_tiles + 1 elements, the count stays on the device
-    const bool exact = n_exact_dev != nullptr;
-    if (exact && (!isect_offsets || image_width <= 0 || image_height <= 0)) return QED_ERR_BAD_ARG;
-    if (exact && n_isects > 0 && CN > 0 && (!geom || (reinterpret_cast<uintptr_t>(geom) & 15))) return QED_ERR_BAD_ARG;
-    if (!exact && geom) return QED_ERR_BAD_ARG;  // geom without n_exact_dev: the caller would not learn the count
+    // exact tile lists (geom != NULL: qed_isect_prepare ran on the EXACT tile counts of qed_project_fwd): offsets has
+    // C * n_tiles + 1 elements; n_exact_dev (optional) receives the entry count on the device
+    const bool exact = geom != nullptr;
+    // (an empty scene has no geom buffer: a caller that passes n_exact_dev still expects the end element)
+    const bool has_end = exact || counts_dev != nullptr || n_exact_dev != nullptr;
+    if (exact && (!isect_offsets || image_width <= 0 || image_height <= 0 || (reinterpret_cast<uintptr_t>(geom) & 15) || tile_size != 16))
+        return QED_ERR_BAD_ARG;
     if (n_isects == 0 || CN == 0) {
         if (isect_offsets && (int64_t)C * n_tiles > 0)
-            QED_CUDA_TRY(cudaMemsetAsync(isect_offsets, 0, ((size_t)C * n_tiles + ((exact || counts_dev) ? 1 : 0)) * 4, stream));
-        if (exact) QED_CUDA_TRY(cudaMemsetAsync(n_exact_dev, 0, 8, stream));
+            QED_CUDA_TRY(cudaMemsetAsync(isect_offsets, 0, ((size_t)C * n_tiles + (has_end ? 1 : 0)) * 4, stream));
+        if (n_exact_dev) QED_CUDA_TRY(cudaMemsetAsync(n_exact_dev, 0, 8, stream));
         return QED_OK;
     }
     if (n_isects > 0x7fffffffLL) return QED_ERR_UNSUPPORTED;
+    if (n_exact_dev && !exact && !counts_dev && !isect_offsets) return QED_ERR_BAD_ARG;
     if (!means2d || !radii || !depths || !prepare_workspace || !workspace || !flatten_ids) return QED_ERR_BAD_ARG;
     if (workspace_bytes < qed_isect_fill_workspace_bytes(n_isects)) return QED_ERR_WORKSPACE;
     const int tile_n_bits = bit_length(n_tiles);
@@ -705,44 +661,25 @@ extern "C" int qed_isect_fill(int C, int N, int64_t n_visible, int64_t n_isects,
     void* hist = ws + 5 * seg;
     const size_t nb = (size_t)((n_isects + kEmitTile - 1) / kEmitTile);
     int32_t* first_j = reinterpret_cast<int32_t*>(ws + 5 * seg + radix_hist_bytes(n_isects));
-    int32_t* seg_counts = reinterpret_cast<int32_t*>(ws + 5 * seg + radix_hist_bytes(n_isects) + align_up((nb + 1) * 4, 256));
-    int64_t* clamped = counts_dev ? reinterpret_cast<int64_t*>(ws + 5 * seg + radix_hist_bytes(n_isects) + align_up((nb + 1) * 4, 256) +
-                                                               align_up((nb + 1) * 8 + 8, 256))
-                                  : nullptr;
+    int64_t* clamped = reinterpret_cast<int64_t*>(ws + 5 * seg + radix_hist_bytes(n_isects) + align_up((nb + 1) * 4, 256));
     if (n_visible == 0) return QED_ERR_BAD_ARG;  // n_isects > 0 needs at least one visible entry (capacity when counts_dev)
     QED_CUDA_TRY(launch_pdl(emit_boundaries_kernel, dim3((unsigned)((n_visible + 255) / 256)), dim3(256), 0, stream, n_visible, n_isects, counts_dev,
                             clamped, cum2, first_j));
-    ExactEmit ex{};
+    const int64_t* cl = counts_dev ? clamped : nullptr;  // kernels take the counts from the device only when the host does not know them
     if (exact) {
-        QED_CUDA_TRY(cudaMemsetAsync(n_exact_dev, 0, 8, stream));
-        ex.geom = reinterpret_cast<const float4*>(geom);
-        ex.seg_counts = seg_counts;
-        ex.n_out = reinterpret_cast<unsigned long long*>(n_exact_dev);
-        ex.width = image_width;
-        ex.height = image_height;
-        QED_CUDA_TRY(launch_pdl(emit_sorted_kernel<true>, dim3((unsigned)nb), dim3(kEmitThreads), 0, stream, n_visible, n_isects, clamped, N, sorted_vals,
-                                cum2, first_j, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width, tile_height,
-                                tile_n_bits, k0, v0, ex));
+        QED_CUDA_TRY(launch_pdl(emit_exact_kernel, dim3((unsigned)nb), dim3(kEmitThreads), 0, stream, n_visible, n_isects, cl, N, sorted_vals, cum2,
+                                first_j, reinterpret_cast<const float2*>(means2d), radii, reinterpret_cast<const float4*>(geom), image_height,
+                                (float)tile_size, tile_width, tile_height, tile_n_bits, k0, v0));
     } else {
-        QED_CUDA_TRY(launch_pdl(emit_sorted_kernel<false>, dim3((unsigned)nb), dim3(kEmitThreads), 0, stream, n_visible, n_isects, clamped, N, sorted_vals,
-                                cum2, first_j, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width, tile_height,
-                                tile_n_bits, k0, v0, ex));
+        QED_CUDA_TRY(launch_pdl(emit_sorted_kernel, dim3((unsigned)nb), dim3(kEmitThreads), 0, stream, n_visible, n_isects, cl, N, sorted_vals, cum2,
+                                first_j, reinterpret_cast<const float2*>(means2d), radii, (float)tile_size, tile_width, tile_height, tile_n_bits,
+                                k0, v0));
     }
-    const int64_t* n_dev = exact ? n_exact_dev : (clamped ? clamped + 1 : nullptr);
-    int rc;
-    if (exact) {
-        // survivors sit at the start of every emit block's segment: make the list dense (k2 / v2), then sort it
-        int32_t* seg_offsets = seg_counts + (nb + 1);
-        QED_CUDA_TRY(launch_pdl(seg_offsets_kernel, dim3(1), dim3(kSegScanThreads), 0, stream, (int64_t)nb, (const int64_t*)clamped,
-                                (const int32_t*)seg_counts, seg_offsets));
-        QED_CUDA_TRY(launch_pdl(seg_compact_kernel, dim3((unsigned)nb), dim3(256), 0, stream, (const int64_t*)clamped, (const int32_t*)seg_counts,
-                                (const int32_t*)seg_offsets, (const uint32_t*)k0, (const int32_t*)v0, k2, v2));
-        rc = radix_sort_pairs<uint32_t>(n_isects, n_dev, k2, v2, k1, flatten_ids, k0, v0, hist, tile_n_bits + cam_bits, stream);
-    } else {
-        rc = radix_sort_pairs<uint32_t>(n_isects, n_dev, k0, v0, k1, flatten_ids, k2, v2, hist, tile_n_bits + cam_bits, stream);
-    }
+    const int64_t* n_dev = has_end ? clamped + 1 : nullptr;  // (always written by emit_boundaries_kernel)
+    int rc = radix_sort_pairs<uint32_t>(n_isects, n_dev, k0, v0, k1, flatten_ids, k2, v2, hist, tile_n_bits + cam_bits, stream);
     if (rc != QED_OK) return rc;
     QED_CUDA_TRY(launch_pdl(compose_ids_ranges_kernel, dim3((unsigned)((n_isects + 256 * kComposePer - 1) / (256 * kComposePer))), dim3(256), 0, stream,
                             n_isects, n_dev, k1, flatten_ids, depths, C, n_tiles, tile_n_bits, isect_ids, isect_offsets));
+    if (n_exact_dev) QED_CUDA_TRY(cudaMemcpyAsync(n_exact_dev, clamped + 1, 8, cudaMemcpyDeviceToDevice, stream));
     return QED_OK;
 }

@@ -39,6 +39,7 @@ struct ProjFwdParams {
     int32_t* radii;
     float *means2d, *depths, *conics, *comps, *colors_out, *opac_out;
     int32_t* tiles;
+    int32_t* tiles_exact;  // optional: tiles that can be reached with alpha >= 1/255 (sum of exact_row_span over the bounding box rows)
     float* geom;
 };
 
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
         keep = keep && (add(mx, radius) > 0.0f) && (sub(mx, radius) < (float)p.width) &&
                (add(my, radius) > 0.0f) && (sub(my, radius) < (float)p.height);
         float ca = 0, cb = 0, cc = 0, comp = 0, o = 0;
-        int ri = 0, ntiles = 0;
+        int ri = 0, ntiles = 0, nexact = 0;
         if (keep) {
             ca = dvd(c11b, det);
             cb = dvd(-c01, det);
@@ -239,6 +240,16 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
             ri = (int)radius;
             TileBox tb = tile_box(mx, my, ri, p.tile_size, p.tile_w, p.tile_h);
             ntiles = (tb.x1 - tb.x0) * (tb.y1 - tb.y0);
+            if (p.tiles_exact) {
+                // the tiles this Gaussian can reach with alpha >= 1/255: one column interval per tile row of the bounding box
+                // (common.cuh, exact_row_span); the intersection stage enumerates exactly these spans from the same floats
+                const ExactCtx ec = exact_ctx(mx, my, o, ca, cb, cc);
+                for (int ty_ = tb.y0; ty_ < tb.y1; ++ty_) {
+                    int c0, c1;
+                    exact_row_span(ec, ty_, p.height, tb.x0, tb.x1, c0, c1);
+                    nexact += c1 - c0;
+                }
+            }
             vismask |= (1u << ci);
         } else {
             mx = 0;
@@ -247,6 +258,7 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
         }
         p.radii[idx] = ri;
         p.tiles[idx] = ntiles;
+        if (p.tiles_exact) p.tiles_exact[idx] = nexact;
         reinterpret_cast<float2*>(p.means2d)[idx] = make_float2(mx, my);
         p.depths[idx] = pz;
         p.conics[idx * 3 + 0] = ca;
@@ -386,7 +398,7 @@ extern "C" int qed_project_fwd(int C, int N, const float* means, const float* qu
                                float eps2d, float near_plane, float far_plane, float radius_clip,
                                int calc_compensations, int tile_size, int n_color, int append_depth,
                                int32_t* radii, float* means2d, float* depths, float* conics, float* compensations,
-                               float* colors_out, float* opacities_out, int32_t* tiles_per_gauss, float* geom,
+                               float* colors_out, float* opacities_out, int32_t* tiles_per_gauss, int32_t* tiles_exact, float* geom,
                                qed_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (C < 0 || N < 0 || width <= 0 || height <= 0 || tile_size <= 0) return QED_ERR_BAD_ARG;
@@ -437,6 +449,8 @@ extern "C" int qed_project_fwd(int C, int N, const float* means, const float* qu
     p.colors_out = colors_out;
     p.opac_out = opacities_out;
     p.tiles = tiles_per_gauss;
+    p.tiles_exact = tiles_exact;
+    if (tiles_exact && tile_size != 16) return QED_ERR_UNSUPPORTED;
     p.geom = geom;
 
     const bool vec_ok = sh_degree >= 0 && ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(colors_in) & 15) == 0);

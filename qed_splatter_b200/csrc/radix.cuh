@@ -35,11 +35,19 @@ __global__ void __launch_bounds__(kSortThreads) radix_upsweep_kernel(int64_t n_h
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
     if (base < n) {
-#pragma unroll 4
+        // all of the tile's keys are requested before the first shared-memory atomic (ncu at 70 M pairs: 23 % issue-active,
+        // long_scoreboard 44 cycles per issue with the loads interleaved four at a time)
+        KeyT key[kSortItems];
+        bool ok[kSortItems];
+#pragma unroll
         for (int k = 0; k < kSortItems; ++k) {
-            int64_t i = base + k * kSortThreads + threadIdx.x;
-            if (i < n && (!SEG || seg.ok(i))) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & mask], 1u);
+            const int64_t i = base + k * kSortThreads + threadIdx.x;
+            ok[k] = i < n && (!SEG || seg.ok(i));
+            key[k] = ok[k] ? keys[i] : (KeyT)0;
         }
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k)
+            if (ok[k]) atomicAdd(&sh[(uint32_t)(key[k] >> shift) & mask], 1u);
     }
     __syncthreads();
     hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = sh[threadIdx.x];

@@ -83,24 +83,27 @@ class _ProjectGaussians(torch.autograd.Function):
         colors_out = torch.empty(C, N, D, device=dev)
         opac_out = torch.empty(C, N, device=dev)
         tiles = torch.empty(C, N, dtype=torch.int32, device=dev)
+        tiles_exact = torch.empty(C, N, dtype=torch.int32, device=dev) if tile_size == 16 else None
         geom = torch.empty(C, N, GEOM_FLOATS, device=dev)
         check(lib.qed_project_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), 0, ptr(colors) if n_color else None,
                                   K, sh_degree, per_cam, ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane,
                                   far_plane, radius_clip, int(calc_compensations), tile_size, n_color, append_depth,
                                   ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), ptr(colors_out),
-                                  ptr(opac_out), ptr(tiles), ptr(geom), current_stream()), "qed_project_fwd")
+                                  ptr(opac_out), ptr(tiles), ptr(tiles_exact), ptr(geom), current_stream()), "qed_project_fwd")
         ctx.save_for_backward(means, quats, scales, opacities, colors, viewmats, Ks, radii, conics, comps)
         ctx.cfg = (width, height, eps2d, calc_compensations, sh_degree, n_color, append_depth, K, per_cam)
-        ctx.mark_non_differentiable(radii, tiles, geom)
+        if tiles_exact is None:
+            tiles_exact = torch.empty(0, dtype=torch.int32, device=dev)
+        ctx.mark_non_differentiable(radii, tiles, geom, tiles_exact)
         if comps is None:
             comps_out = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(comps_out)
         else:
             comps_out = comps
-        return radii, means2d, depths, conics, comps_out, colors_out, opac_out, tiles, geom
+        return radii, means2d, depths, conics, comps_out, colors_out, opac_out, tiles, geom, tiles_exact
 
     @staticmethod
-    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_colors, v_opac, _v_tiles, _v_geom):
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_comps, v_colors, v_opac, _v_tiles, _v_geom, _v_tiles_exact):
         lib = _lib.load()
         means, quats, scales, opacities, colors, viewmats, Ks, radii, conics, comps = ctx.saved_tensors
         width, height, eps2d, calc_comp, sh_degree, n_color, append_depth, K, per_cam = ctx.cfg
@@ -130,7 +133,8 @@ def project_gaussians(means: Tensor, quats: Tensor, scales: Tensor, opacities: T
     """Fused fully_fused_projection + spherical_harmonics (+ clamp_min(c+0.5), depth concat, opacity*comp).
 
     -> radii[C,N] i32, means2d[C,N,2], depths[C,N], conics[C,N,3], compensations[C,N]|None,
-       colors[C,N,D], opacities[C,N], tiles_per_gauss[C,N] i32, geom[C,N,8]
+       colors[C,N,D], opacities[C,N], tiles_per_gauss[C,N] i32, geom[C,N,8], tiles_exact[C,N] i32 (the tiles each Gaussian
+       can reach with alpha >= 1/255: what `isect_tiles_exact` builds the compositor's lists from)
     """
     if colors is None:
         colors = torch.empty(0, device=means.device)
@@ -139,8 +143,8 @@ def project_gaussians(means: Tensor, quats: Tensor, scales: Tensor, opacities: T
                                   float(eps2d), float(near_plane), float(far_plane), float(radius_clip),
                                   bool(calc_compensations), -1 if sh_degree is None else int(sh_degree), int(n_color),
                                   int(bool(append_depth)), int(tile_size))
-    radii, means2d, depths, conics, comps, colors_out, opac_out, tiles, geom = out
-    return radii, means2d, depths, conics, (comps if calc_compensations else None), colors_out, opac_out, tiles, geom
+    radii, means2d, depths, conics, comps, colors_out, opac_out, tiles, geom, tiles_exact = out
+    return radii, means2d, depths, conics, (comps if calc_compensations else None), colors_out, opac_out, tiles, geom, tiles_exact
 
 
 def fully_fused_projection(means: Tensor, covars, quats: Tensor, scales: Tensor, viewmats: Tensor, Ks: Tensor,
@@ -151,7 +155,7 @@ def fully_fused_projection(means: Tensor, covars, quats: Tensor, scales: Tensor,
     if covars is not None or packed or sparse_grad:
         raise NotImplementedError("covars / packed / sparse_grad are not reachable from qed_splatter/model.py:267-288")
     opac = torch.ones(means.shape[0], device=means.device)
-    radii, means2d, depths, conics, comps, _, _, _, _ = project_gaussians(
+    radii, means2d, depths, conics, comps, _, _, _, _, _ = project_gaussians(
         means, quats, scales, opac, None, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
         calc_compensations, None, 0, True)
     return radii, means2d, depths, conics, comps
@@ -250,10 +254,10 @@ _CAPACITY_HINT = {}
 
 @torch.no_grad()
 def isect_tiles_exact(means2d: Tensor, radii: Tensor, depths: Tensor, geom: Tensor, width: int, height: int, tile_size: int,
-                      tile_width: int, tile_height: int, tiles_per_gauss: Tensor, defer: bool = False):
-    """EXACT tile lists for the compositor (not gsplat's `info` lists): every (Gaussian, tile) candidate of gsplat's
-    bounding-box lists that cannot reach alpha = 1/255 at a pixel centre of the tile is dropped before the tile sort
-    (DESIGN.md section 5).  -> flatten_ids[M] i32 (M >= gsplat's count; only the first n_exact entries are filled),
+                      tile_width: int, tile_height: int, tiles_exact: Tensor, defer: bool = False):
+    """EXACT tile lists for the compositor (not gsplat's `info` lists): only the (Gaussian, tile) pairs that can reach
+    alpha = 1/255 at a pixel centre of the tile -- `tiles_exact` = their per-Gaussian counts from `project_gaussians`
+    (DESIGN.md section 5).  -> flatten_ids[M] i32 (M = capacity >= n_exact; the first n_exact entries are filled),
     isect_offsets[C*th*tw + 1] i32 (last element = n_exact = end of the last range), n_exact[1] i64 on the device,
     resolve.
 
@@ -275,7 +279,7 @@ def isect_tiles_exact(means2d: Tensor, radii: Tensor, depths: Tensor, geom: Tens
     cap = _CAPACITY_HINT.get(key, 0) if defer else 0
     deferred = cap > 0 and C * N > 0
     counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True) if deferred else None
-    check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles_per_gauss), ptr(pws), pws_bytes, ptr(counts), ptr(counts_host), stream),
+    check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles_exact), ptr(pws), pws_bytes, ptr(counts), ptr(counts_host), stream),
           "qed_isect_prepare")
     resolve = None
     if deferred:

@@ -123,20 +123,23 @@ class FusedSplatStep:
         colors = self._get("colors", (C, N, D))
         opac = self._get("opac", (C, N))
         tiles = self._get("tiles", (C, N), torch.int32)
+        exact = self.exact_tile_lists and self.sort_impl == "two_level"
+        # exact tile lists: the projection counts the tiles each Gaussian can reach with alpha >= 1/255, the intersection
+        # stage enumerates exactly those (its sizes / capacities then refer to the exact lists)
+        tiles_exact = self._get("tiles_exact", (C, N), torch.int32) if exact else None
         geom = self._get("geom", (C, N, 8))
         check(lib.qed_project_fwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), int(activations), ptr(sh) if want_rgb else None, K, deg,
                                   int(want_rgb and sh_degree is None and sh.dim() == 3), ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane,
                                   far_plane, 0.0, int(comp), tile, n_color, append, ptr(radii), ptr(means2d), ptr(depths),
-                                  ptr(conics), ptr(comps), ptr(colors), ptr(opac), ptr(tiles), ptr(geom), stream), "qed_project_fwd")
+                                  ptr(conics), ptr(comps), ptr(colors), ptr(opac), ptr(tiles), ptr(tiles_exact), ptr(geom), stream), "qed_project_fwd")
         self._mark("project_fwd")
         CN = C * N
-        # exact tile lists: one more element (the end of the last range), the entry count stays on the device
-        exact = self.exact_tile_lists and self.sort_impl == "two_level"
+        # exact tile lists / deferred sizes: one more element (the end of the last range)
         offsets = self._get("offsets", (C * th * tw + 1,), torch.int32)
         if self.sort_impl == "two_level":
             pws_bytes = lib.qed_isect_prepare_workspace_bytes(CN)
             pws = self._get("prep_ws", (pws_bytes,), torch.uint8)
-            check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles), ptr(pws), pws_bytes, ptr(self._counts), ptr(self._counts_host), stream),
+            check(lib.qed_isect_prepare(C, N, ptr(depths), ptr(tiles_exact if exact else tiles), ptr(pws), pws_bytes, ptr(self._counts), ptr(self._counts_host), stream),
                   "qed_isect_prepare")
             self._mark("isect_prepare")
             # the single host sync of the step (output sizes) waits on an EVENT behind the counts' copy, not on the
@@ -381,9 +384,8 @@ class FusedSplatStep:
         """Launches of THIS library's kernels in one step() (memsets and torch's own fill kernels not counted):
         project 1; intersections two_level: flag scan 3 (its last phase compacts) + Gaussian sort + gather scan 3 +
         emit boundaries 1 + emit 1 + tile sort + compose/ranges 1 (a radix sort is 1 histogram + 1 kernel per 8-bit
-        pass when it fits 444 blocks of 4096 pairs, else 3 kernels per pass; the segmented sort behind the exact emit
-        always takes 3 per pass); own/cub: scan 3 + emit 1 + sort + ranges 1; composite fwd 1, loss 3 (+2 with SSIM),
-        composite bwd 1, project bwd 1.  Cross-checked against the ncu launch list (profiles/r01_launches_bench.csv)."""
+        pass when it fits 444 blocks of 4096 pairs, else 3 kernels per pass); own/cub: scan 3 + emit 1 + sort + ranges 1; composite fwd 1, loss 3 (+2 with SSIM),
+        composite bwd 1, project bwd 1.  Cross-checked against the ncu launch list (profiles/r02_step_ncu_summary.txt)."""
         f = self._fwd
         tile_bits = (f["tw"] * f["th"]).bit_length()
         cam_bits = (f["C"] - 1).bit_length()
@@ -394,7 +396,7 @@ class FusedSplatStep:
             return 1 + passes if one_kernel_passes else 3 * passes
 
         if self.sort_impl == "two_level":
-            isect = 3 + radix(f["C"] * f["N"], 32 + cam_bits) + 3 + 1 + 1 + radix(f["M"], tile_bits + cam_bits, bool(f.get("exact"))) + 1
+            isect = 3 + radix(f["C"] * f["N"], 32 + cam_bits) + 3 + 1 + 1 + radix(f["M"], tile_bits + cam_bits) + 1
         else:
             end_bit = 32 + tile_bits + f["C"].bit_length()
             isect = 3 + 1 + (radix(f["M"], end_bit) if self.sort_impl == "own" else 8) + 1

@@ -132,7 +132,7 @@ def rasterization(
     want_depth = render_mode in ("D", "ED", "RGB+D", "RGB+ED")
     normalize = render_mode in ("ED", "RGB+ED")
 
-    radii, means2d, depths, conics, comps, cols, opac, tiles_per_gauss, geom = ops.project_gaussians(
+    radii, means2d, depths, conics, comps, cols, opac, tiles_per_gauss, geom, tiles_exact = ops.project_gaussians(
         means, quats, scales, opacities, colors if want_rgb else None, viewmats, Ks, width, height, eps2d=eps2d,
         near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip,
         calc_compensations=(rasterize_mode == "antialiased"), sh_degree=sh_degree, n_color=3 if want_rgb else 0,
@@ -144,7 +144,7 @@ def rasterization(
     # (sizes of the lists live on the device: from the second call with these shapes on they are read only after the
     # compositor has been queued -- `resolve` -- so the device does not idle on the host)
     flatten_ids, isect_offsets, _, resolve = ops.isect_tiles_exact(means2d, radii, depths, geom, width, height, tile_size, tile_width,
-                                                                   tile_height, tiles_per_gauss, defer=True)
+                                                                   tile_height, tiles_exact, defer=True)
 
     def gsplat_lists(m=means2d.detach(), r=radii, d=depths.detach(), t=tiles_per_gauss):
         return ops.isect_tiles(m, r, d, tile_size, tile_width, tile_height, tiles_per_gauss=t, return_offsets=True)[1:]
@@ -165,7 +165,7 @@ def rasterization(
         # the lists did not fit the buffers sized from earlier calls (the device built empty ones): rebuild with the sizes
         # now known and composite again (rare: first frames of a new viewpoint / after densification)
         flatten_ids, isect_offsets, _, _ = ops.isect_tiles_exact(means2d, radii, depths, geom, width, height, tile_size, tile_width,
-                                                                 tile_height, tiles_per_gauss, defer=False)
+                                                                 tile_height, tiles_exact, defer=False)
         render_colors, render_alphas = ops.rasterize_to_pixels(
             means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
             absgrad=absgrad, geom=geom, normalize_last=normalize)

@@ -40,11 +40,11 @@ def _setup(name, cuda):
     cols_o = torch.clamp_min(oracle.spherical_harmonics(3, dirs, s.sh[None], masks=radii_o > 0) + 0.5, 0.0)
     cols_o = torch.cat([cols_o, depths_o[..., None]], dim=-1)
     g = {k: getattr(s, k).to(cuda) for k in ("means", "quats", "scales", "opacities", "sh", "viewmats", "Ks")}
-    radii, means2d, depths, conics, _, cols, opac, tiles, geom = ops.project_gaussians(
+    radii, means2d, depths, conics, _, cols, opac, tiles, geom, tiles_exact = ops.project_gaussians(
         g["means"], g["quats"], g["scales"], g["opacities"], g["sh"], g["viewmats"], g["Ks"], s.width, s.height, sh_degree=3, n_color=3,
         append_depth=True)
     out = dict(s=s, o=dict(radii=radii_o, means2d=means2d_o, depths=depths_o, conics=conics_o, cols=cols_o, opac=s.opacities[None].contiguous()),
-               g=dict(radii=radii, means2d=means2d, depths=depths, conics=conics, cols=cols, opac=opac, tiles=tiles, geom=geom))
+               g=dict(radii=radii, means2d=means2d, depths=depths, conics=conics, cols=cols, opac=opac, tiles=tiles, geom=geom, tiles_exact=tiles_exact))
     _cache[name] = out
     return out
 
@@ -98,7 +98,8 @@ def test_sampled_tiles_forward_backward_match_oracle_at_full_size(cuda, name, li
     tw, th = ops.tile_grid(W, H, TILE)
     n_tiles = tw * th
     if lists == "exact":
-        flat, offsets, n_exact, _ = ops.isect_tiles_exact(g["means2d"], g["radii"], g["depths"], g["geom"], W, H, TILE, tw, th, g["tiles"])
+        flat, offsets, n_exact, _ = ops.isect_tiles_exact(g["means2d"], g["radii"], g["depths"], g["geom"], W, H, TILE, tw, th, g["tiles_exact"])
+        assert flat.numel() == int(n_exact.item()) == int(g["tiles_exact"].sum())
         bounds = offsets.cpu().long()
         assert int(bounds[-1]) == int(n_exact.item())
     else:

@@ -31,7 +31,7 @@ def test_projection_bit_exact(cuda, deg):
     s.means = s.means * 2.5  # spread the scene so a good share of the Gaussians is culled (behind / off-screen)
     r_o, m_o, d_o, c_o, _, col_o = _project_oracle(s, deg)
     g = s.to(cuda)
-    radii, means2d, depths, conics, comps, cols, opac, tiles, geom = ops.project_gaussians(
+    radii, means2d, depths, conics, comps, cols, opac, tiles, geom, tiles_exact = ops.project_gaussians(
         g.means, g.quats, g.scales, g.opacities, g.sh, g.viewmats, g.Ks, g.width, g.height, sh_degree=deg)
     assert torch.equal(radii.cpu(), r_o), "radii must be bit-exact"
     vis = r_o > 0
@@ -58,7 +58,7 @@ def test_projection_antialiased_and_passthrough(cuda):
     r_o, m_o, d_o, c_o, comp_o, _ = _project_oracle(s, 0, comp=True)
     g = s.to(cuda)
     rgb = torch.rand(s.N, 3, generator=torch.Generator().manual_seed(1))
-    radii, means2d, depths, conics, comps, cols, opac, tiles, geom = ops.project_gaussians(
+    radii, means2d, depths, conics, comps, cols, opac, tiles, geom, tiles_exact = ops.project_gaussians(
         g.means, g.quats, g.scales, g.opacities, rgb.to(cuda), g.viewmats, g.Ks, g.width, g.height,
         calc_compensations=True, sh_degree=None)
     vis = r_o > 0
@@ -91,7 +91,7 @@ def test_projection_backward(cuda, deg, comp):
     gl = [t.detach().to(cuda).requires_grad_(True) for t in (s.means, s.quats, s.scales, s.opacities, s.sh)]
     out = ops.project_gaussians(gl[0], gl[1], gl[2], gl[3], gl[4], g.viewmats, g.Ks, g.width, g.height,
                                 calc_compensations=comp, sh_degree=deg)
-    radii_g, m2g, depg, cong, _, colg, opg, _, _ = out
+    radii_g, m2g, depg, cong, _, colg, opg, _, _, _ = out
     assert torch.equal(radii_g.cpu(), radii)
     visg = vis.to(cuda)
     wg = [t.to(cuda) for t in w]
@@ -243,7 +243,7 @@ def test_isect_full_size_paths_agree(cuda):
     from qed_splatter_b200.scenes import scene_s1
 
     s = scene_s1(N=1_000_000, targets=False).to(cuda)
-    radii, means2d, depths, conics, comps, cols, opac, tiles, geom = ops.project_gaussians(
+    radii, means2d, depths, conics, comps, cols, opac, tiles, geom, tiles_exact = ops.project_gaussians(
         s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, s.width, s.height, sh_degree=3)
     tw, th = ops.tile_grid(s.width, s.height, 16)
     res = {impl: ops.isect_tiles(means2d, radii, depths, 16, tw, th, tiles_per_gauss=tiles, impl=impl) for impl in ops.SORT_IMPLS}

@@ -201,7 +201,7 @@ def test_exact_tile_lists(cuda, size, scale):
         res[exact] = dict(render=out.render.clone(), alphas=out.alphas.clone(), loss=out.loss.clone(), grads={k: v.clone() for k, v in out.grads.items()},
                           flat=f["flat"][:n].tolist(), off=off, n=n, M=out.n_isects, geom=f["geom"].clone(), tw=f["tw"], th=f["th"])
     a, b = res[False], res[True]
-    assert a["n"] == a["M"] == b["M"] and 0 < b["n"] < a["n"]
+    assert a["n"] == a["M"] and b["n"] == b["M"] and 0 < b["n"] < a["n"]
     assert torch.equal(a["render"], b["render"]) and torch.equal(a["alphas"], b["alphas"]) and torch.equal(a["loss"], b["loss"])
     for k in a["grads"]:
         sc = float(a["grads"][k].abs().mean()) + 1e-12
@@ -375,7 +375,7 @@ def test_deferred_size_read_equals_synchronous_path_and_survives_overflow(cuda, 
     second = run(defer, small)      # deferred
     assert defer._cap_isects > 0 and defer.overflow_repeats == 0
     third = run(defer, big)         # deferred, overflows, repeated
-    assert defer.overflow_repeats == 1 and ref_big[4] > 4 * ref_small[4]
+    assert defer.overflow_repeats == 1 and ref_big[4] > ref_small[4] + ref_small[4] // 4 + 4096  # did not fit the capacity learnt from `small`
     fourth = run(defer, big)        # deferred, fits now
     assert defer.overflow_repeats == 1
     for got, ref in ((first, ref_small), (second, ref_small), (third, ref_big), (fourth, ref_big)):
