@@ -82,6 +82,8 @@ def parse_args():
     ap.add_argument("--comm", default="exchange", choices=["exchange", "nccl"],
                     help="N>1, how the gradient arena is summed over the ranks: this library's NVLink path (view-colour exchange + one "
                          "all-reduce kernel, comm.ViewShardedGradients) or torch.distributed / NCCL all-reduce (the library baseline)")
+    ap.add_argument("--radix-onesweep", type=int, default=None, choices=[0, 1, 2],
+                    help="A/B hook: 0 = three kernels per radix pass everywhere, 1 = look-back passes for sorts of <= 444 blocks (library default), 2 = everywhere")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-bucket", action="store_true", help="e2e, N>1: all-reduce one flat bucket of gradient views instead of a coalesced group call")
@@ -427,6 +429,8 @@ def main_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    if args.radix_onesweep is not None:
+        lib.qed_debug_set_radix_onesweep(args.radix_onesweep)
     K, W_ = args.steps, max(args.warmup, 3)
     width, height, N = args.width, args.height, args.gaussians
 
