@@ -63,6 +63,7 @@ DEBUG_SIGNATURES = {
     "qed_debug_set_raster_counters": (c_int, [P]),
     "qed_debug_set_raster_px": (c_int, [c_int, c_int]),
     "qed_debug_set_raster_packed": (c_int, [c_int]),
+    "qed_debug_set_raster_bwd_minb": (c_int, [c_int]),
     "qed_debug_set_radix_onesweep": (c_int, [c_int]),
 }
 

@@ -27,6 +27,8 @@
 //     packed [C*N,12] record.
 // The scalar kernels (raster_fwd_kernel / raster_bwd_kernel: CTA-staged, 1/2/4 pixels per lane, shuffle
 // butterfly) are kept as the cross-check the packed ones are tested against (qed_debug_set_raster_packed).
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace qed {
@@ -348,6 +350,11 @@ struct WarpStream {
     float4 qa[32], qb[32], qc[32];           // queue of the batch being composited (see Staging)
     int qm[32];
 };
+// A loop-invariant per-lane value that ptxas would otherwise re-derive (S2R / I2FP / address arithmetic) inside the
+// inner loop when registers are tight: routed through a self-shuffle it cannot be rematerialised, so it stays in a register.
+__device__ __forceinline__ float pin_reg(float x) { return __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
+__device__ __forceinline__ unsigned pin_reg(unsigned x) { return __shfl_sync(0xffffffffu, x, threadIdx.x & 31); }
+
 template <int D>
 __device__ __forceinline__ void stream_fetch(const RasterParams& p, WarpStream& ws, int buf, int lane, bool have, int g) {
     if (have) {
@@ -369,6 +376,24 @@ __device__ __forceinline__ void stream_fetch(const RasterParams& p, WarpStream& 
 // ------------------------------------------------------------------------------------------------
 // `thr` is the per-pixel alpha threshold: 1/255 while the pixel is live, 2 (never reached) once it is opaque
 // or outside the image -- "live" costs no instruction in the test.
+// One pixel's accept / stop decision of the forward, as a chain of predicated compares (the C++ formulation compiles to
+// ~8.5 compare / select / predicate-logic instructions per pixel, this is 6):
+//   ok = (am >= thr) && (pw <= lo);  upd = ok && (nT > 1e-4);  al = upd ? am : 0;  last = upd ? sid : last;
+//   thr = (ok && !upd) ? 2 : thr     (stop: the pixel is opaque, no later Gaussian passes `am >= 2`)
+__device__ __forceinline__ float fwd_accept(float am, float pw, float lo, float nT, int sid, float& thr, int32_t& last) {
+    float al;
+    asm("{\n\t.reg .pred ok, upd;\n\t"
+        "setp.ge.f32 ok, %3, %1;\n\t"
+        "setp.le.and.f32 ok, %4, %5, ok;\n\t"
+        "setp.gt.and.f32 upd, %6, 0f38D1B717, ok;\n\t"  // kTransmittanceThreshold
+        "selp.f32 %0, %3, 0f00000000, upd;\n\t"
+        "selp.b32 %2, %7, %2, upd;\n\t"
+        "@ok selp.f32 %1, %1, 0f40000000, upd;\n\t}"
+        : "=f"(al), "+f"(thr), "+r"(last)
+        : "f"(am), "f"(pw), "f"(lo), "f"(nT), "r"(sid));
+    return al;
+}
+
 template <int D, bool STATS>
 __device__ __forceinline__ void fwd_pk_block(int a, const float4& A, const float4& B, const float4& Cc, float px0, f32x2 dy2, f32x2 t2,
                                              f32x2 cy2, f32x2& T2, f32x2 (&acc2)[D], int32_t (&last)[2], float (&thr)[2],
@@ -378,23 +403,31 @@ __device__ __forceinline__ void fwd_pk_block(int a, const float4& A, const float
     const f32x2 pw2 = fma2(add2(t2, bc2(ax)), bc2(dx), cy2);  // log2(opacity * exp(-sigma))
     const float pw0 = lo2(pw2), pw1 = hi2(pw2);
     const float am0 = fminf(kMaxAlpha, ex2_approx(pw0)), am1 = fminf(kMaxAlpha, ex2_approx(pw1));
-    const bool ok0 = (pw0 <= A.z) && (am0 >= thr[0]);  // pw <= lo  <=>  sigma >= 0
-    const bool ok1 = (pw1 <= A.z) && (am1 >= thr[1]);
     const f32x2 nT2 = mul2(T2, sub2(bc2(1.0f), pk2(am0, am1)));
-    const bool stop0 = ok0 && (lo2(nT2) <= kTransmittanceThreshold), stop1 = ok1 && (hi2(nT2) <= kTransmittanceThreshold);
-    const bool upd0 = ok0 && !stop0, upd1 = ok1 && !stop1;
-    st.add(3, (thr[0] < 1.0f ? 1 : 0) + (thr[1] < 1.0f ? 1 : 0));
-    st.add(4, (upd0 ? 1 : 0) + (upd1 ? 1 : 0));
-    const f32x2 al2 = pk2(upd0 ? am0 : 0.0f, upd1 ? am1 : 0.0f);  // alpha = 0: the pixel skips this Gaussian
+    const int sid = __float_as_int(A.w);
+    float al0, al1;
+    if (STATS) {
+        const bool ok0 = (pw0 <= A.z) && (am0 >= thr[0]);  // pw <= lo  <=>  sigma >= 0
+        const bool ok1 = (pw1 <= A.z) && (am1 >= thr[1]);
+        const bool stop0 = ok0 && (lo2(nT2) <= kTransmittanceThreshold), stop1 = ok1 && (hi2(nT2) <= kTransmittanceThreshold);
+        const bool upd0 = ok0 && !stop0, upd1 = ok1 && !stop1;
+        st.add(3, (thr[0] < 1.0f ? 1 : 0) + (thr[1] < 1.0f ? 1 : 0));
+        st.add(4, (upd0 ? 1 : 0) + (upd1 ? 1 : 0));
+        al0 = upd0 ? am0 : 0.0f;
+        al1 = upd1 ? am1 : 0.0f;
+        last[0] = upd0 ? sid : last[0];
+        last[1] = upd1 ? sid : last[1];
+        thr[0] = stop0 ? 2.0f : thr[0];
+        thr[1] = stop1 ? 2.0f : thr[1];
+    } else {
+        al0 = fwd_accept(am0, pw0, A.z, lo2(nT2), sid, thr[0], last[0]);
+        al1 = fwd_accept(am1, pw1, A.z, hi2(nT2), sid, thr[1], last[1]);
+    }
+    const f32x2 al2 = pk2(al0, al1);  // alpha = 0: the pixel skips this Gaussian
     const f32x2 w2 = mul2(al2, T2);
 #pragma unroll
     for (int d = 0; d < D; ++d) acc2[d] = fma2(bc2(d == 0 ? Cc.x : d == 1 ? Cc.y : d == 2 ? Cc.z : Cc.w), w2, acc2[d]);
     T2 = mul2(T2, sub2(bc2(1.0f), al2));  // == nT2 where updated (same two roundings), T * 1 elsewhere
-    const int sid = __float_as_int(A.w);
-    last[0] = upd0 ? sid : last[0];
-    last[1] = upd1 ? sid : last[1];
-    thr[0] = stop0 ? 2.0f : thr[0];
-    thr[1] = stop1 ? 2.0f : thr[1];
 }
 
 // 14 resident CTAs per SM asked of ptxas (72 registers, no spills; 16 would rematerialise pixel coordinates
@@ -410,7 +443,7 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 14) raster_fwd_ws_kernel(c
     WarpStream& ws = wss[warp];
     const int ox = tx * kTile, oy = ty * kTile + warp * S::kFootH;
     const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);
-    const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
+    const float px0 = pin_reg((float)j0 + 0.5f), py0 = (float)i0 + 0.5f;
     const f32x2 npy2 = pk2(-py0, -(py0 + 4.0f));
 
     const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
@@ -760,6 +793,21 @@ __global__ void __launch_bounds__(Shape<PX>::kThreads) raster_bwd_kernel(const R
 //   * the cross-lane gradient sums go through a shared-memory transpose + red.global.add.v4.f32 instead of a
 //     shuffle butterfly (reduce_entries).
 // ------------------------------------------------------------------------------------------------
+// One pixel's accept decision of the backward as a chain of predicated compares (4 compares + 2 selects; the C++
+// formulation compiles to one compare AND one select per condition):
+//   valid = (sid <= bin_final) && (pw <= lo) && (am >= 1/255);  al = valid ? am : 0;  ag = (valid && ar <= 0.999) ? am : 0
+__device__ __forceinline__ void bwd_accept(int sid, int bin_final, float pw, float lo, float am, float ar, float& al, float& ag) {
+    asm("{\n\t.reg .pred v, c;\n\t"
+        "setp.le.s32 v, %2, %3;\n\t"
+        "setp.le.and.f32 v, %4, %5, v;\n\t"
+        "setp.ge.and.f32 v, %6, 0f3B808081, v;\n\t"  // kAlphaThreshold
+        "selp.f32 %0, %6, 0f00000000, v;\n\t"
+        "setp.le.and.f32 c, %7, 0f3F7FBE77, v;\n\t"  // kMaxAlpha
+        "selp.f32 %1, %6, 0f00000000, c;\n\t}"
+        : "=f"(al), "=f"(ag)
+        : "r"(sid), "r"(bin_final), "f"(pw), "f"(lo), "f"(am), "f"(ar));
+}
+
 // One 8x8 block (column half `a`): the lane's two pixels (rows i0, i0 + 4) in the two halves of every
 // f32x2.  FIRST: v[] is written, else accumulated (no zero-fill, no register shuffling where the paths
 // join).  Returns nonzero if a pixel passed the alpha test.
@@ -773,15 +821,25 @@ __device__ __forceinline__ int bwd_pk_block(int a, const float4& A, const float4
     const float pw0 = lo2(pw2), pw1 = hi2(pw2);
     const float ar0 = ex2_approx(pw0), ar1 = ex2_approx(pw1);
     const float am0 = fminf(kMaxAlpha, ar0), am1 = fminf(kMaxAlpha, ar1);
-    const bool valid0 = (sid <= bin_final[0]) && (pw0 <= A.z) && (am0 >= kAlphaThreshold);
-    const bool valid1 = (sid <= bin_final[1]) && (pw1 <= A.z) && (am1 >= kAlphaThreshold);
-    st.add(3, (sid <= bin_final[0] ? 1 : 0) + (sid <= bin_final[1] ? 1 : 0));
-    st.add(4, (valid0 ? 1 : 0) + (valid1 ? 1 : 0));
     // a pixel that fails the test gets alpha = 0: then 1/(1-alpha) = 1 exactly (rcp.approx is exact at 1),
     // T and bsum pass through unchanged and every gradient term is 0 -- no selects after the packed ops
-    const float al0 = valid0 ? am0 : 0.0f, al1 = valid1 ? am1 : 0.0f;
+    float al0, al1, ag0, ag1;  // ag: alpha where it carries a gradient (not clamped to kMaxAlpha)
+    bool valid0 = false, valid1 = false;
+    if (STATS) {
+        valid0 = (sid <= bin_final[0]) && (pw0 <= A.z) && (am0 >= kAlphaThreshold);
+        valid1 = (sid <= bin_final[1]) && (pw1 <= A.z) && (am1 >= kAlphaThreshold);
+        st.add(3, (sid <= bin_final[0] ? 1 : 0) + (sid <= bin_final[1] ? 1 : 0));
+        st.add(4, (valid0 ? 1 : 0) + (valid1 ? 1 : 0));
+        al0 = valid0 ? am0 : 0.0f;
+        al1 = valid1 ? am1 : 0.0f;
+        ag0 = ar0 <= kMaxAlpha ? al0 : 0.0f;
+        ag1 = ar1 <= kMaxAlpha ? al1 : 0.0f;
+    } else {
+        bwd_accept(sid, bin_final[0], pw0, A.z, am0, ar0, al0, ag0);
+        bwd_accept(sid, bin_final[1], pw1, A.z, am1, ar1, al1, ag1);
+    }
     const f32x2 al2 = pk2(al0, al1);
-    const f32x2 ag2 = pk2(ar0 <= kMaxAlpha ? al0 : 0.0f, ar1 <= kMaxAlpha ? al1 : 0.0f);  // clamped alpha: no gradient
+    const f32x2 ag2 = pk2(ag0, ag1);
     const f32x2 oma2 = sub2(bc2(1.0f), al2);
     const f32x2 ra2 = pk2(rcp_approx(lo2(oma2)), rcp_approx(hi2(oma2)));
     const f32x2 Tn2 = mul2(T2, ra2);  // transmittance in front of this Gaussian
@@ -823,7 +881,7 @@ __device__ __forceinline__ int bwd_pk_block(int a, const float4& A, const float4
 #pragma unroll
         for (int d = 0; d < D; ++d) v[8 + d] = fma2(fac2, vout2[d], v[8 + d]);
     }
-    return (valid0 || valid1) ? 1 : 0;
+    return (valid0 || valid1) ? 1 : 0;  // STATS only
 }
 
 // Per-pixel start state of the packed backward (warp footprint 16x8 at (j0 - lane%8, i0 - lane/8)): final
@@ -893,49 +951,113 @@ __device__ __forceinline__ void bwd_pk_prologue(const RasterParams& p, int cam, 
 struct GradTranspose {
     float4 v[6][36];
 };
+constexpr int kRedRowBytes = 36 * 16;               // one [slot group] row
+constexpr int kRedParityBytes = 3 * kRedRowBytes;  // the three rows of one queue-entry parity
 
 // Position of lane l in a `red` row: every 8 lanes are followed by one float4 of padding, so that the eight
 // lanes of a shared-memory phase hit eight different 16-B columns on the write AND on the transposed read.
 __device__ __forceinline__ int red_pos(int l) { return (l >> 3) * 9 + (l & 7); }
 
-// Cross-lane sums of the gradient slots of queue entries q0 (even) .. q0+count-1 (count <= 2), whose
-// per-lane values sit in `red`.  Instead of a shuffle butterfly per Gaussian (16 SHFL + 22 FSEL + 16 FADD),
-// the values are transposed through shared memory: lane = (entry, slot group, quarter) sums 8 lanes' float4
-// with FADD2 and adds its quarter-sum with ONE vector red.global.add.v4.f32.
-__device__ __forceinline__ void reduce_entries(const RasterParams& p, const WarpStream& ws, const GradTranspose& red, int q0, int count, int lane) {
-    const int item = lane >> 2, quarter = lane & 3;  // item = entry parity * 3 + slot group
-    const int qq = item >= 3 ? 1 : 0, sg = item - qq * 3;
-    if (lane < 24 && qq < count) {
-        const float4* src = &red.v[item][quarter * 9];
-        f32x2 s01 = pk2(src[0].x, src[0].y), s23 = pk2(src[0].z, src[0].w);
+// Shared-memory accesses by 32-bit shared-window address + immediate offset: the per-lane base addresses are computed
+// once (pin_reg) instead of being re-derived from %tid / %ctaid inside the inner loop.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ float4 lds_v4(unsigned addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr), "n"(OFF) : "memory");
+    return r;
+}
+template <int OFF>
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(r) : "r"(addr), "n"(OFF) : "memory");
+    return r;
+}
+template <int OFF>
+__device__ __forceinline__ int lds_b32(unsigned addr) {
+    int r;
+    asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(r) : "r"(addr), "n"(OFF) : "memory");
+    return r;
+}
+
+// The lane's 12 gradient values of one queue entry (two pixels per f32x2 -> one float) into its column of the transpose
+// rows.  One copy per control-flow path of the caller (PATH only makes the three asm strings differ): sunk into a common
+// tail, the compiler has to shuffle 12 registers into a common layout at the join.
+#define QED_STS_V4(PATH)                                                                                                        \
+    asm volatile("st.shared.v4.f32 [%0+%5], {%1,%2,%3,%4};  // path " #PATH ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "n"(OFF) \
+                 : "memory")
+template <int PATH, int OFF>
+__device__ __forceinline__ void sts_v4(unsigned addr, float a, float b, float c, float d) {
+    if (PATH == 0) QED_STS_V4(0);
+    else if (PATH == 1) QED_STS_V4(1);
+    else QED_STS_V4(2);
+}
+template <int PATH>
+__device__ __forceinline__ void store_grad_slots(unsigned addr, const f32x2 (&v)[12]) {
+    float vs[12];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) {
-            const float4 x = src[j];
-            s01 = add2(s01, pk2(x.x, x.y));
-            s23 = add2(s23, pk2(x.z, x.w));
-        }
-        // back to the (mean2d, conic, opacity, colour) parametrisation:
-        //   v_mean = g u / log2e ; v_conic = -(g dx^2 / 2, g dx dy, g dy^2 / 2) ; v_opacity = g / opacity
-        const int g = __float_as_int(ws.qb[q0 + qq].w);
-        float k0 = 1.0f, k1 = 1.0f, k3 = 1.0f;
-        if (sg == 0) k0 = k1 = k3 = 1.0f / kLog2e;
-        if (sg == 1) {
-            k0 = -0.5f;
-            k1 = -1.0f;
-            k3 = ex2_approx(-ws.qa[q0 + qq].z);
-        }
-        s01 = mul2(s01, pk2(k0, k1));
-        s23 = mul2(s23, pk2(k0, k3));
-        red_add_v4(p.packed_grads + (int64_t)g * kGradFloats + sg * 4, lo2(s01), hi2(s01), lo2(s23), hi2(s23));
+    for (int s = 0; s < 12; ++s) vs[s] = lo2(v[s]) + hi2(v[s]);
+    sts_v4<PATH, 0>(addr, vs[0], vs[1], vs[2], vs[3]);
+    sts_v4<PATH, kRedRowBytes>(addr, vs[4], vs[5], vs[6], vs[7]);
+    sts_v4<PATH, 2 * kRedRowBytes>(addr, vs[8], vs[9], vs[10], vs[11]);
+}
+
+// Role of a lane in the cross-lane sums: lane = (entry parity qq, slot group sg, quarter) sums 8 lanes' float4 of slot
+// group sg of queue entry q0 + qq with FADD2 and adds its quarter-sum with ONE vector red.global.add.v4.f32 -- instead
+// of a shuffle butterfly per Gaussian (16 SHFL + 22 FSEL + 16 FADD).  All per-lane constants of the role live in registers.
+struct ReduceRole {
+    unsigned src;    // shared address of red.v[qq * 3 + sg][quarter * 9]
+    unsigned entry;  // shared address of ws.qa[qq]
+    int need;        // the lane works iff (entries in this round) > need
+    unsigned sg16;   // 16 * slot group (0 = means2d + absgrad, 1 = conic + opacity, 2 = colour): byte offset of the group
+};                   // inside the packed record and of its row in kSlotScale
+// back to the (mean2d, conic, opacity, colour) parametrisation, per slot group:
+//   v_mean = g u / log2e ; v_conic = -(g dx^2 / 2, g dx dy, g dy^2 / 2) ; v_opacity = g / opacity (.w of group 1, patched per Gaussian)
+__constant__ float4 kSlotScale[3] = {{1.0f / kLog2e, 1.0f / kLog2e, 1.0f / kLog2e, 1.0f / kLog2e}, {-0.5f, -1.0f, -0.5f, 1.0f}, {1.0f, 1.0f, 1.0f, 1.0f}};
+
+__device__ __forceinline__ ReduceRole make_reduce_role(const WarpStream& ws, const GradTranspose& red, int lane) {
+    ReduceRole r;
+    const int item = min(lane >> 2, 5), quarter = lane & 3;  // item = entry parity * 3 + slot group
+    const int qq = item >= 3 ? 1 : 0;
+    r.sg16 = (unsigned)(item - qq * 3) * 16u;
+    r.src = pin_reg(smem_u32(&red.v[item][quarter * 9]));
+    r.entry = pin_reg(smem_u32(&ws.qa[qq]));
+    r.need = lane < 24 ? qq : 2;
+    return r;
+}
+
+// Cross-lane sums of the gradient slots of queue entries q0 (even) .. q0+count-1 (count <= 2), whose per-lane values
+// sit in `red`.
+__device__ __forceinline__ void reduce_entries(const RasterParams& p, const ReduceRole& r, int q0, int count) {
+    if (count > r.need) {
+        float4 x = lds_v4<0>(r.src);
+        f32x2 s01 = pk2(x.x, x.y), s23 = pk2(x.z, x.w);
+#define QED_RED_STEP(J)                 \
+        x = lds_v4<16 * (J)>(r.src);    \
+        s01 = add2(s01, pk2(x.x, x.y)); \
+        s23 = add2(s23, pk2(x.z, x.w));
+        QED_RED_STEP(1) QED_RED_STEP(2) QED_RED_STEP(3) QED_RED_STEP(4) QED_RED_STEP(5) QED_RED_STEP(6) QED_RED_STEP(7)
+#undef QED_RED_STEP
+        const unsigned e = r.entry + q0 * 16;
+        const int g = lds_b32<512 + 12>(e);  // WarpStream::qb[q].w
+        const char* ks = reinterpret_cast<const char*>(kSlotScale) + r.sg16;
+        const float2 k01 = *reinterpret_cast<const float2*>(ks);
+        float k3 = *reinterpret_cast<const float*>(ks + 12);
+        if (r.sg16 == 16u) k3 = ex2_approx(-lds_f32<8>(e));  // WarpStream::qa[q].z = log2(opacity)
+        s01 = mul2(s01, pk2(k01.x, k01.y));
+        s23 = mul2(s23, pk2(k01.x, k3));
+        char* dst = reinterpret_cast<char*>(p.packed_grads) + ((uint64_t)(unsigned)g * (kGradFloats * 4) + r.sg16);
+        red_add_v4(reinterpret_cast<float*>(dst), lo2(s01), hi2(s01), lo2(s23), hi2(s23));
     }
 }
 
-// 12 resident CTAs per SM asked of ptxas (80 registers): occupancy is worth more than the 4 bytes it spills.
-template <int D, bool CULL, bool STATS>
-__global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(const RasterParams p) {
+// MINB resident CTAs per SM asked of ptxas: 12 -> 80 registers, 10 -> 96 (qed_debug_set_raster_bwd_minb).
+template <int D, bool CULL, bool STATS, int MINB>
+__global__ void __launch_bounds__(Shape<4>::kThreads, MINB) raster_bwd_ws_kernel(const RasterParams p) {
     using S = Shape<4>;
     __shared__ WarpStream wss[S::kWarps];
     __shared__ GradTranspose reds[S::kWarps];
+    static_assert(offsetof(WarpStream, qb) - offsetof(WarpStream, qa) == 512, "reduce_entries addresses qb relative to qa");
     StatCounters<STATS> st;
     pdl_enter();
     const int cam = blockIdx.z, ty = blockIdx.y, tx = blockIdx.x;
@@ -944,9 +1066,8 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(c
     GradTranspose& red = reds[warp];
     const int ox = tx * kTile, oy = ty * kTile + warp * S::kFootH;
     const int j0 = ox + (lane & 7), i0 = oy + (lane >> 3);
-    const float px0 = (float)j0 + 0.5f, py0 = (float)i0 + 0.5f;
+    const float px0 = pin_reg((float)j0 + 0.5f), py0 = (float)i0 + 0.5f;
     const f32x2 npy2 = pk2(-py0, -(py0 + 4.0f));
-    const int rpos = red_pos(lane);
 
     const int64_t tile_id = ((int64_t)cam * p.tile_h + ty) * p.tile_w + tx;
     const int range_start = p.offsets[tile_id];
@@ -958,6 +1079,9 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(c
     int want = 0, wmax = -1;
     bwd_pk_prologue<D>(p, cam, i0, j0, T2, bsum2, vout2, bin_final, sub_max, want, wmax);
     if (wmax < 0) return;  // nothing composited under this warp's footprint (no block-wide barrier below)
+
+    const unsigned red_dst = pin_reg(smem_u32(&red.v[0][red_pos(lane)]));  // this lane's column of the transpose rows
+    const ReduceRole role = make_reduce_role(ws, red, lane);
 
     // batch i covers sorted indices (top - 32 i - 31 .. top - 32 i], lane l owns top - 32 i - l
     const int top = wmax;
@@ -1004,7 +1128,8 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(c
         }
         __syncwarp();
         const int nq = __popc(m);
-        for (int q = 0; q < nq; ++q) {
+        unsigned par = 0;  // byte offset of the transpose rows of this entry's parity
+        for (int q = 0; q < nq; ++q, par ^= kRedParityBytes) {
             const float4 A = ws.qa[q], B = ws.qb[q], Cc = ws.qc[q];
             const int mask = ws.qm[q];
             if (lane == 0) st.add(2, __popc(mask));
@@ -1013,28 +1138,27 @@ __global__ void __launch_bounds__(Shape<4>::kThreads, 12) raster_bwd_ws_kernel(c
             const f32x2 t2 = mul2(bc2(B.y), dy2);
             const f32x2 cy2 = fma2(mul2(bc2(B.z), dy2), dy2, bc2(A.z));
             const float qc2 = B.z + B.z;
+            const unsigned dst = red_dst + par;
             f32x2 v[12];
             int any_valid;
             if (mask == 3) {  // one basic block: the two independent blocks interleave (ILP)
                 any_valid = bwd_pk_block<D, true, STATS>(0, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[0], bsum2[0], vout2[0], bin_final[0], v, st);
                 any_valid |= bwd_pk_block<D, false, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
+                store_grad_slots<0>(dst, v);
             } else if (mask == 1) {
                 any_valid = bwd_pk_block<D, true, STATS>(0, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[0], bsum2[0], vout2[0], bin_final[0], v, st);
+                store_grad_slots<1>(dst, v);
             } else {
                 any_valid = bwd_pk_block<D, true, STATS>(1, A, B, Cc, sid, px0, dy2, t2, cy2, qc2, T2[1], bsum2[1], vout2[1], bin_final[1], v, st);
+                store_grad_slots<2>(dst, v);
             }
             if (STATS) {  // every lane votes
                 const bool any = __any_sync(0xffffffffu, any_valid);
                 if (lane == 0 && any) st.add(5, 1);
             }
-            float vs[12];
-#pragma unroll
-            for (int s = 0; s < 12; ++s) vs[s] = lo2(v[s]) + hi2(v[s]);
-#pragma unroll
-            for (int sg = 0; sg < 3; ++sg) red.v[(q & 1) * 3 + sg][rpos] = make_float4(vs[4 * sg], vs[4 * sg + 1], vs[4 * sg + 2], vs[4 * sg + 3]);
             if ((q & 1) || q == nq - 1) {
                 __syncwarp();
-                reduce_entries(p, ws, red, q & ~1, (q & 1) + 1, lane);
+                reduce_entries(p, role, q & ~1, (q & 1) + 1);
                 __syncwarp();
             }
         }
@@ -1084,6 +1208,8 @@ static thread_local int g_raster_cull = 1;                           // 0 disabl
 static thread_local unsigned long long* g_raster_counters = nullptr;  // device uint64[6] -> STATS kernels
 static thread_local int g_px_fwd = 4, g_px_bwd = 4;                   // pixels per lane
 static thread_local int g_raster_packed = 1;                          // f32x2 kernels where they exist (backward, 4 px/lane)
+constexpr int kBwdMinBlocks = 12, kBwdMinBlocksAlt = 10;              // resident CTAs per SM asked of ptxas (80 / 96 registers)
+static thread_local int g_bwd_minb = kBwdMinBlocks;
 
 template <int D, int PX, bool BWD>
 static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
@@ -1108,11 +1234,14 @@ static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
         }
     } else if (PX == 4 && g_raster_packed) {
         if (stats) {
-            if (cull) (void)launch_pdl(raster_bwd_ws_kernel<D, true, true>, grid, dim3(T), 0, stream, p);
-            else (void)launch_pdl(raster_bwd_ws_kernel<D, false, true>, grid, dim3(T), 0, stream, p);
+            if (cull) (void)launch_pdl(raster_bwd_ws_kernel<D, true, true, kBwdMinBlocks>, grid, dim3(T), 0, stream, p);
+            else (void)launch_pdl(raster_bwd_ws_kernel<D, false, true, kBwdMinBlocks>, grid, dim3(T), 0, stream, p);
+        } else if (!cull) {
+            (void)launch_pdl(raster_bwd_ws_kernel<D, false, false, kBwdMinBlocks>, grid, dim3(T), 0, stream, p);
+        } else if (g_bwd_minb == kBwdMinBlocksAlt) {
+            (void)launch_pdl(raster_bwd_ws_kernel<D, true, false, kBwdMinBlocksAlt>, grid, dim3(T), 0, stream, p);
         } else {
-            if (cull) (void)launch_pdl(raster_bwd_ws_kernel<D, true, false>, grid, dim3(T), 0, stream, p);
-            else (void)launch_pdl(raster_bwd_ws_kernel<D, false, false>, grid, dim3(T), 0, stream, p);
+            (void)launch_pdl(raster_bwd_ws_kernel<D, true, false, kBwdMinBlocks>, grid, dim3(T), 0, stream, p);
         }
     } else {
         if (stats) {
@@ -1190,6 +1319,13 @@ extern "C" int qed_debug_set_raster_counters(void* counters) {
 extern "C" int qed_debug_set_raster_packed(int enabled) {
     int old = g_raster_packed;
     g_raster_packed = enabled ? 1 : 0;
+    return old;
+}
+
+// occupancy / register trade-off of the packed backward (12 or 10 resident CTAs per SM).  Returns the previous value.
+extern "C" int qed_debug_set_raster_bwd_minb(int minb) {
+    int old = g_bwd_minb;
+    if (minb == kBwdMinBlocks || minb == kBwdMinBlocksAlt) g_bwd_minb = minb;
     return old;
 }
 
