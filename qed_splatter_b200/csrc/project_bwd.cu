@@ -144,6 +144,18 @@ __device__ __forceinline__ void sh_bases_vjp(float x, float y, float z, const fl
     }
 }
 
+__device__ __forceinline__ void quat_to_rotmat(float qw, float qx, float qy, float qz, float (&R)[9]) {
+    R[0] = 1.0f - 2.0f * (qy * qy + qz * qz);
+    R[1] = 2.0f * (qx * qy - qw * qz);
+    R[2] = 2.0f * (qx * qz + qw * qy);
+    R[3] = 2.0f * (qx * qy + qw * qz);
+    R[4] = 1.0f - 2.0f * (qx * qx + qz * qz);
+    R[5] = 2.0f * (qy * qz - qw * qx);
+    R[6] = 2.0f * (qx * qz - qw * qy);
+    R[7] = 2.0f * (qy * qz + qw * qx);
+    R[8] = 1.0f - 2.0f * (qx * qx + qy * qy);
+}
+
 // DEG=-1: colours pass through.  VEC: coefficient rows 16-byte aligned and K*3 % 4 == 0.
 // XCH (multi-GPU view-colour exchange, VEC only): no coefficient gradient is built or written (half the shared memory, 192 B
 // per Gaussian less HBM traffic); the gated colour gradient goes to every rank's exchange buffer instead.
@@ -166,21 +178,65 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
     const int D = p.n_color + p.append_depth;
     const bool use_sh = DEG >= 0 && p.n_color > 0;
 
+    // Every global load of this Gaussian is ISSUED before the first one is used (the kernel runs 16 warps per SM, so a
+    // chain of dependent round trips -- inputs, radii, SH rows, packed gradients, conics -- is what bounds it): radii first
+    // (they gate the SH staging), then the raw parameters, then the SH rows (cp.async) and the first view's upstream
+    // gradients; the arithmetic on the parameters starts while those are in flight.
     float m0 = 0, m1 = 0, m2 = 0, s0 = 0, s1 = 0, s2 = 0, opac = 0, qn = 1;
     float qw = 1, qx = 0, qy = 0, qz = 0;
-    float R[9] = {0}, M[9] = {0};
     float S00 = 0, S01 = 0, S02 = 0, S11 = 0, S12 = 0, S22 = 0;
+    float4 q = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
     bool anyvis = false;
+    int rad0 = 0;
     if (in_range) {
+        rad0 = p.radii[n];
+        anyvis = rad0 > 0;
+        for (int c = 1; c < p.C; ++c) anyvis |= p.radii[(int64_t)c * p.N + n] > 0;
         m0 = p.means[n * 3 + 0];
         m1 = p.means[n * 3 + 1];
         m2 = p.means[n * 3 + 2];
         const float* qp = p.quats + (int64_t)n * 4;  // scalar loads: callers' views are only 4-byte aligned
-        float4 q = make_float4(qp[0], qp[1], qp[2], qp[3]);
+        q = make_float4(qp[0], qp[1], qp[2], qp[3]);
         s0 = p.scales[n * 3 + 0];
         s1 = p.scales[n * 3 + 1];
         s2 = p.scales[n * 3 + 2];
         opac = p.opacities ? p.opacities[n] : 0.0f;
+    }
+
+    // ---- stage SH coefficients (visible rows) and clear the coefficient-gradient rows ----
+    float4* my_coef = coefbuf + (warp * 32 + lane) * Sh::kStrideVec;
+    float4* my_vcoef = vcoefbuf + (warp * 32 + lane) * Sh::kStrideVec;
+    const int row_floats = p.K * 3;
+    if (use_sh && VEC) {
+        const uint32_t warp_vis = __ballot_sync(0xffffffffu, anyvis);
+        const int64_t row0 = (int64_t)blockIdx.x * kProjBwdThreads + warp * 32;
+        const float4* src = reinterpret_cast<const float4*>(p.colors_in) + row0 * (row_floats / 4);
+        float4* wbuf = coefbuf + warp * 32 * Sh::kStrideVec;
+        for (int v = lane; v < 32 * Sh::kVec; v += 32) {
+            int r = v / Sh::kVec, j = v - r * Sh::kVec;
+            if ((warp_vis >> r) & 1u) cp_async16(wbuf + r * Sh::kStrideVec + j, src + (int64_t)r * (row_floats / 4) + j);
+        }
+        cp_async_commit();
+    }
+    // upstream gradients + conic of the first view (the later views' are fetched one view ahead inside the loop)
+    float4 pf0 = make_float4(0, 0, 0, 0), pf1 = pf0, pf2 = pf0;
+    float pfa = 0, pfb = 0, pfc = 0;
+    if (rad0 > 0) {
+        if (p.packed) {
+            const float4* r = reinterpret_cast<const float4*>(p.packed) + (int64_t)n * 3;
+            pf0 = r[0];
+            pf1 = r[1];
+            pf2 = r[2];
+        }
+        pfa = p.conics[(int64_t)n * 3 + 0];
+        pfb = p.conics[(int64_t)n * 3 + 1];
+        pfc = p.conics[(int64_t)n * 3 + 2];
+    }
+    if (use_sh && !XCH) {
+#pragma unroll
+        for (int j = 0; j < Sh::kVec; ++j) my_vcoef[j] = make_float4(0, 0, 0, 0);
+    }
+    if (in_range) {
         if (p.activations & QED_ACT_LOG_SCALES) {
             s0 = expf(s0);
             s1 = expf(s1);
@@ -192,15 +248,8 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         qx = q.y / qn;
         qy = q.z / qn;
         qz = q.w / qn;
-        R[0] = 1.0f - 2.0f * (qy * qy + qz * qz);
-        R[1] = 2.0f * (qx * qy - qw * qz);
-        R[2] = 2.0f * (qx * qz + qw * qy);
-        R[3] = 2.0f * (qx * qy + qw * qz);
-        R[4] = 1.0f - 2.0f * (qx * qx + qz * qz);
-        R[5] = 2.0f * (qy * qz - qw * qx);
-        R[6] = 2.0f * (qx * qz - qw * qy);
-        R[7] = 2.0f * (qy * qz + qw * qx);
-        R[8] = 1.0f - 2.0f * (qx * qx + qy * qy);
+        float R[9], M[9];  // R(q), M = R diag(s): rebuilt in the epilogue instead of living in 18 registers across the view loop
+        quat_to_rotmat(qw, qx, qy, qz, R);
         for (int i = 0; i < 3; ++i) {
             M[i * 3 + 0] = R[i * 3 + 0] * s0;
             M[i * 3 + 1] = R[i * 3 + 1] * s1;
@@ -212,49 +261,43 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         S11 = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
         S12 = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
         S22 = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
-        for (int c = 0; c < p.C; ++c) anyvis |= p.radii[(int64_t)c * p.N + n] > 0;
     }
-
-    // ---- stage SH coefficients (visible rows) and clear the coefficient-gradient rows ----
-    float4* my_coef = coefbuf + (warp * 32 + lane) * Sh::kStrideVec;
-    float4* my_vcoef = vcoefbuf + (warp * 32 + lane) * Sh::kStrideVec;
-    const int row_floats = p.K * 3;
-    if (use_sh) {
-        if (VEC) {
-            const uint32_t warp_vis = __ballot_sync(0xffffffffu, anyvis);
-            const int64_t row0 = (int64_t)blockIdx.x * kProjBwdThreads + warp * 32;
-            const float4* src = reinterpret_cast<const float4*>(p.colors_in) + row0 * (row_floats / 4);
-            float4* wbuf = coefbuf + warp * 32 * Sh::kStrideVec;
-            for (int q = lane; q < 32 * Sh::kVec; q += 32) {
-                int r = q / Sh::kVec, j = q - r * Sh::kVec;
-                if ((warp_vis >> r) & 1u) cp_async16(wbuf + r * Sh::kStrideVec + j, src + (int64_t)r * (row_floats / 4) + j);
-            }
-            cp_async_commit();
-        }
-        if (!XCH) {
-#pragma unroll
-            for (int j = 0; j < Sh::kVec; ++j) my_vcoef[j] = make_float4(0, 0, 0, 0);
-        }
-        if (VEC) {
-            cp_async_wait<0>();
-            __syncwarp();
-        }
+    if (use_sh && VEC) {
+        cp_async_wait<0>();
+        __syncwarp();
     }
 
     float vS00 = 0, vS01 = 0, vS02 = 0, vS11 = 0, vS12 = 0, vS22 = 0;  // full symmetric matrix gradient (off-diag = one side)
     float vm0 = 0, vm1 = 0, vm2 = 0, vopac = 0;
 
     if (in_range && anyvis) {
+        int rad_c = rad0;
         for (int c = 0; c < p.C; ++c) {
             const int64_t idx = (int64_t)c * p.N + n;
-            if (p.radii[idx] <= 0) continue;
+            const bool vis = rad_c > 0;
+            const float4 r0 = pf0, r1 = pf1, r2 = pf2;
+            const float ca = pfa, cb = pfb, cc = pfc;  // conic of the blurred covariance (stored by the forward)
+            if (c + 1 < p.C) {  // next view: radius, upstream gradients, conic
+                const int64_t nx = idx + p.N;
+                rad_c = p.radii[nx];
+                if (rad_c > 0) {
+                    if (p.packed) {
+                        const float4* r = reinterpret_cast<const float4*>(p.packed) + nx * 3;
+                        pf0 = r[0];
+                        pf1 = r[1];
+                        pf2 = r[2];
+                    }
+                    pfa = p.conics[nx * 3 + 0];
+                    pfb = p.conics[nx * 3 + 1];
+                    pfc = p.conics[nx * 3 + 2];
+                }
+            }
+            if (!vis) continue;
             const CamB& cam = cams[c];
             const float* W = cam.W;
             // ---- incoming gradients ----
             float g_mx = 0, g_my = 0, g_d = 0, g_ca = 0, g_cb = 0, g_cc = 0, g_o = 0, g_col[4] = {0, 0, 0, 0};
             if (p.packed) {
-                const float4* r = reinterpret_cast<const float4*>(p.packed) + idx * 3;
-                float4 r0 = r[0], r1 = r[1], r2 = r[2];
                 g_mx = r0.x;
                 g_my = r0.y;
                 g_ca = r1.x;
@@ -278,9 +321,11 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
             }
             if (p.v_opac_cn) g_o += p.v_opac_cn[idx];
             if (p.v_colors) {
-                for (int ch = 0; ch < D; ++ch) g_col[ch] += p.v_colors[idx * D + ch];
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    if (ch < D) g_col[ch] += p.v_colors[idx * D + ch];
             }
-            if (p.append_depth) g_d += g_col[p.n_color];
+            if (p.append_depth) g_d += p.n_color == 3 ? g_col[3] : (p.n_color == 1 ? g_col[1] : g_col[0]);  // no dynamic index: registers
 
             // ---- recompute forward intermediates ----
             float x = W[0] * m0 + W[1] * m1 + W[2] * m2 + cam.t[0];
@@ -305,8 +350,6 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
             float tx = z * fmaxf(fminf(xz, cam.lim_xp), -cam.lim_xn);
             float ty = z * fmaxf(fminf(yz, cam.lim_yp), -cam.lim_yn);
             float J00 = cam.fx * rz, J02 = -cam.fx * tx * rz2, J11 = cam.fy * rz, J12 = -cam.fy * ty * rz2;
-            // conic of the blurred covariance (stored by the forward)
-            float ca = p.conics[idx * 3 + 0], cb = p.conics[idx * 3 + 1], cc = p.conics[idx * 3 + 2];
 
             // ---- conic -> blurred 2x2 covariance: G = -X V X, V = [[va, vb/2],[vb/2, vc]] ----
             float hv = 0.5f * g_cb;
@@ -474,6 +517,13 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
     if (in_range) {
         // ---- Sigma = M M^T ; M = R diag(s) ----
         // vM = 2 vSigma M  (vSigma symmetric)
+        float R[9], M[9];
+        quat_to_rotmat(qw, qx, qy, qz, R);
+        for (int i = 0; i < 3; ++i) {
+            M[i * 3 + 0] = R[i * 3 + 0] * s0;
+            M[i * 3 + 1] = R[i * 3 + 1] * s1;
+            M[i * 3 + 2] = R[i * 3 + 2] * s2;
+        }
         float vM[9];
         for (int j = 0; j < 3; ++j) {
             vM[0 + j] = 2.0f * (vS00 * M[0 + j] + vS01 * M[3 + j] + vS02 * M[6 + j]);
