@@ -37,7 +37,7 @@ typedef void* qed_stream_t; /* cudaStream_t */
 #define QED_ERR_UNSUPPORTED (-2)
 #define QED_ERR_WORKSPACE (-3)
 
-#define QED_ABI_VERSION 2
+#define QED_ABI_VERSION 3
 
 /* Library / ABI version (QED_ABI_VERSION the .so was built with). */
 int qed_abi_version(void);
@@ -289,6 +289,32 @@ int qed_arena_gather(int64_t n_new, const int32_t* src, const uint8_t* fresh, co
                      const float* old_exp_avg, const float* old_exp_avg_sq, const int64_t* old_group_starts,
                      float* new_param, float* new_exp_avg, float* new_exp_avg_sq, const int64_t* new_group_starts,
                      qed_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * camera + data side
+ */
+/* qed_splatter/model.py:22-38 `get_viewmat`: nerfstudio camera-to-world [C, rows, 4] (rows = 3 or 4; OpenGL camera axes)
+ * -> gsplat world-to-camera viewmats [C,4,4]: flip the y and z columns of R, analytic rigid inverse [R^T | -R^T T].
+ * Called once per step by the model (model.py:246) on the optimised camera pose. */
+int qed_viewmat_from_c2w(int C, int rows, const float* camera_to_worlds, float* viewmats, qed_stream_t stream);
+
+/* qed_splatter/create_init_pointcloud.py:148-196 `backproject_frame` (Open3D PointCloud.create_from_depth_image, :176-185):
+ * depth [height,width] float32 or raw uint16 (depth_is_u16), metres = value * depth_unit_scale (float32 product, :165);
+ * every `stride`-th pixel (u, v) with 0 < d < depth_max gives the world point inverse(extrinsic) * ((u-cx) d/fx, (v-cy) d/fy, d).
+ * intrinsic_host [3,3] and extrinsic_host [4,4] (OpenCV world-to-camera, :59-70) are HOST arrays.  points [ceil(W/stride) *
+ * ceil(H/stride), 3] receives the survivors compacted in pixel order, *n_points_dev (device) their count. */
+size_t qed_backproject_workspace_bytes(int width, int height, int stride);
+int qed_backproject_depth(int width, int height, const void* depth, int depth_is_u16, double depth_unit_scale, float depth_max,
+                          int stride, const float* intrinsic_host, const float* extrinsic_host, float* points,
+                          int64_t* n_points_dev, void* workspace, size_t workspace_bytes, qed_stream_t stream);
+
+/* Open3D PointCloud.voxel_down_sample (create_init_pointcloud.py:89, :194, :260): points [n,3] binned by
+ * floor(p / voxel_size); every occupied voxel yields the mean of its points.  Output sorted by voxel key (x, then y, then z
+ * index), *n_out_dev (device) = number of voxels; points_out needs room for n rows.  n_dev (optional, device): only the
+ * first min(*n_dev, n) points are real (the count qed_backproject_depth left on the device -- no host sync in between). */
+size_t qed_voxel_downsample_workspace_bytes(int64_t n);
+int qed_voxel_downsample(int64_t n, const int64_t* n_dev, const float* points, float voxel_size, float* points_out,
+                         int64_t* n_out_dev, void* workspace, size_t workspace_bytes, qed_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * multi-GPU: sum of the gradient arena over the ranks of the view-sharded step (the reference has

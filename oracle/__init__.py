@@ -20,5 +20,5 @@ reference's own call-site arithmetic (`qed_splatter/model.py:22-38`,
 float64 autograd vs finite differences, the explicit compositing backward vs
 autograd, SH-basis orthonormality, and compositing invariants.
 """
-from . import torch_impl  # noqa: F401
+from . import pointcloud, torch_impl  # noqa: F401
 from .torch_impl import *  # noqa: F401,F403

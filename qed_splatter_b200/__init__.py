@@ -7,6 +7,7 @@ loss-gradient / trainer step built on the same kernels.  Hand-written CUDA behin
 """
 from .rendering import rasterization  # noqa: F401
 from .losses import depth_supervised_loss  # noqa: F401
-from . import ops, scenes  # noqa: F401
+from .data_side import get_viewmat  # noqa: F401
+from . import data_side, ops, scenes  # noqa: F401
 
 __version__ = "0.1.0"

@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("QED_SPLAT_LIB", _PKG / "libqedsplat.so"))
 
 P = c_void_p  # every device pointer / stream
-ABI_VERSION = 2  # QED_ABI_VERSION of include/qed_splat.h this binding was written against
+ABI_VERSION = 3  # QED_ABI_VERSION of include/qed_splat.h this binding was written against
 
 # name -> (restype, argtypes); must match include/qed_splat.h exactly (tests/test_abi.py checks the names)
 SIGNATURES = {
@@ -56,6 +56,11 @@ SIGNATURES = {
     "qed_comm_barrier": (c_int, [P, c_int, c_int, ctypes.c_uint32, P]),
     "qed_comm_allreduce_f32": (c_int, [P, P, P, c_int, c_int, c_int64, c_int64, ctypes.c_uint32, c_int, P]),
     "qed_arena_gather": (c_int, [c_int64, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "qed_viewmat_from_c2w": (c_int, [c_int, c_int, P, P, P]),
+    "qed_backproject_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "qed_backproject_depth": (c_int, [c_int, c_int, P, c_int, c_double, c_float, c_int, P, P, P, P, P, c_size_t, P]),
+    "qed_voxel_downsample_workspace_bytes": (c_size_t, [c_int64]),
+    "qed_voxel_downsample": (c_int, [c_int64, P, P, c_float, P, P, P, c_size_t, P]),
 }
 # test hooks, not part of the reference-facing surface
 DEBUG_SIGNATURES = {

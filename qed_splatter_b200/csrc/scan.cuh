@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(int64_t n_hos
 }
 
 // single block: exclusive scan of block sums in place; writes the grand total
-__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int64_t nb, int64_t* __restrict__ block_sums, int64_t* __restrict__ total_dev) {
+static __global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int64_t nb, int64_t* __restrict__ block_sums, int64_t* __restrict__ total_dev) {
     __shared__ int64_t sw[kScanThreads / 32 + 1];
     pdl_enter();
     int64_t carry = 0;

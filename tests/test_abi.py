@@ -39,7 +39,7 @@ def test_load_and_error_strings():
     from qed_splatter_b200 import _lib
 
     lib = _lib.load()
-    assert lib.qed_abi_version() == 2
+    assert lib.qed_abi_version() == 3
     assert b"bad argument" in lib.qed_error_string(-1)
     assert lib.qed_error_string(0) == b"ok"
     # workspace queries are pure host functions
