@@ -39,7 +39,7 @@ def timed(fn, reps=20, warm=3):
 def main():
     peak = 6537.0
     try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_copy_gbps"]["burst"])
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
     dev = torch.device("cuda", 0)

@@ -70,6 +70,7 @@ DEBUG_SIGNATURES = {
     "qed_debug_set_raster_packed": (c_int, [c_int]),
     "qed_debug_set_raster_bwd_minb": (c_int, [c_int]),
     "qed_debug_set_radix_onesweep": (c_int, [c_int]),
+    "qed_debug_set_flat_scan": (c_int, [c_int]),
 }
 
 

@@ -162,6 +162,14 @@ extern "C" int qed_debug_set_radix_onesweep(int enabled) {
     return old;
 }
 
+// 1 (default): the two scans of qed_isect_prepare run as single launches (scan_flat_to); 0: three launches each.
+static thread_local int g_flat_scan = 1;
+extern "C" int qed_debug_set_flat_scan(int enabled) {
+    int old = g_flat_scan;
+    g_flat_scan = enabled ? 1 : 0;
+    return old;
+}
+
 // ---- library baseline (what gsplat calls) ----
 extern "C" size_t qed_sort_pairs_cub_workspace_bytes(int64_t n) {
     size_t bytes = 0;
@@ -218,7 +226,7 @@ extern "C" int qed_sort_pairs(int64_t n, int64_t* keys_in, int32_t* vals_in, int
 namespace qed {
 
 struct PrepareLayout {
-    size_t scan_ws, keys[3], vals[3], hist, cum2, total;
+    size_t scan_ws, scan_state, keys[3], vals[3], hist, cum2, total;
 };
 
 static PrepareLayout prepare_layout(int64_t CN) {
@@ -230,6 +238,7 @@ static PrepareLayout prepare_layout(int64_t CN) {
         return r;
     };
     L.scan_ws = take(scan_workspace_bytes(CN));
+    L.scan_state = take(2 * kFlatScanStateBytes);  // one per scan of qed_isect_prepare, zeroed by one memset
     for (int i = 0; i < 3; ++i) L.keys[i] = take((size_t)CN * 8);
     for (int i = 0; i < 3; ++i) L.vals[i] = take((size_t)CN * 4);
     L.hist = take(radix_hist_bytes(CN));
@@ -584,26 +593,33 @@ extern "C" int qed_isect_prepare(int C, int N, const float* depths, const int32_
         // 1. ordered compaction of the visible entries (scan of the flags, the compaction being its final phase;
         //    n_visible -> counts_dev[0]);  2. stable sort by (camera, depth bits): sorted flat indices land in vals1
         int rc;
+        char* st0 = ws + L.scan_state;
+        char* st1 = st0 + kFlatScanStateBytes;
+        const bool flat = g_flat_scan != 0;
+        if (flat) QED_CUDA_TRY(cudaMemsetAsync(st0, 0, 2 * kFlatScanStateBytes, stream));
         if (C == 1) {
             uint32_t* k0 = reinterpret_cast<uint32_t*>(ws + L.keys[0]);
             uint32_t* k1 = reinterpret_cast<uint32_t*>(ws + L.keys[1]);
             uint32_t* k2 = reinterpret_cast<uint32_t*>(ws + L.keys[2]);
-            rc = scan_inclusive_to(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, CompactVisibleSink<uint32_t>{N, depths, k0, vals0}, counts_dev,
-                                   ws + L.scan_ws, stream);
+            rc = flat ? scan_flat_to(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, CompactVisibleSink<uint32_t>{N, depths, k0, vals0}, counts_dev, st0, stream)
+                      : scan_inclusive_to(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, CompactVisibleSink<uint32_t>{N, depths, k0, vals0}, counts_dev,
+                                          ws + L.scan_ws, stream);
             if (rc != QED_OK) return rc;
             rc = radix_sort_pairs<uint32_t>(CN, counts_dev, k0, vals0, k1, vals1, k2, vals2, ws + L.hist, 32, stream);
         } else {
             uint64_t* k0 = reinterpret_cast<uint64_t*>(ws + L.keys[0]);
             uint64_t* k1 = reinterpret_cast<uint64_t*>(ws + L.keys[1]);
             uint64_t* k2 = reinterpret_cast<uint64_t*>(ws + L.keys[2]);
-            rc = scan_inclusive_to(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, CompactVisibleSink<uint64_t>{N, depths, k0, vals0}, counts_dev,
-                                   ws + L.scan_ws, stream);
+            rc = flat ? scan_flat_to(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, CompactVisibleSink<uint64_t>{N, depths, k0, vals0}, counts_dev, st0, stream)
+                      : scan_inclusive_to(CN, nullptr, ScanFlagPositive{tiles_per_gauss}, CompactVisibleSink<uint64_t>{N, depths, k0, vals0}, counts_dev,
+                                          ws + L.scan_ws, stream);
             if (rc != QED_OK) return rc;
             rc = radix_sort_pairs<uint64_t>(CN, counts_dev, k0, vals0, k1, vals1, k2, vals2, ws + L.hist, 32 + bit_length(C - 1), stream);
         }
         if (rc != QED_OK) return rc;
         // 3. tile counts in depth order -> write offsets, n_isects -> counts_dev[1]
-        rc = scan_inclusive(CN, counts_dev, ScanGather{tiles_per_gauss, vals1}, cum2, counts_dev + 1, ws + L.scan_ws, stream);
+        rc = flat ? scan_flat_to(CN, counts_dev, ScanGather{tiles_per_gauss, vals1}, ScanStore{cum2}, counts_dev + 1, st1, stream)
+                  : scan_inclusive(CN, counts_dev, ScanGather{tiles_per_gauss, vals1}, cum2, counts_dev + 1, ws + L.scan_ws, stream);
         if (rc != QED_OK) return rc;
     }
     if (counts_host_pinned) QED_CUDA_TRY(cudaMemcpyAsync(counts_host_pinned, counts_dev, 16, cudaMemcpyDeviceToHost, stream));

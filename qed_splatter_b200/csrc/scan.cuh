@@ -137,6 +137,118 @@ inline int scan_inclusive_to(int64_t capacity, const int64_t* n_dev, F f, Sink s
     return QED_OK;
 }
 
+// ---- single-launch variant ("flat" scan) ---------------------------------------------------------------------------------
+// The three launches above cost ~23 us for 1M flags (489 blocks of 2048: launch + drain three times, 12 us of it in kernels
+// that are 10-25 % issue-active).  Here at most kFlatScanBlocks blocks (<= what is co-resident: 148 SMs x 8 blocks of 256
+// threads) each own a contiguous range of tiles -- ONE tile up to 2M elements, kept in registers: the range is summed, the
+// sum is published as ONE 64-bit word (bit 63 = ready), every block then adds up the words of ALL its predecessors in
+// parallel (a few per thread -- no look-back chain, which at this size costs a full walk because every block publishes at
+// the same moment), and the scan is emitted.  Blocks take their range from a ticket, so a block only ever waits on blocks
+// that are already running.  `state` must be zero when the kernel starts (FlatScanState, kFlatScanStateBytes).
+constexpr int kFlatScanBlocks = 1024;
+struct FlatScanState {
+    unsigned long long agg[kFlatScanBlocks];
+    unsigned int ticket, pad;
+};
+constexpr size_t kFlatScanStateBytes = sizeof(FlatScanState);
+
+template <typename F, typename Sink>
+__global__ void __launch_bounds__(kScanThreads) scan_flat_kernel(int64_t n_host, const int64_t* n_dev, F f, Sink sink, FlatScanState* __restrict__ st,
+                                                                int64_t* __restrict__ total_dev, int tiles_per_block) {
+    __shared__ int64_t sw[kScanThreads / 32 + 1];
+    __shared__ unsigned int s_vb;
+    pdl_enter();
+    const int64_t n = n_dev ? min(*n_dev, n_host) : n_host;
+    if (threadIdx.x == 0) s_vb = atomicAdd(&st->ticket, 1u);
+    __syncthreads();
+    const unsigned int vb = s_vb;
+    const int64_t tile0 = (int64_t)vb * tiles_per_block;
+    // blocked arrangement: thread t owns kScanItems consecutive items of a tile
+    int32_t v[kScanItems];
+    int64_t s = 0, ex0 = 0, total;
+    if (tiles_per_block == 1) {  // the tile stays in registers
+        const int64_t base = tile0 * kScanTile + (int64_t)threadIdx.x * kScanItems;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (base + k < n) ? f(base + k) : 0;
+            s += v[k];
+        }
+        ex0 = block_exclusive_scan(s, sw, total);
+    } else {  // pass 1: sum of the range (strided: coalesced)
+        for (int t = 0; t < tiles_per_block; ++t) {
+            const int64_t base = (tile0 + t) * kScanTile;
+            if (base >= n) break;
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) {
+                const int64_t i = base + k * kScanThreads + threadIdx.x;
+                if (i < n) s += f(i);
+            }
+        }
+        block_exclusive_scan(s, sw, total);
+    }
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* slot = st->agg + vb;
+        *slot = (1ull << 63) | (unsigned long long)total;
+    }
+    // sum of all predecessors' totals: thread t waits for the words of blocks t, t + 256, ...
+    int64_t mine = 0;
+    for (unsigned int b = threadIdx.x; b < vb; b += kScanThreads) {
+        volatile const unsigned long long* slot = st->agg + b;
+        unsigned long long w;
+        do {
+            w = *slot;
+        } while (!(w >> 63));
+        mine += (int64_t)(w & ~(1ull << 63));
+    }
+    int64_t prefix;
+    block_exclusive_scan(mine, sw, prefix);  // `prefix` = block-wide total of `mine`
+    if (vb == gridDim.x - 1 && threadIdx.x == 0 && total_dev) *total_dev = prefix + total;
+    if (tiles_per_block == 1) {
+        const int64_t base = tile0 * kScanTile + (int64_t)threadIdx.x * kScanItems;
+        int64_t ex = ex0 + prefix;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            ex += v[k];
+            if (base + k < n) sink(base + k, v[k], ex);
+        }
+        return;
+    }
+    // pass 2: re-read (L2 hits), running carry over the tiles
+    int64_t carry = prefix;
+    for (int t = 0; t < tiles_per_block; ++t) {
+        const int64_t tbase = (tile0 + t) * kScanTile;
+        if (tbase >= n) break;
+        const int64_t base = tbase + (int64_t)threadIdx.x * kScanItems;
+        int64_t ts = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (base + k < n) ? f(base + k) : 0;
+            ts += v[k];
+        }
+        int64_t tile_total;
+        int64_t ex = block_exclusive_scan(ts, sw, tile_total) + carry;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            ex += v[k];
+            if (base + k < n) sink(base + k, v[k], ex);
+        }
+        carry += tile_total;
+    }
+}
+
+// Same contract as scan_inclusive_to; `state` = kFlatScanStateBytes of ZEROED device memory (consumed by this launch).
+template <typename F, typename Sink>
+inline int scan_flat_to(int64_t capacity, const int64_t* n_dev, F f, Sink sink, int64_t* total_dev, void* state, cudaStream_t stream) {
+    int64_t tiles = (capacity + kScanTile - 1) / kScanTile;
+    if (tiles == 0) tiles = 1;
+    const int blocks = (int)(tiles < kFlatScanBlocks ? tiles : kFlatScanBlocks);
+    const int tiles_per_block = (int)((tiles + blocks - 1) / blocks);
+    const int used = (int)((tiles + tiles_per_block - 1) / tiles_per_block);  // no trailing block without a tile
+    QED_CUDA_TRY(launch_pdl(scan_flat_kernel<F, Sink>, dim3((unsigned)used), dim3(kScanThreads), 0, stream, capacity, n_dev, f, sink,
+                            reinterpret_cast<FlatScanState*>(state), total_dev, tiles_per_block));
+    return QED_OK;
+}
+
 template <typename F>
 inline int scan_inclusive(int64_t capacity, const int64_t* n_dev, F f, int64_t* out, int64_t* total_dev, void* workspace, cudaStream_t stream) {
     return scan_inclusive_to(capacity, n_dev, f, ScanStore{out}, total_dev, workspace, stream);

@@ -382,7 +382,7 @@ class FusedSplatStep:
     @property
     def launches_per_step(self) -> int:
         """Launches of THIS library's kernels in one step() (memsets and torch's own fill kernels not counted):
-        project 1; intersections two_level: flag scan 3 (its last phase compacts) + Gaussian sort + gather scan 3 +
+        project 1; intersections two_level: flag scan 1 (single launch; its last phase compacts) + Gaussian sort + gather scan 1 +
         emit boundaries 1 + emit 1 + tile sort + compose/ranges 1 (a radix sort is 1 histogram + 1 kernel per 8-bit
         pass when it fits 444 blocks of 4096 pairs, else 3 kernels per pass); own/cub: scan 3 + emit 1 + sort + ranges 1; composite fwd 1, loss 3 (+2 with SSIM),
         composite bwd 1, project bwd 1.  Cross-checked against the ncu launch list (profiles/r02_step_ncu_summary.txt)."""
@@ -396,7 +396,7 @@ class FusedSplatStep:
             return 1 + passes if one_kernel_passes else 3 * passes
 
         if self.sort_impl == "two_level":
-            isect = 3 + radix(f["C"] * f["N"], 32 + cam_bits) + 3 + 1 + 1 + radix(f["M"], tile_bits + cam_bits) + 1
+            isect = 1 + radix(f["C"] * f["N"], 32 + cam_bits) + 1 + 1 + 1 + radix(f["M"], tile_bits + cam_bits) + 1
         else:
             end_bit = 32 + tile_bits + f["C"].bit_length()
             isect = 3 + 1 + (radix(f["M"], end_bit) if self.sort_impl == "own" else 8) + 1
