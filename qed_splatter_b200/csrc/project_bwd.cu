@@ -212,9 +212,25 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         const int64_t row0 = (int64_t)blockIdx.x * kProjBwdThreads + warp * 32;
         const float4* src = reinterpret_cast<const float4*>(p.colors_in) + row0 * (row_floats / 4);
         float4* wbuf = coefbuf + warp * 32 * Sh::kStrideVec;
-        for (int v = lane; v < 32 * Sh::kVec; v += 32) {
-            int r = v / Sh::kVec, j = v - r * Sh::kVec;
-            if ((warp_vis >> r) & 1u) cp_async16(wbuf + r * Sh::kStrideVec + j, src + (int64_t)r * (row_floats / 4) + j);
+        if (Sh::kVec == 12 && row_floats == 48) {
+            // degree 3, K = 16: 4 lanes per row, 8 rows per step -- row / column are bit operations of the lane plus
+            // compile-time constants (the generic loop below spends ~30 instructions per float4 on q / kVec and 64-bit
+            // address arithmetic: 16 % of the kernel's instructions)
+            const int r0 = lane >> 2, j0 = lane & 3;
+            const float4* s0 = src + r0 * 12 + j0;
+            float4* d0 = wbuf + r0 * Sh::kStrideVec + j0;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                if ((warp_vis >> (r0 + 8 * rr)) & 1u) {
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) cp_async16(d0 + rr * 8 * Sh::kStrideVec + 4 * jj, s0 + rr * 8 * 12 + 4 * jj);
+                }
+            }
+        } else {
+            for (int v = lane; v < 32 * Sh::kVec; v += 32) {
+                int r = v / Sh::kVec, j = v - r * Sh::kVec;
+                if ((warp_vis >> r) & 1u) cp_async16(wbuf + r * Sh::kStrideVec + j, src + (int64_t)r * (row_floats / 4) + j);
+            }
         }
         cp_async_commit();
     }
@@ -244,10 +260,11 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         }
         if ((p.activations & QED_ACT_LOGIT_OPACITIES) && p.opacities) opac = 1.0f / (1.0f + expf(-opac));
         qn = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
-        qw = q.x / qn;
-        qx = q.y / qn;
-        qy = q.z / qn;
-        qz = q.w / qn;
+        const float rqn = 1.0f / qn;  // one division, then products (IEEE `/` is a ~12-instruction sequence with a slow path)
+        qw = q.x * rqn;
+        qx = q.y * rqn;
+        qy = q.z * rqn;
+        qz = q.w * rqn;
         float R[9], M[9];  // R(q), M = R diag(s): rebuilt in the epilogue instead of living in 18 registers across the view loop
         quat_to_rotmat(qw, qx, qy, qz, R);
         for (int i = 0; i < 3; ++i) {
@@ -439,7 +456,8 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
                 } else {
                     float dx = m0 - cam.campos[0], dy = m1 - cam.campos[1], dz = m2 - cam.campos[2];
                     float dn = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
-                    float ux = dx / dn, uy = dy / dn, uz = dz / dn;
+                    const float rdn = 1.0f / dn;
+                    float ux = dx * rdn, uy = dy * rdn, uz = dz * rdn;
                     float b[16], vb[16];
                     sh_bases_b<DG>(ux, uy, uz, b);
 #pragma unroll
@@ -506,9 +524,9 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
                     float vux, vuy, vuz;
                     sh_bases_vjp<DG>(ux, uy, uz, vb, vux, vuy, vuz);
                     float dotp = vux * ux + vuy * uy + vuz * uz;
-                    vm0 += (vux - dotp * ux) / dn;
-                    vm1 += (vuy - dotp * uy) / dn;
-                    vm2 += (vuz - dotp * uz) / dn;
+                    vm0 += (vux - dotp * ux) * rdn;
+                    vm1 += (vuy - dotp * uy) * rdn;
+                    vm2 += (vuz - dotp * uz) * rdn;
                 }
             }
         }
@@ -544,7 +562,8 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         float vy = 2.0f * (qx * (vR[1] + vR[3]) + qz * (vR[5] + vR[7]) + qw * (vR[2] - vR[6]) - 2.0f * qy * (vR[0] + vR[8]));
         float vz = 2.0f * (qx * (vR[2] + vR[6]) + qy * (vR[5] + vR[7]) + qw * (vR[3] - vR[1]) - 2.0f * qz * (vR[0] + vR[4]));
         float dotq = vw * qw + vx * qx + vy * qy + vz * qz;
-        float4 vq = make_float4((vw - dotq * qw) / qn, (vx - dotq * qx) / qn, (vy - dotq * qy) / qn, (vz - dotq * qz) / qn);
+        const float rqn = 1.0f / qn;
+        float4 vq = make_float4((vw - dotq * qw) * rqn, (vx - dotq * qx) * rqn, (vy - dotq * qy) * rqn, (vz - dotq * qz) * rqn);
         p.v_means[n * 3 + 0] = vm0;
         p.v_means[n * 3 + 1] = vm1;
         p.v_means[n * 3 + 2] = vm2;
@@ -579,10 +598,22 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         float4* dst = reinterpret_cast<float4*>(p.v_colors_in) + row0 * row_vec;
         const float4* wbuf = vcoefbuf + warp * 32 * Sh::kStrideVec;
         const int rows = (p.N - row0) < 32 ? (int)(p.N - row0) : 32;
-        for (int q = lane; q < rows * row_vec; q += 32) {
-            int r = q / row_vec, j = q - r * row_vec;
-            float4 v = (j < Sh::kVec) ? wbuf[r * Sh::kStrideVec + j] : make_float4(0, 0, 0, 0);
-            dst[q] = v;
+        if (Sh::kVec == 12 && row_vec == 12) {  // same lane -> (row, column) mapping as the staging above
+            const int r0 = lane >> 2, j0 = lane & 3;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = r0 + 8 * rr;
+                if (r < rows) {
+#pragma unroll
+                    for (int jj = 0; jj < 3; ++jj) dst[r * 12 + j0 + 4 * jj] = wbuf[r * Sh::kStrideVec + j0 + 4 * jj];
+                }
+            }
+        } else {
+            for (int q = lane; q < rows * row_vec; q += 32) {
+                int r = q / row_vec, j = q - r * row_vec;
+                float4 v = (j < Sh::kVec) ? wbuf[r * Sh::kStrideVec + j] : make_float4(0, 0, 0, 0);
+                dst[q] = v;
+            }
         }
     }
 }

@@ -294,10 +294,26 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
             float4* wbuf = reinterpret_cast<float4*>(shbuf) + warp * 32 * Sh::kStrideVec;
             const float4* src = reinterpret_cast<const float4*>(p.colors_in) + row0 * (row_floats / 4);
             const int row_vec = row_floats / 4;
+            if (Sh::kVec == 12 && row_vec == 12) {
+                // degree 3, K = 16: 4 lanes per row, 8 rows per step -- row / column are bit operations of the lane plus
+                // compile-time constants (the generic loop below spends ~30 instructions per float4 on q / kVec and
+                // 64-bit address arithmetic)
+                const int r0 = lane >> 2, j0 = lane & 3;
+                const float4* s0 = src + r0 * 12 + j0;
+                float4* d0 = wbuf + r0 * Sh::kStrideVec + j0;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    if ((warp_vis >> (r0 + 8 * rr)) & 1u) {
+#pragma unroll
+                        for (int jj = 0; jj < 3; ++jj) cp_async16(d0 + rr * 8 * Sh::kStrideVec + 4 * jj, s0 + rr * 8 * 12 + 4 * jj);
+                    }
+                }
+            } else {
 #pragma unroll 4
-            for (int q = lane; q < 32 * Sh::kVec; q += 32) {
-                int r = q / Sh::kVec, j = q - r * Sh::kVec;
-                if ((warp_vis >> r) & 1u) cp_async16(wbuf + r * Sh::kStrideVec + j, src + (int64_t)r * row_vec + j);
+                for (int q = lane; q < 32 * Sh::kVec; q += 32) {
+                    int r = q / Sh::kVec, j = q - r * Sh::kVec;
+                    if ((warp_vis >> r) & 1u) cp_async16(wbuf + r * Sh::kStrideVec + j, src + (int64_t)r * row_vec + j);
+                }
             }
             cp_async_commit();
             cp_async_wait<0>();
