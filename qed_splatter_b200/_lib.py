@@ -69,6 +69,7 @@ DEBUG_SIGNATURES = {
     "qed_debug_set_raster_px": (c_int, [c_int, c_int]),
     "qed_debug_set_raster_packed": (c_int, [c_int]),
     "qed_debug_set_raster_bwd_minb": (c_int, [c_int]),
+    "qed_debug_set_raster_fwd_minb": (c_int, [c_int]),
     "qed_debug_set_radix_onesweep": (c_int, [c_int]),
     "qed_debug_set_flat_scan": (c_int, [c_int]),
 }

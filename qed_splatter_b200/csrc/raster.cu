@@ -430,10 +430,11 @@ __device__ __forceinline__ void fwd_pk_block(int a, const float4& A, const float
     T2 = mul2(T2, sub2(bc2(1.0f), al2));  // == nT2 where updated (same two roundings), T * 1 elsewhere
 }
 
-// 14 resident CTAs per SM asked of ptxas (72 registers, no spills; 16 would rematerialise pixel coordinates
-// inside the inner loop).
-template <int D, bool CULL, bool STATS>
-__global__ void __launch_bounds__(Shape<4>::kThreads, 14) raster_fwd_ws_kernel(const RasterParams p) {
+// MINB resident CTAs per SM asked of ptxas: 12 -> 78 registers (default), 14 -> 72; the pixel coordinate stays in a register
+// through pin_reg.  More resident warps do not help (the kernel is bound by issue slots and the fp32 / ALU pipes, not by
+// latency): 16 CTAs (64 registers) measured 1 % slower, 12 1 % faster than 14.  qed_debug_set_raster_fwd_minb.
+template <int D, bool CULL, bool STATS, int MINB>
+__global__ void __launch_bounds__(Shape<4>::kThreads, MINB) raster_fwd_ws_kernel(const RasterParams p) {
     using S = Shape<4>;
     __shared__ WarpStream wss[S::kWarps];
     StatCounters<STATS> st;
@@ -1051,7 +1052,8 @@ __device__ __forceinline__ void reduce_entries(const RasterParams& p, const Redu
     }
 }
 
-// MINB resident CTAs per SM asked of ptxas: 12 -> 80 registers, 10 -> 96 (qed_debug_set_raster_bwd_minb).
+// MINB resident CTAs per SM asked of ptxas: 10 -> 96 registers, no spills (default); 8 -> 102 registers, 3 % slower; 12 ->
+// 80 registers with spills, 1 % slower (qed_debug_set_raster_bwd_minb).
 template <int D, bool CULL, bool STATS, int MINB>
 __global__ void __launch_bounds__(Shape<4>::kThreads, MINB) raster_bwd_ws_kernel(const RasterParams p) {
     using S = Shape<4>;
@@ -1208,8 +1210,10 @@ static thread_local int g_raster_cull = 1;                           // 0 disabl
 static thread_local unsigned long long* g_raster_counters = nullptr;  // device uint64[6] -> STATS kernels
 static thread_local int g_px_fwd = 4, g_px_bwd = 4;                   // pixels per lane
 static thread_local int g_raster_packed = 1;                          // f32x2 kernels where they exist (backward, 4 px/lane)
-constexpr int kBwdMinBlocks = 12, kBwdMinBlocksAlt = 10;              // resident CTAs per SM asked of ptxas (80 / 96 registers)
+constexpr int kBwdMinBlocks = 10, kBwdMinBlocksAlt = 8;               // resident CTAs per SM asked of ptxas (96 / 128 registers; 12 = 80 registers was 1 % slower)
 static thread_local int g_bwd_minb = kBwdMinBlocks;
+constexpr int kFwdMinBlocks = 12, kFwdMinBlocksAlt = 14;              // forward: 78 / 72 registers (measured at S1: 12 is 1 % faster than 14, 16 = 64 registers 1 % slower)
+static thread_local int g_fwd_minb = kFwdMinBlocks;
 
 template <int D, int PX, bool BWD>
 static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
@@ -1218,11 +1222,14 @@ static void launch_raster_px(const RasterParams& p, cudaStream_t stream) {
     const bool cull = g_raster_cull != 0, stats = p.counters != nullptr;
     if (!BWD && PX == 4 && g_raster_packed) {
         if (stats) {
-            if (cull) (void)launch_pdl(raster_fwd_ws_kernel<D, true, true>, grid, dim3(T), 0, stream, p);
-            else (void)launch_pdl(raster_fwd_ws_kernel<D, false, true>, grid, dim3(T), 0, stream, p);
+            if (cull) (void)launch_pdl(raster_fwd_ws_kernel<D, true, true, kFwdMinBlocks>, grid, dim3(T), 0, stream, p);
+            else (void)launch_pdl(raster_fwd_ws_kernel<D, false, true, kFwdMinBlocks>, grid, dim3(T), 0, stream, p);
+        } else if (!cull) {
+            (void)launch_pdl(raster_fwd_ws_kernel<D, false, false, kFwdMinBlocks>, grid, dim3(T), 0, stream, p);
+        } else if (g_fwd_minb == kFwdMinBlocksAlt) {
+            (void)launch_pdl(raster_fwd_ws_kernel<D, true, false, kFwdMinBlocksAlt>, grid, dim3(T), 0, stream, p);
         } else {
-            if (cull) (void)launch_pdl(raster_fwd_ws_kernel<D, true, false>, grid, dim3(T), 0, stream, p);
-            else (void)launch_pdl(raster_fwd_ws_kernel<D, false, false>, grid, dim3(T), 0, stream, p);
+            (void)launch_pdl(raster_fwd_ws_kernel<D, true, false, kFwdMinBlocks>, grid, dim3(T), 0, stream, p);
         }
     } else if (!BWD) {
         if (stats) {
@@ -1326,6 +1333,12 @@ extern "C" int qed_debug_set_raster_packed(int enabled) {
 extern "C" int qed_debug_set_raster_bwd_minb(int minb) {
     int old = g_bwd_minb;
     if (minb == kBwdMinBlocks || minb == kBwdMinBlocksAlt) g_bwd_minb = minb;
+    return old;
+}
+
+extern "C" int qed_debug_set_raster_fwd_minb(int minb) {
+    int old = g_fwd_minb;
+    if (minb == kFwdMinBlocks || minb == kFwdMinBlocksAlt) g_fwd_minb = minb;
     return old;
 }
 
