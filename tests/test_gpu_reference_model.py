@@ -120,3 +120,28 @@ def test_unmodified_reference_model_runs_on_the_cuda_shim(cuda, name):
         assert hasattr(xys, "absgrad") and xys.absgrad.shape == (1, s.N, 2)
         assert bool((xys.absgrad >= xys.grad.abs() - 1e-12).all())
         assert model.info["width"] == s.width and model.info["n_cameras"] == 1
+
+
+@pytest.mark.skipif(rm.reference_root() is None, reason="reference package not on this machine (baseline/_ref not built)")
+def test_reference_model_with_get_viewmat_rebound_to_the_kernel(cuda):
+    """Row a1: `qed_splatter.model.get_viewmat = qed_splatter_b200.get_viewmat` -- the unmodified model
+    then builds its viewmat (model.py:246) with the one-launch kernel; the kernel must agree with the reference's own
+    function on the model's camera to the last bits that matter (rotation block exact, translation to 1 ulp of the sum)
+    and the step must reproduce the fixture."""
+    from qed_splatter_b200 import get_viewmat
+
+    z, s, cam, step, mask = _load("ref_model_plain")
+    with rm.reference_modules("cuda") as mod:
+        model = rm.build_model(mod, s, cuda, step=step)
+        model.train()
+        camera = rm.make_camera(s, cam, cuda)
+        ref_vm = mod.get_viewmat(camera.camera_to_worlds)  # the reference's own lines on the GPU
+        got_vm = get_viewmat(camera.camera_to_worlds)
+        assert torch.equal(got_vm[:, :3, :3], ref_vm[:, :3, :3]) and torch.equal(got_vm[:, 3], ref_vm[:, 3])
+        torch.testing.assert_close(got_vm, ref_vm, rtol=0, atol=2e-6)
+        mod.get_viewmat = get_viewmat
+        out = model.get_outputs(camera)
+        loss = model.get_loss_dict(out, {"image": s.gt_rgb[cam].to(cuda), "depth_image": s.gt_depth[cam].to(cuda)})
+        for k in ("rgb", "depth", "accumulation"):
+            assert_close_frac(out[k], torch.from_numpy(z[k]), 1e-4, 1e-4, 2e-3, k)
+        assert float(loss["depth_loss"]) == pytest.approx(float(z["depth_loss"]), rel=2e-4, abs=1e-6)
