@@ -159,17 +159,22 @@ __device__ __forceinline__ void quat_to_rotmat(float qw, float qx, float qy, flo
 // DEG=-1: colours pass through.  VEC: coefficient rows 16-byte aligned and K*3 % 4 == 0.
 // XCH (multi-GPU view-colour exchange, VEC only): no coefficient gradient is built or written (half the shared memory, 192 B
 // per Gaussian less HBM traffic); the gated colour gradient goes to every rank's exchange buffer instead.
-template <int DEG, bool VEC, bool XCH = false>
-__global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const ProjBwdParams p) {
+// ONE (a single view, VEC only -- the reference's case, model.py:211): the coefficient gradient b (x) vpre needs no sum over
+// views, so it overwrites the staged coefficient row in place: half the shared memory, and with it 5 resident blocks per SM
+// instead of 4 (the kernel is latency-bound: 35 % issue-active at 16 warps per SM).  ONE = resident blocks asked of ptxas (5: 96
+// registers, 6: 80 registers).
+template <int DEG, bool VEC, bool XCH = false, int ONE = 0>
+__global__ void __launch_bounds__(kProjBwdThreads, ONE ? ONE : 4) project_bwd_kernel(const ProjBwdParams p) {
     extern __shared__ float4 smem4[];
     pdl_enter();
+    const int nC = ONE ? 1 : p.C;  // ONE: the view loops collapse at compile time
     CamB* cams = reinterpret_cast<CamB*>(smem4);
     constexpr int DG = DEG < 0 ? 0 : DEG;
     using Sh = ShShapeB<DG>;
-    float4* coefbuf = smem4 + p.C * (kCamFloatsB / 4);
-    float4* vcoefbuf = coefbuf + kProjBwdThreads * Sh::kStrideVec;
+    float4* coefbuf = smem4 + nC * (kCamFloatsB / 4);
+    float4* vcoefbuf = ONE ? coefbuf : coefbuf + kProjBwdThreads * Sh::kStrideVec;
 
-    for (int c = threadIdx.x; c < p.C; c += kProjBwdThreads) load_camera_b(p.viewmats + c * 16, p.Ks + c * 9, p.width, p.height, cams[c]);
+    for (int c = threadIdx.x; c < nC; c += kProjBwdThreads) load_camera_b(p.viewmats + c * 16, p.Ks + c * 9, p.width, p.height, cams[c]);
     __syncthreads();
 
     const int n = blockIdx.x * kProjBwdThreads + threadIdx.x;
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
     if (in_range) {
         rad0 = p.radii[n];
         anyvis = rad0 > 0;
-        for (int c = 1; c < p.C; ++c) anyvis |= p.radii[(int64_t)c * p.N + n] > 0;
+        for (int c = 1; c < nC; ++c) anyvis |= p.radii[(int64_t)c * p.N + n] > 0;
         m0 = p.means[n * 3 + 0];
         m1 = p.means[n * 3 + 1];
         m2 = p.means[n * 3 + 2];
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
         pfb = p.conics[(int64_t)n * 3 + 1];
         pfc = p.conics[(int64_t)n * 3 + 2];
     }
-    if (use_sh && !XCH) {
+    if (use_sh && !XCH && (!ONE || !anyvis)) {  // ONE: the rows of visible Gaussians are being filled by cp.async; nobody touches the others
 #pragma unroll
         for (int j = 0; j < Sh::kVec; ++j) my_vcoef[j] = make_float4(0, 0, 0, 0);
     }
@@ -289,12 +294,12 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
 
     if (in_range && anyvis) {
         int rad_c = rad0;
-        for (int c = 0; c < p.C; ++c) {
+        for (int c = 0; c < nC; ++c) {
             const int64_t idx = (int64_t)c * p.N + n;
             const bool vis = rad_c > 0;
             const float4 r0 = pf0, r1 = pf1, r2 = pf2;
             const float ca = pfa, cb = pfb, cc = pfc;  // conic of the blurred covariance (stored by the forward)
-            if (c + 1 < p.C) {  // next view: radius, upstream gradients, conic
+            if (c + 1 < nC) {  // next view: radius, upstream gradients, conic
                 const int64_t nx = idx + p.N;
                 rad_c = p.radii[nx];
                 if (rad_c > 0) {
@@ -501,8 +506,14 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
                         for (int j = 0; j < Sh::kVec; ++j) {
                             float4 cf = my_coef[j];
                             float cfa[4] = {cf.x, cf.y, cf.z, cf.w};
-                            float4 acc = my_vcoef[j];
-                            float out[4] = {acc.x, acc.y, acc.z, acc.w};
+                            float out[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                            if (!ONE) {
+                                const float4 acc = my_vcoef[j];
+                                out[0] = acc.x;
+                                out[1] = acc.y;
+                                out[2] = acc.z;
+                                out[3] = acc.w;
+                            }
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int f = 4 * j + i;
@@ -618,12 +629,12 @@ __global__ void __launch_bounds__(kProjBwdThreads, 4) project_bwd_kernel(const P
     }
 }
 
-template <int DEG, bool VEC, bool XCH = false>
+template <int DEG, bool VEC, bool XCH = false, int ONE = 0>
 static int launch_project_bwd(const ProjBwdParams& p, cudaStream_t stream) {
     using Sh = ShShapeB<(DEG < 0 ? 0 : DEG)>;
     size_t smem = (size_t)p.C * kCamFloatsB * 4;
-    if (DEG >= 0 && p.n_color > 0) smem += (size_t)(XCH ? 1 : 2) * kProjBwdThreads * Sh::kStrideVec * 16;
-    auto kern = project_bwd_kernel<DEG, VEC, XCH>;
+    if (DEG >= 0 && p.n_color > 0) smem += (size_t)((XCH || ONE) ? 1 : 2) * kProjBwdThreads * Sh::kStrideVec * 16;
+    auto kern = project_bwd_kernel<DEG, VEC, XCH, ONE>;
     if (smem > 48 * 1024) QED_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (p.N + kProjBwdThreads - 1) / kProjBwdThreads;
     QED_CUDA_TRY(launch_pdl(kern, dim3(blocks), dim3(kProjBwdThreads), smem, stream, p));
@@ -711,6 +722,14 @@ static int launch_sh_grad(int V, int N, int K, const float* means, const float4*
 
 using namespace qed;
 
+// test hook (thread-local): 0 = the single-view specialisation of the projection backward is not used
+static thread_local int g_projbwd_one = 5;
+extern "C" int qed_debug_set_project_bwd_one(int blocks) {  // 0 = off, 5 / 6 = resident blocks per SM of the specialisation
+    int old = g_projbwd_one;
+    g_projbwd_one = (blocks == 6) ? 6 : (blocks ? 5 : 0);
+    return old;
+}
+
 static int project_bwd_impl(int C, int N, const float* means, const float* quats, const float* scales,
                             const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
                             int colors_per_camera, const float* viewmats, const float* Ks, int width, int height,
@@ -787,7 +806,10 @@ static int project_bwd_impl(int C, int N, const float* means, const float* quats
         case 0: return vec_ok ? launch_project_bwd<0, true>(p, stream) : launch_project_bwd<0, false>(p, stream);
         case 1: return vec_ok ? launch_project_bwd<1, true>(p, stream) : launch_project_bwd<1, false>(p, stream);
         case 2: return vec_ok ? launch_project_bwd<2, true>(p, stream) : launch_project_bwd<2, false>(p, stream);
-        case 3: return vec_ok ? launch_project_bwd<3, true>(p, stream) : launch_project_bwd<3, false>(p, stream);
+        case 3:
+            if (vec_ok && p.C == 1 && g_projbwd_one == 6) return launch_project_bwd<3, true, false, 6>(p, stream);
+            if (vec_ok && p.C == 1 && g_projbwd_one) return launch_project_bwd<3, true, false, 5>(p, stream);
+            return vec_ok ? launch_project_bwd<3, true>(p, stream) : launch_project_bwd<3, false>(p, stream);
         default: return launch_project_bwd<-1, false>(p, stream);
     }
 }
