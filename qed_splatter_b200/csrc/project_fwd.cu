@@ -129,15 +129,18 @@ struct ShShape {
 };
 
 // DEG = -1: colours pass through (or no colour channels at all).  VEC: 16-byte staging path.
-template <int DEG, bool VEC>
-__global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwdParams p) {
+// ONE != 0: a single view (the reference's case, model.py:211) -- the view loops and the visibility mask collapse at compile
+// time (78 -> 68 registers); ONE = resident blocks per SM asked of ptxas (4: 64 registers, 32 warps per SM).
+template <int DEG, bool VEC, int ONE = 0>
+__global__ void __launch_bounds__(kProjThreads, ONE ? ONE : 1) project_fwd_kernel(const ProjFwdParams p) {
     extern __shared__ float4 smem4[];
     pdl_enter();
+    const int nC = ONE ? 1 : p.Cc, c0 = ONE ? 0 : p.c0;
     Cam* cams = reinterpret_cast<Cam*>(smem4);
-    float* shbuf = reinterpret_cast<float*>(smem4 + p.Cc * (kCamFloats / 4));
+    float* shbuf = reinterpret_cast<float*>(smem4 + nC * (kCamFloats / 4));
 
-    if (threadIdx.x < p.Cc) {
-        int c = p.c0 + threadIdx.x;
+    if (threadIdx.x < nC) {
+        int c = c0 + threadIdx.x;
         load_camera(p.viewmats + c * 16, p.Ks + c * 9, p.width, p.height, cams[threadIdx.x]);
     }
     __syncthreads();
@@ -187,11 +190,11 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
     }
 
     uint32_t vismask = 0;
-    for (int ci = 0; ci < p.Cc; ++ci) {
+    for (int ci = 0; ci < nC; ++ci) {
         if (!in_range) break;
         const Cam& cam = cams[ci];
         const float* W = cam.W;
-        const int64_t idx = (int64_t)(p.c0 + ci) * p.N + n;
+        const int64_t idx = (int64_t)(c0 + ci) * p.N + n;
         float px = add(mad3(W[0], m0, W[1], m1, W[2], m2), cam.t[0]);
         float py = add(mad3(W[3], m0, W[4], m1, W[5], m2), cam.t[1]);
         float pz = add(mad3(W[6], m0, W[7], m1, W[8], m2), cam.t[2]);
@@ -277,8 +280,8 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
     if (DEG < 0) {
         // colours pass through ([N,3] or [C,N,3]); culled entries get zeros
         if (!in_range) return;
-        for (int ci = 0; ci < p.Cc; ++ci) {
-            const int64_t idx = (int64_t)(p.c0 + ci) * p.N + n;
+        for (int ci = 0; ci < nC; ++ci) {
+            const int64_t idx = (int64_t)(c0 + ci) * p.N + n;
             const float* src = p.colors_in + (p.colors_per_camera ? idx * 3 : (int64_t)n * 3);
             bool vis = (vismask >> ci) & 1u;
 #pragma unroll
@@ -330,8 +333,8 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
         if (!in_range || vismask == 0) {
             // still have to zero the colour channels of culled entries
             if (in_range) {
-                for (int ci = 0; ci < p.Cc; ++ci) {
-                    const int64_t idx = (int64_t)(p.c0 + ci) * p.N + n;
+                for (int ci = 0; ci < nC; ++ci) {
+                    const int64_t idx = (int64_t)(c0 + ci) * p.N + n;
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) p.colors_out[idx * D + ch] = 0.0f;
                 }
@@ -354,8 +357,8 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
 #pragma unroll
             for (int j = 0; j < Sh::kFloats; ++j) coef[j] = row[j];
         }
-        for (int ci = 0; ci < p.Cc; ++ci) {
-            const int64_t idx = (int64_t)(p.c0 + ci) * p.N + n;
+        for (int ci = 0; ci < nC; ++ci) {
+            const int64_t idx = (int64_t)(c0 + ci) * p.N + n;
             float r = 0, g = 0, b = 0;
             if ((vismask >> ci) & 1u) {
                 const Cam& cam = cams[ci];
@@ -392,12 +395,12 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(const ProjFwd
     }
 }
 
-template <int DEG, bool VEC>
+template <int DEG, bool VEC, int ONE = 0>
 static int launch_project_fwd(const ProjFwdParams& p, cudaStream_t stream) {
     using Sh = ShShape<(DEG < 0 ? 0 : DEG)>;
     size_t smem = (size_t)p.Cc * kCamFloats * 4;
     if (DEG >= 0 && p.n_color > 0) smem += (size_t)kProjThreads * (VEC ? Sh::kStrideVec * 16 : Sh::kStrideScalar * 4);
-    auto kern = project_fwd_kernel<DEG, VEC>;
+    auto kern = project_fwd_kernel<DEG, VEC, ONE>;
     if (smem > 48 * 1024) QED_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = (p.N + kProjThreads - 1) / kProjThreads;
     QED_CUDA_TRY(launch_pdl(kern, dim3(blocks), dim3(kProjThreads), smem, stream, p));
@@ -407,6 +410,14 @@ static int launch_project_fwd(const ProjFwdParams& p, cudaStream_t stream) {
 }  // namespace qed
 
 using namespace qed;
+
+// test hook (thread-local): 0 = generic kernel, 3 / 4 = single-view specialisation with that many resident blocks per SM
+static thread_local int g_projfwd_one = 4;
+extern "C" int qed_debug_set_project_fwd_one(int blocks) {
+    int old = g_projfwd_one;
+    g_projfwd_one = (blocks == 4) ? 4 : (blocks ? 3 : 0);
+    return old;
+}
 
 extern "C" int qed_project_fwd(int C, int N, const float* means, const float* quats, const float* scales,
                                const float* opacities, int activations, const float* colors_in, int K, int sh_degree,
@@ -478,7 +489,11 @@ extern "C" int qed_project_fwd(int C, int N, const float* means, const float* qu
             case 0: rc = vec_ok ? launch_project_fwd<0, true>(p, stream) : launch_project_fwd<0, false>(p, stream); break;
             case 1: rc = vec_ok ? launch_project_fwd<1, true>(p, stream) : launch_project_fwd<1, false>(p, stream); break;
             case 2: rc = vec_ok ? launch_project_fwd<2, true>(p, stream) : launch_project_fwd<2, false>(p, stream); break;
-            case 3: rc = vec_ok ? launch_project_fwd<3, true>(p, stream) : launch_project_fwd<3, false>(p, stream); break;
+            case 3:
+                if (vec_ok && p.Cc == 1 && p.c0 == 0 && g_projfwd_one == 4) rc = launch_project_fwd<3, true, 4>(p, stream);
+                else if (vec_ok && p.Cc == 1 && p.c0 == 0 && g_projfwd_one) rc = launch_project_fwd<3, true, 3>(p, stream);
+                else rc = vec_ok ? launch_project_fwd<3, true>(p, stream) : launch_project_fwd<3, false>(p, stream);
+                break;
             default: rc = launch_project_fwd<-1, false>(p, stream); break;
         }
         if (rc != QED_OK) return rc;
