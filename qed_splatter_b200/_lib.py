@@ -72,6 +72,7 @@ DEBUG_SIGNATURES = {
     "qed_debug_set_raster_fwd_minb": (c_int, [c_int]),
     "qed_debug_set_radix_onesweep": (c_int, [c_int]),
     "qed_debug_set_flat_scan": (c_int, [c_int]),
+    "qed_debug_set_radix_small_tiles": (c_int, [c_int]),
     "qed_debug_set_project_bwd_one": (c_int, [c_int]),
     "qed_debug_set_project_fwd_one": (c_int, [c_int]),
 }

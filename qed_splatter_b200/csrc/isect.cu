@@ -162,6 +162,12 @@ extern "C" int qed_debug_set_radix_onesweep(int enabled) {
     return old;
 }
 
+extern "C" int qed_debug_set_radix_small_tiles(int enabled) {
+    int old = g_radix_small_tiles;
+    g_radix_small_tiles = enabled ? 1 : 0;
+    return old;
+}
+
 // 1 (default): the two scans of qed_isect_prepare run as single launches (scan_flat_to); 0: three launches each.
 static thread_local int g_flat_scan = 1;
 extern "C" int qed_debug_set_flat_scan(int enabled) {

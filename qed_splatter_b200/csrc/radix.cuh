@@ -9,6 +9,7 @@
 
 namespace qed {
 
+static thread_local int g_radix_small_tiles = 0;  // test hook (qed_debug_set_radix_small_tiles): half-size tiles for small look-back sorts (measured SLOWER, off)
 static thread_local int g_radix_onesweep = 1;  // test hook (qed_debug_set_radix_onesweep), thread-local: 0 = three kernels per pass
 
 constexpr int kSortThreads = 256;
@@ -317,19 +318,24 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <typename KeyT>
-__global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(int64_t n_host, const int64_t* n_dev, const KeyT* __restrict__ keys_in,
+// ITEMS pairs per thread: 16 (the tile of the three-kernel passes) or 8 -- a sort of a few hundred thousand pairs has ~1 block
+// of 4096 per SM, so a pass costs one block's serial work (16 ranking rounds per warp) + the look-back; half-size tiles double
+// the parallelism.  MEASURED at S1 (668 k keys, 4 passes): isect_prepare 0.122 -> 0.133 ms with ITEMS = 8 -- twice the blocks make
+// the look-back walk longer than the ranking gets shorter -- so 16 stays the default and 8 is only reachable through the hook.
+template <typename KeyT, int ITEMS>
+__global__ void __launch_bounds__(kSortThreads, ITEMS == 16 ? 3 : 4) radix_onesweep_kernel(int64_t n_host, const int64_t* n_dev, const KeyT* __restrict__ keys_in,
                                                                         const int32_t* __restrict__ vals_in, KeyT* __restrict__ keys_out,
                                                                         int32_t* __restrict__ vals_out, int shift, uint32_t mask, int pass,
                                                                         const uint32_t* __restrict__ hist_all, uint64_t* __restrict__ status,
                                                                         uint32_t* __restrict__ tickets) {
+    constexpr int kTile = kSortThreads * ITEMS;
     constexpr int kWarps = kSortThreads / 32;
-    constexpr int kPerWarp = kSortTile / kWarps;
+    constexpr int kPerWarp = kTile / kWarps;
     constexpr int kRounds = kPerWarp / 32;
     extern __shared__ __align__(16) unsigned char sort_smem[];
     KeyT* skeys = reinterpret_cast<KeyT*>(sort_smem);
-    int32_t* svals = reinterpret_cast<int32_t*>(skeys + kSortTile);
-    uint32_t(*warp_hist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(svals + kSortTile);
+    int32_t* svals = reinterpret_cast<int32_t*>(skeys + kTile);
+    uint32_t(*warp_hist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(svals + kTile);
     uint32_t* digit_start = &warp_hist[0][0] + kWarps * kRadix;
     uint32_t* global_base = digit_start + kRadix;
     uint32_t* sscan = global_base + kRadix;  // [16]
@@ -344,9 +350,9 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(int64_t
     for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&warp_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t vb = s_ticket;  // virtual block id: tiles are handed out in ticket order
-    const int64_t base = (int64_t)vb * kSortTile;
+    const int64_t base = (int64_t)vb * kTile;
     if (base >= n) return;
-    const int tile_n = (n - base) < kSortTile ? (int)(n - base) : kSortTile;
+    const int tile_n = (n - base) < kTile ? (int)(n - base) : kTile;
 
     KeyT key[kRounds];
     int32_t val[kRounds];
@@ -481,8 +487,9 @@ inline size_t radix_hist_bytes(int64_t capacity) {
     if (nb < 1) nb = 1;
     // [two per-block histograms + digit totals] for the three-kernel passes, [status words + all-pass histogram +
     // tickets] for the single-kernel passes
+    // (status words: one per (block, digit); the half-size-tile passes have 2 nb blocks)
     return 2 * (((size_t)kRadix * nb * 4 + 255) / 256 * 256) + ((kRadix * 4 + 255) / 256 * 256) +
-           (((size_t)kRadix * nb * 8 + 255) / 256 * 256) + ((size_t)(kMaxPasses * kRadix + kMaxPasses) * 4 + 255) / 256 * 256;
+           (((size_t)kRadix * 2 * nb * 8 + 255) / 256 * 256) + ((size_t)(kMaxPasses * kRadix + kMaxPasses) * 4 + 255) / 256 * 256;
 }
 
 // Sort on key bits [0, end_bit).  Result lands in (keys_out, vals_out); (tmp_keys, tmp_vals) is the
@@ -506,14 +513,18 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
     }
     if (!seg.counts && g_radix_onesweep && passes <= kMaxPasses && (nb <= kOnesweepMaxBlocks || g_radix_onesweep > 1)) {
         char* ows = reinterpret_cast<char*>(hist_ws) + 2 * hist_bytes + ((kRadix * 4 + 255) / 256 * 256);
+        // half-size tiles while the whole sort is <= 2 blocks of 4096 per SM (g_radix_small_tiles: test hook)
+        const bool small = g_radix_small_tiles && nb <= 2 * 148;
+        const int nbk = small ? (int)((capacity + kSortTile / 2 - 1) / (kSortTile / 2)) : nb;
         uint64_t* status = reinterpret_cast<uint64_t*>(ows);
-        const size_t status_bytes = ((size_t)kRadix * nb * 8 + 255) / 256 * 256;
+        const size_t status_bytes = ((size_t)kRadix * 2 * nb * 8 + 255) / 256 * 256;
         uint32_t* hist_all = reinterpret_cast<uint32_t*>(ows + status_bytes);
         uint32_t* tickets = hist_all + kMaxPasses * kRadix;
         QED_CUDA_TRY(cudaMemsetAsync(ows, 0, status_bytes + (size_t)(kMaxPasses * kRadix + kMaxPasses) * 4, stream));
         QED_CUDA_TRY(launch_pdl(radix_histogram_kernel<KeyT>, dim3(nb), dim3(kSortThreads), 0, stream, capacity, n_dev, keys_in, passes, end_bit, hist_all));
-        auto one = radix_onesweep_kernel<KeyT>;
-        QED_CUDA_TRY(cudaFuncSetAttribute(one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RadixSmem<KeyT>::kBytes));
+        auto one = small ? radix_onesweep_kernel<KeyT, 8> : radix_onesweep_kernel<KeyT, 16>;
+        const size_t one_smem = small ? RadixSmem<KeyT>::kBytes - (size_t)(kSortTile / 2) * (sizeof(KeyT) + 4) : RadixSmem<KeyT>::kBytes;
+        QED_CUDA_TRY(cudaFuncSetAttribute(one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)one_smem));
         const KeyT* sk = keys_in;
         const int32_t* sv = vals_in;
         for (int pass = 0; pass < passes; ++pass) {
@@ -521,7 +532,7 @@ inline int radix_sort_pairs(int64_t capacity, const int64_t* n_dev, const KeyT* 
             KeyT* dk = to_out ? keys_out : tmp_keys;
             int32_t* dv = to_out ? vals_out : tmp_vals;
             const int bits = (end_bit - pass * 8) < 8 ? (end_bit - pass * 8) : 8;
-            QED_CUDA_TRY(launch_pdl(one, dim3(nb), dim3(kSortThreads), RadixSmem<KeyT>::kBytes, stream, capacity, n_dev, sk, sv, dk, dv, pass * 8,
+            QED_CUDA_TRY(launch_pdl(one, dim3(nbk), dim3(kSortThreads), one_smem, stream, capacity, n_dev, sk, sv, dk, dv, pass * 8,
                                     (1u << bits) - 1u, pass, hist_all, status, tickets));
             sk = dk;
             sv = dv;
