@@ -206,8 +206,8 @@ int qed_raster_fwd(int C, int N, int64_t n_isects, int D, const float* geom, con
  *  v_render[C,H,W,D], v_alphas[C,H,W] (NULL = zero): gradients w.r.t. the OUTPUTS of qed_raster_fwd
  *  (i.e. after ED normalisation when normalize_last).
  *  packed_grads[C*N,12] ACCUMULATES (caller zero-fills): {v_mx,v_my,|v_mx|,|v_my| | v_conic a,b,c,
- *  v_opacity | v_colour[0..D-1], 0..}.  Per-Gaussian sums are warp-reduced by shuffles, then one
- *  atomic add per value per warp.
+ *  v_opacity | v_colour[0..D-1], 0..}.  Per warp and Gaussian the 12 values are summed over the lanes (transposed through
+ *  shared memory) and added with vector reductions (red.global.add.v4.f32): the sums are order-dependent in the last bits.
  */
 int qed_raster_bwd(int C, int N, int64_t n_isects, int D, const float* geom, const float* colors,
                    const float* backgrounds, int width, int height, int tile_size, int tile_width,
