@@ -260,3 +260,43 @@ def test_isect_full_size_paths_agree(cuda):
     counts = torch.bincount(tile_of_entry, minlength=tw * th)
     ends = torch.cat([off[1:], torch.tensor([ids.numel()], device=cuda)])
     assert torch.equal(ends - off, counts)
+
+
+@pytest.mark.parametrize("N", [5003, 129])
+def test_single_view_specialisations_equal_generic_kernels(cuda, N):
+    """The reference renders one camera per step (model.py:211): the projection kernels have single-view instantiations
+    (view loops collapsed at compile time, forward at 4 resident blocks, backward writing the SH gradient over the staged
+    row).  They must be the generic kernels' results: forward bit for bit against a 3-view launch's slice, backward
+    against the generic kernel (hook) to float reassociation."""
+    from qed_splatter_b200 import _lib
+
+    lib = _lib.load()
+    s = scene_s0(N=N, C=3, size=112)  # N not a multiple of the 128 / 256-thread blocks
+    s.means = s.means * 2.0
+    g = s.to(cuda)
+    full = ops.project_gaussians(g.means, g.quats, g.scales, g.opacities, g.sh, g.viewmats, g.Ks, g.width, g.height, sh_degree=3)
+    for c in range(s.C):
+        one = ops.project_gaussians(g.means, g.quats, g.scales, g.opacities, g.sh, g.viewmats[c:c + 1].contiguous(), g.Ks[c:c + 1].contiguous(),
+                                    g.width, g.height, sh_degree=3)
+        for a, b, name in zip(one, full, ("radii", "means2d", "depths", "conics", "comps", "colors", "opac", "tiles", "geom", "tiles_exact")):
+            if b.numel():
+                assert torch.equal(a[0], b[c]), f"view {c}: {name}"
+    # backward: specialised vs generic instantiation on the same single view
+    grads = {}
+    for mode in (5, 0, 6):
+        old_b = lib.qed_debug_set_project_bwd_one(mode)
+        old_f = lib.qed_debug_set_project_fwd_one(4 if mode else 0)
+        try:
+            leaves = [t.clone().requires_grad_(True) for t in (g.means, g.quats, g.scales, g.opacities, g.sh)]
+            out = ops.project_gaussians(*leaves, g.viewmats[1:2].contiguous(), g.Ks[1:2].contiguous(), g.width, g.height, sh_degree=3)
+            gen = torch.Generator(device="cpu").manual_seed(3)
+            loss = sum((o * torch.randn(o.shape, generator=gen).to(cuda)).sum() for o in (out[1], out[2], out[3], out[5], out[6]))
+            loss.backward()
+            grads[mode] = [t.grad.clone() for t in leaves]
+        finally:
+            lib.qed_debug_set_project_bwd_one(old_b)
+            lib.qed_debug_set_project_fwd_one(old_f)
+    for mode in (5, 6):
+        for a, b, name in zip(grads[mode], grads[0], ("means", "quats", "scales", "opacities", "sh")):
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=1e-6 * float(b.abs().max()), msg=lambda m: f"mode {mode} v_{name}: {m}")
+    assert torch.equal(grads[5][4], grads[0][4]), "SH coefficient gradient of one view is a product, not a sum: identical"
