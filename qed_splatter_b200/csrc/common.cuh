@@ -22,7 +22,7 @@
 
 namespace qed {
 
-// ---- programmatic dependent launch (sm_90+): a step is a chain of ~28 mostly short kernels on one stream.  Every
+// ---- programmatic dependent launch (sm_90+): a step is a chain of ~23 mostly short kernels on one stream.  Every
 // hot-path kernel starts with pdl_enter(): `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be
 // scheduled as soon as every CTA of this one has started (its CTAs then fill the slots this kernel's tail leaves
 // empty), `griddepcontrol.wait` holds this kernel until every kernel before it has completed and flushed -- nothing of a

@@ -1210,7 +1210,7 @@ static thread_local int g_raster_cull = 1;                           // 0 disabl
 static thread_local unsigned long long* g_raster_counters = nullptr;  // device uint64[6] -> STATS kernels
 static thread_local int g_px_fwd = 4, g_px_bwd = 4;                   // pixels per lane
 static thread_local int g_raster_packed = 1;                          // f32x2 kernels where they exist (backward, 4 px/lane)
-constexpr int kBwdMinBlocks = 10, kBwdMinBlocksAlt = 8;               // resident CTAs per SM asked of ptxas (96 / 128 registers; 12 = 80 registers was 1 % slower)
+constexpr int kBwdMinBlocks = 10, kBwdMinBlocksAlt = 8;               // resident CTAs per SM asked of ptxas (96 / 102 registers; 12 = 80 registers was 1 % slower)
 static thread_local int g_bwd_minb = kBwdMinBlocks;
 constexpr int kFwdMinBlocks = 12, kFwdMinBlocksAlt = 14;              // forward: 78 / 72 registers (measured at S1: 12 is 1 % faster than 14, 16 = 64 registers 1 % slower)
 static thread_local int g_fwd_minb = kFwdMinBlocks;
@@ -1329,7 +1329,7 @@ extern "C" int qed_debug_set_raster_packed(int enabled) {
     return old;
 }
 
-// occupancy / register trade-off of the packed backward (12 or 10 resident CTAs per SM).  Returns the previous value.
+// occupancy / register trade-off of the packed backward (10 or 8 resident CTAs per SM).  Returns the previous value.
 extern "C" int qed_debug_set_raster_bwd_minb(int minb) {
     int old = g_bwd_minb;
     if (minb == kBwdMinBlocks || minb == kBwdMinBlocksAlt) g_bwd_minb = minb;
