@@ -58,6 +58,25 @@ def test_no_cpu_fallback():
         rasterization(s.means, s.quats, s.scales, s.opacities, s.sh, s.viewmats, s.Ks, 16, 16, sh_degree=3)
 
 
+def test_no_cpu_fallback_on_the_data_side():
+    import numpy as np
+    import torch
+
+    from qed_splatter_b200 import data_side, get_viewmat
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        get_viewmat(torch.eye(4)[None, :3])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        data_side.backproject_frame(torch.ones(8, 8), np.eye(3, dtype=np.float32), np.eye(4, dtype=np.float32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        data_side.voxel_down_sample(torch.zeros(4, 3), 0.1)
+    # pure host helpers need no GPU: the axis flip of create_init_pointcloud.py:59-70 and the merge schedule's error path
+    w2c = data_side.opengl_c2w_to_opencv_w2c(np.eye(4))
+    assert w2c.dtype == np.float32 and np.array_equal(np.diag(w2c), np.float32([1, -1, -1, 1]))
+    with pytest.raises(RuntimeError, match="No valid point clouds"):
+        data_side.merge_pointclouds([])
+
+
 def test_product_never_imports_oracle():
     for f in (ROOT / "qed_splatter_b200").rglob("*.py"):
         text = f.read_text()
