@@ -48,6 +48,34 @@ def tile_grid(width: int, height: int, tile_size: int) -> Tuple[int, int]:
     return math.ceil(width / tile_size), math.ceil(height / tile_size)
 
 
+def ctypes_ptr(addr: Optional[int]):
+    import ctypes
+
+    return None if addr is None else ctypes.c_void_p(addr)
+
+
+def _packed_record_of(v_means2d, v_conics, v_colors, v_opac, C: int, N: int, D: int) -> Optional[int]:
+    """Address of the packed [C*N,12] gradient record if the four tensors are exactly the views
+    `_RasterizeToPixels.backward` returns of one such record (same storage, slots 0:2 / 4:7 / 8:8+D / 7, row stride 12),
+    else None (autograd summed or copied them: they are then ordinary tensors and are passed one by one)."""
+    ts = (v_means2d, v_conics, v_colors, v_opac)
+    if any(t is None or t.dtype != torch.float32 or not t.is_cuda for t in ts):
+        return None
+    base = v_means2d.untyped_storage().data_ptr()
+    if any(t.untyped_storage().data_ptr() != base for t in ts):
+        return None
+    o0 = v_means2d.storage_offset()
+    want = ((v_means2d, (C, N, 2), o0), (v_conics, (C, N, 3), o0 + 4), (v_colors, (C, N, D), o0 + 8), (v_opac, (C, N), o0 + 7))
+    for t, shape, off in want:
+        if tuple(t.shape) != shape or t.storage_offset() != off:
+            return None
+        st = t.stride()
+        if st[0] != N * GRAD_FLOATS or st[1] != GRAD_FLOATS or (len(st) == 3 and shape[2] > 1 and st[2] != 1):
+            return None
+    addr = base + 4 * o0
+    return addr if addr % 16 == 0 else None
+
+
 # --------------------------------------------------------------------------------------------- #
 # (a) fused projection + SH
 # --------------------------------------------------------------------------------------------- #
@@ -116,11 +144,16 @@ class _ProjectGaussians(torch.autograd.Function):
         v_scales = torch.empty_like(scales)
         v_opacities = torch.empty_like(opacities) if opacities is not None else None
         v_colors_in = torch.empty_like(colors) if n_color else None
+        packed = _packed_record_of(v_means2d, v_conics, v_colors, v_opac, C, N, n_color + append_depth)
+        if packed is not None:
+            # the four gradients are the views _RasterizeToPixels.backward made of ONE packed record: the kernel reads it directly
+            separate = (None, ptr(_f32c(v_depths)), None, None, None)
+        else:
+            separate = (ptr(_f32c(v_means2d)), ptr(_f32c(v_depths)), ptr(_f32c(v_conics)), ptr(_f32c(v_colors)), ptr(_f32c(v_opac)))
         check(lib.qed_project_bwd(C, N, ptr(means), ptr(quats), ptr(scales), ptr(opacities), 0, ptr(colors) if n_color else None,
                                   K, sh_degree, per_cam, ptr(viewmats), ptr(Ks), width, height, eps2d, int(calc_comp),
                                   n_color, append_depth, ptr(radii), ptr(conics), ptr(comps),
-                                  ptr(_f32c(v_means2d)), ptr(_f32c(v_depths)), ptr(_f32c(v_conics)), ptr(_f32c(v_colors)),
-                                  ptr(_f32c(v_opac)), None, ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_opacities),
+                                  *separate, ctypes_ptr(packed), ptr(v_means), ptr(v_quats), ptr(v_scales), ptr(v_opacities),
                                   ptr(v_colors_in), current_stream()), "qed_project_bwd")
         return (v_means, v_quats, v_scales, v_opacities, v_colors_in, None, None) + (None,) * 11
 
@@ -366,15 +399,13 @@ class _RasterizeToPixels(torch.autograd.Function):
                                  tile_size, tile_width, tile_height, ptr(isect_offsets), ptr(flatten_ids),
                                  int(normalize_last), ptr(render), ptr(alphas), ptr(last_ids), ptr(v_render),
                                  ptr(_f32c(v_alphas)), ptr(packed), current_stream()), "qed_raster_bwd")
-        v_means2d = torch.empty(C, N, 2, device=dev)
-        v_abs = torch.empty(C, N, 2, device=dev) if absgrad else None
-        v_conics = torch.empty(C, N, 3, device=dev)
-        v_colors = torch.empty(C, N, D, device=dev)
-        v_opac = torch.empty(C, N, device=dev)
-        check(lib.qed_unpack_grads(C * N, D, ptr(packed), ptr(v_means2d), ptr(v_abs), ptr(v_conics), ptr(v_colors),
-                                   ptr(v_opac), current_stream()), "qed_unpack_grads")
+        # the gradients leave as strided VIEWS of the packed [C*N,12] record (no unpack pass, no five allocations);
+        # _ProjectGaussians.backward recognises them and hands the record to the kernel as it is (qed_project_bwd's
+        # `packed_grads`), anything else that consumes them sees ordinary [C,N,k] tensors
+        P = packed.view(C, N, GRAD_FLOATS)
+        v_means2d, v_conics, v_opac, v_colors = P[..., 0:2], P[..., 4:7], P[..., 7], P[..., 8:8 + D]
         if absgrad:
-            means2d.absgrad = v_abs  # side channel read by gsplat's DefaultStrategy (model.py:284 absgrad=True)
+            means2d.absgrad = P[..., 2:4]  # side channel read by gsplat's DefaultStrategy (model.py:284 absgrad=True)
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[4]:
             g = v_render
