@@ -608,8 +608,9 @@ def main_ours(args):
             for p_ in params:
                 grad_views.append(grad_bucket[o_:o_ + p_.numel()].view_as(p_))
                 o_ += p_.numel()
-        # the step's inputs come from pinned host memory on a copy stream (what a data loader does); the loss
-        # waits on the copy event, so the H2D of the ground truth overlaps projection/sort/compositing
+        # the step's inputs come from pinned host memory on a copy stream (what a data loader does): the camera first (the
+        # render needs it), the ground truth once the render is launched; the loss waits on the copy event, so the H2D of the
+        # ground truth overlaps projection/sort/compositing
         copy_stream = torch.cuda.Stream()
         vm_d, K_d = torch.empty_like(viewmats), torch.empty_like(Ks)
         # ground-truth RGB travels as the reference's data side holds it: the uint8 image cache (config.py:37
@@ -624,9 +625,6 @@ def main_ours(args):
                 vm_d.copy_(vm_h, non_blocking=True)
                 K_d.copy_(K_h, non_blocking=True)
                 cam_ready.record(copy_stream)
-                rgb_d.copy_(e2e_rgb_h, non_blocking=True)
-                depth_d.copy_(gt_depth_h, non_blocking=True)
-                gt_ready.record(copy_stream)
             torch.cuda.current_stream().wait_event(cam_ready)
             vm, Kc, rgb_gt, d_gt = vm_d, K_d, rgb_d, depth_d
             if grad_bucket is None:
@@ -640,6 +638,12 @@ def main_ours(args):
                                                 tile_size=16, packed=False, near_plane=0.01, far_plane=1e10, render_mode=args.mode,
                                                 sh_degree=3, sparse_grad=False, absgrad=True, rasterize_mode="classic")
             info["means2d"].retain_grad()
+            # the ground truth is only needed by the loss: its copies are queued (copy stream) once the render is launched and
+            # run under the projection / intersection / compositing kernels
+            with torch.cuda.stream(copy_stream):
+                rgb_d.copy_(e2e_rgb_h, non_blocking=True)
+                depth_d.copy_(gt_depth_h, non_blocking=True)
+                gt_ready.record(copy_stream)
             torch.cuda.current_stream().wait_event(gt_ready)
             if reference_lines:
                 rgb_gt = rgb_gt.float() / 255.0 if rgb_gt.dtype == torch.uint8 else rgb_gt  # splatfacto get_gt_img
