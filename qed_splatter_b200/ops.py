@@ -59,7 +59,7 @@ def _packed_record_of(v_means2d, v_conics, v_colors, v_opac, C: int, N: int, D: 
     `_RasterizeToPixels.backward` returns of one such record (same storage, slots 0:2 / 4:7 / 8:8+D / 7, row stride 12),
     else None (autograd summed or copied them: they are then ordinary tensors and are passed one by one)."""
     ts = (v_means2d, v_conics, v_colors, v_opac)
-    if any(t is None or t.dtype != torch.float32 or not t.is_cuda for t in ts):
+    if any(t is None or t.dtype != torch.float32 for t in ts):
         return None
     base = v_means2d.untyped_storage().data_ptr()
     if any(t.untyped_storage().data_ptr() != base for t in ts):
